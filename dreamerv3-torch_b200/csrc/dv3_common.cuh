@@ -1,0 +1,150 @@
+// Shared device helpers + host-side error plumbing for libdv3_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <math.h>
+#include "../../include/dv3_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libdv3_b200 targets sm_100a (B200) only"
+#endif
+
+namespace dv3 {
+
+// ---- host error state -------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define DV3_CHECK_CUDA(expr)                                   \
+  do {                                                         \
+    cudaError_t _e = (expr);                                   \
+    if (_e != cudaSuccess) return ::dv3::cuda_fail(_e, #expr); \
+  } while (0)
+
+#define DV3_CHECK_LAUNCH(name)                                   \
+  do {                                                           \
+    cudaError_t _e = cudaGetLastError();                         \
+    if (_e != cudaSuccess) return ::dv3::cuda_fail(_e, name);    \
+  } while (0)
+
+#define DV3_REQUIRE(cond, code, ...)   \
+  do {                                 \
+    if (!(cond)) {                     \
+      ::dv3::set_error(__VA_ARGS__);   \
+      return (code);                   \
+    }                                  \
+  } while (0)
+
+#define DV3_TRY(expr)            \
+  do {                           \
+    int _rc = (expr);            \
+    if (_rc != 0) return _rc;    \
+  } while (0)
+
+// ---- device helpers ----------------------------------------------------------------------
+constexpr int WARP = 32;
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, o));
+  return v;
+}
+
+// Block-wide sum of up to 4 values at once; every thread gets the totals.  `red` is a
+// shared array of at least 4*32 floats.  Ends with a barrier, so `red` is reusable.
+template <int NV>
+__device__ __forceinline__ void block_sum(float (&v)[NV], float* red) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) red[i * 32 + wid] = v[i];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    float t = (lane < nw) ? red[i * 32 + lane] : 0.f;
+    v[i] = warp_sum(t);
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+__device__ __forceinline__ float siluf_(float x) { return x * sigmoidf_(x); }
+// d/dx [x*sigmoid(x)]
+__device__ __forceinline__ float silu_grad(float x) {
+  const float s = sigmoidf_(x);
+  return s * (1.f + x * (1.f - s));
+}
+
+// ---- internal host launchers (definitions spread over the .cu files) ----------------------
+struct LinearArgs {
+  const float* A[2];
+  const float* W[2];
+  int lda[2], ldw[2], K[2];
+  const float* bias;
+  const float* addend;
+  int ldadd;
+  float* C;
+  int ldc, M, N, accumulate;
+};
+int launch_linear(const LinearArgs& g, cudaStream_t st);
+int linear1(const float* A, int lda, const float* W, int ldw, int K, const float* bias, float* C,
+            int ldc, int M, int N, int accumulate, cudaStream_t st);
+int launch_transpose(const float* in, int ld, int R, int C, float* out, cudaStream_t st);
+
+// Row-wise kernels.  Every matrix argument is (pointer, row stride) so that batch-major
+// [B,T,w] tensors can be addressed per time step as (base + t*w, T*w).
+int ln_silu_fwd(const float* pre, int ld, const float* g, const float* b, float eps, int M, int n,
+                float* out, int ldo, cudaStream_t st);
+int ln_silu_bwd(const float* pre, int ld, const float* g, const float* b, float eps,
+                const float* d_out, int ldd, int M, int n, float* d_pre, int ldp, float* d_ln,
+                int ldl, cudaStream_t st);
+// x_pre = addend + sum_g WT[g*C+idx[g]] + sum_a act[a]*WT[S*C+a];  x = SiLU(LN(x_pre))
+int gather_ln_silu(const int32_t* idx, int ldi, int S, int C, const float* act, int lda, int A,
+                   const float* WT, const float* addend, int ldadd, const float* g, const float* b,
+                   float eps, int M, int n, float* pre, int ldp, float* out, int ldo,
+                   cudaStream_t st);
+int gru_gates_fwd(const float* g_pre, int ldg, const float* g, const float* b, float eps,
+                  const float* h, int ldh, int M, int D, float* h_new, int ldn, cudaStream_t st);
+// dh_in: up to 4 addends (NULL = skip), each with its own row stride
+int gru_gates_bwd(const float* g_pre, int ldg, const float* g, const float* b, float eps,
+                  const float* h, int ldh, const float* const dh_in[4], const int ld_in[4], int M,
+                  int D, float* d_g_pre, int ldp, float* d_g_ln, int ldl, float* dh_direct,
+                  int ldd, cudaStream_t st);
+// u row r is read at row perm(r) = (r % permT) * permB + r / permT when permT > 0
+int onehot_sample(const float* logits, int ldl, const float* u, int ldu, int permT, int permB,
+                  float unimix, int M, int S, int C, int32_t* idx, int ldi, float* onehot, int ldo,
+                  cudaStream_t st);
+int onehot_st_bwd(const float* logits, int ldl, const float* g1, int ldg1, const float* g2,
+                  int ldg2, const float* ext, int lde, float unimix, int M, int S, int C,
+                  float* d_logits, int ldd, cudaStream_t st);
+int idx_to_onehot(const int32_t* idx, int ldi, int M, int S, int C, float* out, int ld,
+                  cudaStream_t st);
+int copy_rows(const float* in, int ldi, int M, int n, float* out, int ldo, cudaStream_t st);
+int copy_rows_i32(const int32_t* in, int ldi, int M, int n, int32_t* out, int ldo, cudaStream_t st);
+int tanh_vec(const float* in, int n, float* out, cudaStream_t st);
+int fill_zero(void* p, size_t bytes, cudaStream_t st);
+
+// bump allocator over the caller's workspace
+struct Arena {
+  char* base; size_t size, used;
+  Arena(void* p, size_t n) : base(static_cast<char*>(p)), size(n), used(0) {}
+  template <typename T> T* take(size_t count) {
+    size_t bytes = (count * sizeof(T) + 255) & ~size_t(255);
+    T* r = base ? reinterpret_cast<T*>(base + used) : nullptr;
+    used += bytes;
+    return r;
+  }
+  bool ok() const { return used <= size; }
+};
+
+}  // namespace dv3

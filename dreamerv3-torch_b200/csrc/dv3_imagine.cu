@@ -1,0 +1,347 @@
+// ImagBehavior._imagine: H-step actor-in-the-loop prior rollout from N start states, and its
+// backward ('dynamics' gradient: BPTT through img_step w.r.t. activations).
+//
+// Per step k:  feat_k = [one-hot stoch_k | deter_k] (detached for the actor, models.py:514)
+//              a_k    = actor(feat_k).sample()       (networks.py:657-700, tools.py:594-598)
+//              state_{k+1} = img_step(state_k, a_k)  (networks.py:208-233)
+// The successor of the last step is never returned by the reference (models.py:546), so its
+// img_step is not computed here.
+// One-hot inputs: both Linear layers that consume `stoch` (W_in and the first actor layer) are
+// evaluated as a gather-sum of S rows of the transposed weight plus a dense product over the
+// remaining (action / deter) columns -- 2*S*C*width flops per row become S*width adds.
+#include "dv3_common.cuh"
+
+namespace dv3 {
+
+__global__ void actor_normal_sample_kernel(const float* __restrict__ mean_raw,
+                                           const float* __restrict__ std_raw,
+                                           const float* __restrict__ eps, float min_std,
+                                           float max_std, long long total,
+                                           float* __restrict__ action) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const float mean = tanhf(mean_raw[i]);
+  const float std = (max_std - min_std) * sigmoidf_(std_raw[i] + 2.f) + min_std;
+  const float out = mean + std * eps[i];
+  action[i] = out * (1.f / fmaxf(fabsf(out), 1.f));
+}
+
+// g1 + g2 = gradient reaching the returned action; the clip factor is a constant (detached)
+__global__ void actor_normal_sample_bwd_kernel(const float* __restrict__ mean_raw,
+                                               const float* __restrict__ std_raw,
+                                               const float* __restrict__ eps,
+                                               const float* __restrict__ g1, int ld1, int c1,
+                                               const float* __restrict__ g2, float min_std,
+                                               float max_std, int N, int A,
+                                               float* __restrict__ d_mean_raw,
+                                               float* __restrict__ d_std_raw) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)N * A) return;
+  const int r = (int)(i / A), a = (int)(i % A);
+  float g = 0.f;
+  if (g1) g += g1[(size_t)r * ld1 + c1 + a];
+  if (g2) g += g2[i];
+  const float mean = tanhf(mean_raw[i]);
+  const float sg = sigmoidf_(std_raw[i] + 2.f);
+  const float std = (max_std - min_std) * sg + min_std;
+  const float out = mean + std * eps[i];
+  const float dout = g * (1.f / fmaxf(fabsf(out), 1.f));
+  d_mean_raw[i] = dout * (1.f - mean * mean);
+  d_std_raw[i] = dout * eps[i] * (max_std - min_std) * sg * (1.f - sg);
+}
+
+struct ImgFwdWs {
+  float* WinT;   // [(SC+A), Hd]
+  float* Wa0T;   // [F, U]
+  float* a_add;  // [N, U]
+};
+
+static void carve_img_fwd(Arena& a, const dv3_rssm_dims* d, const dv3_actor* act, int N,
+                          ImgFwdWs& w) {
+  const size_t SC = (size_t)d->stoch * d->classes;
+  w.WinT = a.take<float>((SC + d->actions) * d->hidden);
+  if (act) {
+    w.Wa0T = a.take<float>((SC + d->deter) * act->units);
+    w.a_add = a.take<float>((size_t)N * act->units);
+  } else {
+    w.Wa0T = w.a_add = nullptr;
+  }
+}
+
+static int check_actor(const dv3_rssm_dims* d, const dv3_actor* a, const char* who) {
+  if (!a) return 0;
+  DV3_REQUIRE(a->layers >= 1 && a->layers <= 16 && a->units >= 4 && a->units % 4 == 0,
+              DV3_ERR_BAD_SHAPE, "%s: actor layers=%d units=%d", who, a->layers, a->units);
+  DV3_REQUIRE(a->dist == 0 || a->dist == 1, DV3_ERR_BAD_SHAPE, "%s: actor dist=%d", who, a->dist);
+  DV3_REQUIRE(a->dist == 0 || d->actions <= 32, DV3_ERR_BAD_SHAPE,
+              "%s: onehot actor with %d > 32 actions", who, d->actions);
+  DV3_REQUIRE(a->w && a->ln_g && a->ln_b && a->w_mean && a->b_mean, DV3_ERR_NULL,
+              "%s: null actor parameter", who);
+  DV3_REQUIRE(a->dist == 1 || (a->w_std && a->b_std), DV3_ERR_NULL, "%s: null actor std layer",
+              who);
+  return 0;
+}
+
+static int check_rssm_dims(const dv3_rssm_dims* d, const char* who) {
+  DV3_REQUIRE(d, DV3_ERR_NULL, "%s: dims is NULL", who);
+  DV3_REQUIRE(d->stoch >= 1 && d->classes >= 1 && d->classes <= 32 && d->deter % 4 == 0 &&
+                  d->hidden % 4 == 0 && d->deter >= 4 && d->hidden >= 4 && d->actions >= 1,
+              DV3_ERR_BAD_SHAPE, "%s: unsupported dims S=%d C=%d D=%d Hd=%d A=%d", who, d->stoch,
+              d->classes, d->deter, d->hidden, d->actions);
+  return 0;
+}
+
+}  // namespace dv3
+
+using namespace dv3;
+
+extern "C" size_t dv3_imagine_workspace_bytes(const dv3_rssm_dims* d, const dv3_actor* a, int32_t N,
+                                              int32_t H) {
+  if (!d || N <= 0 || H <= 0) return 0;
+  Arena ar(nullptr, 0);
+  ImgFwdWs w;
+  carve_img_fwd(ar, d, a, N, w);
+  return ar.used;
+}
+
+extern "C" int dv3_imagine_fwd(const dv3_rssm_dims* d, const dv3_rssm_params* p, const dv3_actor* a,
+                               const dv3_imagine_io* io, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DV3_TRY(check_rssm_dims(d, "imagine_fwd"));
+  DV3_TRY(check_actor(d, a, "imagine_fwd"));
+  DV3_REQUIRE(p && io, DV3_ERR_NULL, "imagine_fwd: params/io is NULL");
+  const int N = io->N, H = io->H;
+  DV3_REQUIRE(N >= 0 && H >= 0, DV3_ERR_BAD_SHAPE, "imagine_fwd: N=%d H=%d", N, H);
+  if (N == 0 || H == 0) return 0;
+  const int S = d->stoch, C = d->classes, SC = S * C, D = d->deter, Hd = d->hidden, A = d->actions,
+            F = SC + D;
+  DV3_REQUIRE(io->start_idx && io->start_deter && io->u_state, DV3_ERR_NULL,
+              "imagine_fwd: null input");
+  DV3_REQUIRE(a ? io->act_noise != nullptr : io->given_action != nullptr, DV3_ERR_NULL,
+              "imagine_fwd: need act_noise (actor) or given_action (no actor)");
+  DV3_REQUIRE(io->feat && io->logit && io->action && io->idx && io->x_pre && io->x && io->g_pre &&
+                  io->y_pre && io->y,
+              DV3_ERR_NULL, "imagine_fwd: null output");
+  DV3_REQUIRE(!a || (io->a_pre && io->a_act && io->a_mean_raw && (a->dist == 1 || io->a_std_raw)),
+              DV3_ERR_NULL, "imagine_fwd: null actor activation buffer");
+  Arena arena(io->workspace, io->workspace_bytes);
+  ImgFwdWs w;
+  carve_img_fwd(arena, d, a, N, w);
+  DV3_REQUIRE(io->workspace && arena.ok(), DV3_ERR_WORKSPACE,
+              "imagine_fwd: workspace %zu < %zu bytes", io->workspace_bytes, arena.used);
+  const int U = a ? a->units : 0, L = a ? a->layers : 0;
+
+  DV3_TRY(launch_transpose(p->w_in, SC + A, Hd, SC + A, w.WinT, st));
+  if (a) DV3_TRY(launch_transpose(a->w[0], F, U, F, w.Wa0T, st));
+  // state 0
+  DV3_TRY(copy_rows_i32(io->start_idx, S, N, S, io->idx, S, st));
+  DV3_TRY(idx_to_onehot(io->start_idx, S, N, S, C, io->feat, F, st));
+  DV3_TRY(copy_rows(io->start_deter, D, N, D, io->feat + SC, F, st));
+
+  for (int k = 0; k < H; ++k) {
+    float* featk = io->feat + (size_t)k * N * F;
+    const int32_t* idxk = io->idx + (size_t)k * N * S;
+    float* actk = io->action + (size_t)k * N * A;
+    if (a) {
+      const size_t lstride = (size_t)H * N * U;
+      float* pre0 = io->a_pre + (size_t)k * N * U;
+      float* act0 = io->a_act + (size_t)k * N * U;
+      // layer 0: deter columns dense, stoch columns gathered
+      DV3_TRY(linear1(featk + SC, F, a->w[0] + SC, F, D, nullptr, w.a_add, U, N, U, 0, st));
+      DV3_TRY(gather_ln_silu(idxk, S, S, C, nullptr, 0, 0, w.Wa0T, w.a_add, U, a->ln_g[0],
+                             a->ln_b[0], d->ln_eps, N, U, pre0, U, act0, U, st));
+      for (int i = 1; i < L; ++i) {
+        float* prei = io->a_pre + i * lstride + (size_t)k * N * U;
+        float* acti = io->a_act + i * lstride + (size_t)k * N * U;
+        const float* prev = io->a_act + (i - 1) * lstride + (size_t)k * N * U;
+        DV3_TRY(linear1(prev, U, a->w[i], U, U, nullptr, prei, U, N, U, 0, st));
+        DV3_TRY(ln_silu_fwd(prei, U, a->ln_g[i], a->ln_b[i], d->ln_eps, N, U, acti, U, st));
+      }
+      const float* top = io->a_act + (L - 1) * lstride + (size_t)k * N * U;
+      float* mraw = io->a_mean_raw + (size_t)k * N * A;
+      DV3_TRY(linear1(top, U, a->w_mean, U, U, a->b_mean, mraw, A, N, A, 0, st));
+      if (a->dist == 0) {
+        float* sraw = io->a_std_raw + (size_t)k * N * A;
+        DV3_TRY(linear1(top, U, a->w_std, U, U, a->b_std, sraw, A, N, A, 0, st));
+        const long long tot = (long long)N * A;
+        actor_normal_sample_kernel<<<(int)((tot + 255) / 256), 256, 0, st>>>(
+            mraw, sraw, io->act_noise + (size_t)k * N * A, a->min_std, a->max_std, tot, actk);
+        DV3_CHECK_LAUNCH("actor_normal_sample_kernel");
+      } else {
+        DV3_TRY(onehot_sample(mraw, A, io->act_noise + (size_t)k * N * A, A, 0, 0, a->unimix, N, 1,
+                              A, nullptr, 0, actk, A, st));
+      }
+    } else if (k < H - 1) {
+      DV3_TRY(copy_rows(io->given_action + (size_t)k * N * A, A, N, A, actk, A, st));
+    } else {
+      DV3_TRY(fill_zero(actk, (size_t)N * A * 4, st));
+    }
+    if (k == H - 1) break;
+
+    float* featn = io->feat + (size_t)(k + 1) * N * F;
+    float* xpre = io->x_pre + (size_t)k * N * Hd;
+    float* xk = io->x + (size_t)k * N * Hd;
+    float* gpre = io->g_pre + (size_t)k * N * 3 * D;
+    float* ypre = io->y_pre + (size_t)k * N * Hd;
+    float* yk = io->y + (size_t)k * N * Hd;
+    float* logn = io->logit + (size_t)(k + 1) * N * SC;
+    DV3_TRY(gather_ln_silu(idxk, S, S, C, actk, A, A, w.WinT, nullptr, 0, p->ln_in_g, p->ln_in_b,
+                           d->ln_eps, N, Hd, xpre, Hd, xk, Hd, st));
+    LinearArgs g{};
+    g.A[0] = xk; g.lda[0] = Hd; g.W[0] = p->w_gru; g.ldw[0] = Hd + D; g.K[0] = Hd;
+    g.A[1] = featk + SC; g.lda[1] = F; g.W[1] = p->w_gru + Hd; g.ldw[1] = Hd + D; g.K[1] = D;
+    g.C = gpre; g.ldc = 3 * D; g.M = N; g.N = 3 * D;
+    DV3_TRY(launch_linear(g, st));
+    DV3_TRY(gru_gates_fwd(gpre, 3 * D, p->ln_gru_g, p->ln_gru_b, d->ln_eps, featk + SC, F, N, D,
+                          featn + SC, F, st));
+    DV3_TRY(linear1(featn + SC, F, p->w_out, D, D, nullptr, ypre, Hd, N, Hd, 0, st));
+    DV3_TRY(ln_silu_fwd(ypre, Hd, p->ln_out_g, p->ln_out_b, d->ln_eps, N, Hd, yk, Hd, st));
+    DV3_TRY(linear1(yk, Hd, p->w_ims, Hd, Hd, p->b_ims, logn, SC, N, SC, 0, st));
+    DV3_TRY(onehot_sample(logn, SC, io->u_state + (size_t)k * N * SC, SC, 0, 0, d->unimix, N, S, C,
+                          io->idx + (size_t)(k + 1) * N * S, S, featn, F, st));
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------
+namespace dv3 {
+
+struct ImgBwdWs {
+  float *WimsT, *WoutT, *WgruT, *WinT;
+  float *d_y, *dh_y, *dxh, *dxh_add, *dsa;
+};
+
+static void carve_img_bwd(Arena& a, const dv3_rssm_dims* d, int N, ImgBwdWs& w) {
+  const size_t SC = (size_t)d->stoch * d->classes, D = d->deter, Hd = d->hidden, A = d->actions;
+  // W_in^T is padded to a multiple of 4 columns... the product d_x_pre @ W_in has N = SC+A
+  w.WimsT = a.take<float>(Hd * SC);
+  w.WoutT = a.take<float>(D * Hd);
+  w.WgruT = a.take<float>((Hd + D) * 3 * D);
+  w.WinT = a.take<float>((SC + A) * Hd);
+  w.d_y = a.take<float>((size_t)N * Hd);
+  w.dh_y = a.take<float>((size_t)N * D);
+  w.dxh = a.take<float>((size_t)N * (Hd + D));
+  w.dxh_add = a.take<float>((size_t)N * (Hd + D));
+  w.dsa = a.take<float>((size_t)N * (SC + A));
+}
+
+__global__ void add2_rows_kernel(const float* __restrict__ a, int lda, const float* __restrict__ b,
+                                 int ldb, int M, int n, float* __restrict__ out, int ldo) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)M * n) return;
+  const int r = (int)(i / n), c = (int)(i % n);
+  float v = 0.f;
+  if (a) v += a[(size_t)r * lda + c];
+  if (b) v += b[(size_t)r * ldb + c];
+  out[(size_t)r * ldo + c] = v;
+}
+
+}  // namespace dv3
+
+extern "C" size_t dv3_imagine_bwd_workspace_bytes(const dv3_rssm_dims* d, const dv3_actor* a,
+                                                  int32_t N, int32_t H) {
+  (void)a;
+  if (!d || N <= 0 || H <= 0) return 0;
+  Arena ar(nullptr, 0);
+  ImgBwdWs w;
+  carve_img_bwd(ar, d, N, w);
+  return ar.used;
+}
+
+extern "C" int dv3_imagine_bwd(const dv3_rssm_dims* d, const dv3_rssm_params* p, const dv3_actor* a,
+                               const dv3_imagine_bwd_io* io, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DV3_TRY(check_rssm_dims(d, "imagine_bwd"));
+  DV3_TRY(check_actor(d, a, "imagine_bwd"));
+  DV3_REQUIRE(p && io, DV3_ERR_NULL, "imagine_bwd: params/io is NULL");
+  const int N = io->N, H = io->H;
+  DV3_REQUIRE(N >= 0 && H >= 0, DV3_ERR_BAD_SHAPE, "imagine_bwd: N=%d H=%d", N, H);
+  if (N == 0 || H == 0) return 0;
+  const int S = d->stoch, C = d->classes, SC = S * C, D = d->deter, Hd = d->hidden, A = d->actions,
+            F = SC + D;
+  DV3_REQUIRE(io->logit && io->feat && io->x_pre && io->g_pre && io->y_pre, DV3_ERR_NULL,
+              "imagine_bwd: null saved tensor");
+  DV3_REQUIRE(!a || (io->a_mean_raw && io->act_noise && io->d_mean_raw &&
+                     (a->dist == 1 || (io->a_std_raw && io->d_std_raw))),
+              DV3_ERR_NULL, "imagine_bwd: null actor tensor");
+  DV3_REQUIRE(io->d_x_pre && io->d_x_ln && io->d_g_pre && io->d_g_ln && io->d_y_pre &&
+                  io->d_y_ln && io->d_logit,
+              DV3_ERR_NULL, "imagine_bwd: null output");
+  Arena arena(io->workspace, io->workspace_bytes);
+  ImgBwdWs w;
+  carve_img_bwd(arena, d, N, w);
+  DV3_REQUIRE(io->workspace && arena.ok(), DV3_ERR_WORKSPACE,
+              "imagine_bwd: workspace %zu < %zu bytes", io->workspace_bytes, arena.used);
+
+  DV3_TRY(launch_transpose(p->w_ims, Hd, SC, Hd, w.WimsT, st));
+  DV3_TRY(launch_transpose(p->w_out, D, Hd, D, w.WoutT, st));
+  DV3_TRY(launch_transpose(p->w_gru, Hd + D, 3 * D, Hd + D, w.WgruT, st));
+  DV3_TRY(launch_transpose(p->w_in, SC + A, Hd, SC + A, w.WinT, st));
+  DV3_TRY(fill_zero(w.dxh_add, (size_t)N * (Hd + D) * 4, st));
+
+  auto actor_bwd = [&](int k, const float* d_a, int ld, int col) -> int {
+    if (!a) return 0;
+    const size_t o = (size_t)k * N * A;
+    const float* gact = io->g_action ? io->g_action + o : nullptr;
+    if (a->dist == 0) {
+      const long long tot = (long long)N * A;
+      actor_normal_sample_bwd_kernel<<<(int)((tot + 255) / 256), 256, 0, st>>>(
+          io->a_mean_raw + o, io->a_std_raw + o, io->act_noise + o, d_a, ld, col, gact, a->min_std,
+          a->max_std, N, A, io->d_mean_raw + o, io->d_std_raw + o);
+      DV3_CHECK_LAUNCH("actor_normal_sample_bwd_kernel");
+      return 0;
+    }
+    return onehot_st_bwd(io->a_mean_raw + o, A, d_a ? d_a + col : nullptr, ld, gact, A, nullptr, 0,
+                         a->unimix, N, 1, A, io->d_mean_raw + o, A, st);
+  };
+
+  // the last action feeds nothing downstream
+  DV3_TRY(actor_bwd(H - 1, nullptr, 0, 0));
+
+  const float* ds_rec = nullptr;  // [N, SC+A] view into dsa once it is valid
+  const float* dh_rec = nullptr;  // h columns of dxh
+  for (int k = H - 2; k >= 0; --k) {
+    const size_t on = (size_t)(k + 1) * N;  // row offset of state k+1
+    const float* gs = io->g_stoch ? io->g_stoch + on * SC : nullptr;
+    const float* gl = io->g_logit ? io->g_logit + on * SC : nullptr;
+    float* dlog = io->d_logit + on * SC;
+    DV3_TRY(onehot_st_bwd(io->logit + on * SC, SC, gs, SC, ds_rec, SC + A, gl, SC, d->unimix, N, S,
+                          C, dlog, SC, st));
+    DV3_TRY(linear1(dlog, SC, w.WimsT, SC, SC, nullptr, w.d_y, Hd, N, Hd, 0, st));
+    const size_t ok = (size_t)k * N;
+    DV3_TRY(ln_silu_bwd(io->y_pre + ok * Hd, Hd, p->ln_out_g, p->ln_out_b, d->ln_eps, w.d_y, Hd, N,
+                        Hd, io->d_y_pre + ok * Hd, Hd, io->d_y_ln + ok * Hd, Hd, st));
+    DV3_TRY(linear1(io->d_y_pre + ok * Hd, Hd, w.WoutT, Hd, Hd, nullptr, w.dh_y, D, N, D, 0, st));
+    const float* dh_in[4] = {w.dh_y, io->g_deter ? io->g_deter + on * D : nullptr, dh_rec, nullptr};
+    const int ld_in[4] = {D, D, Hd + D, 0};
+    DV3_TRY(gru_gates_bwd(io->g_pre + ok * 3 * D, 3 * D, p->ln_gru_g, p->ln_gru_b, d->ln_eps,
+                          io->feat + ok * F + SC, F, dh_in, ld_in, N, D, io->d_g_pre + ok * 3 * D,
+                          3 * D, io->d_g_ln + ok * 3 * D, 3 * D, w.dxh_add + Hd, Hd + D, st));
+    LinearArgs g{};
+    g.A[0] = io->d_g_pre + ok * 3 * D; g.lda[0] = 3 * D; g.W[0] = w.WgruT; g.ldw[0] = 3 * D;
+    g.K[0] = 3 * D; g.addend = w.dxh_add; g.ldadd = Hd + D; g.C = w.dxh; g.ldc = Hd + D; g.M = N;
+    g.N = Hd + D;
+    DV3_TRY(launch_linear(g, st));
+    dh_rec = w.dxh + Hd;
+    DV3_TRY(ln_silu_bwd(io->x_pre + ok * Hd, Hd, p->ln_in_g, p->ln_in_b, d->ln_eps, w.dxh, Hd + D,
+                        N, Hd, io->d_x_pre + ok * Hd, Hd, io->d_x_ln + ok * Hd, Hd, st));
+    // [d stoch_k | d action_k] = d_x_pre @ W_in
+    DV3_TRY(linear1(io->d_x_pre + ok * Hd, Hd, w.WinT, Hd, Hd, nullptr, w.dsa, SC + A, N, SC + A, 0,
+                    st));
+    ds_rec = w.dsa;
+    DV3_TRY(actor_bwd(k, w.dsa, SC + A, SC));
+  }
+  if (io->d_start_stoch) {
+    add2_rows_kernel<<<(int)(((long long)N * SC + 255) / 256), 256, 0, st>>>(
+        io->g_stoch, SC, ds_rec, SC + A, N, SC, io->d_start_stoch, SC);
+    DV3_CHECK_LAUNCH("add2_rows_kernel");
+  }
+  if (io->d_start_deter) {
+    add2_rows_kernel<<<(int)(((long long)N * D + 255) / 256), 256, 0, st>>>(
+        io->g_deter, D, dh_rec, Hd + D, N, D, io->d_start_deter, D);
+    DV3_CHECK_LAUNCH("add2_rows_kernel");
+  }
+  return 0;
+}

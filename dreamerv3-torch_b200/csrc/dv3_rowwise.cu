@@ -1,0 +1,519 @@
+// Row-wise kernels of the RSSM step: LayerNorm+SiLU, the LayerNorm-GRU gate block, the one-hot
+// gather that replaces "one_hot(stoch) @ W", and the unimix categorical draw with its
+// straight-through backward.  One CTA per row (LayerNorm needs the whole row), one warp per
+// categorical group (C <= 32 classes: one class per lane, reductions are shuffles).
+//
+// Reference semantics (paths relative to the reference tree):
+//   Linear->LayerNorm(eps 1e-3)->SiLU blocks      networks.py:48-78, 623-632
+//   GRUCell.forward                                networks.py:760-768
+//   OneHotDist.__init__/sample/mode                tools.py:436-460 (+ torch Categorical)
+#include "dv3_common.cuh"
+
+namespace dv3 {
+
+constexpr int ROW_THREADS = 256;
+
+// mean and 1/sqrt(var+eps) of a row (two-pass, biased variance, like ATen's layer_norm)
+__device__ __forceinline__ void row_stats(const float* __restrict__ row, int n, float eps,
+                                          float* red, float& mean, float& rstd) {
+  float s[1] = {0.f};
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s[0] += row[i];
+  block_sum<1>(s, red);
+  mean = s[0] / (float)n;
+  float v[1] = {0.f};
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float d = row[i] - mean;
+    v[0] = fmaf(d, d, v[0]);
+  }
+  block_sum<1>(v, red);
+  rstd = 1.f / sqrtf(v[0] / (float)n + eps);
+}
+
+// ------------------------------------------------------------------------------------------
+// SiLU(LayerNorm(pre))
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ROW_THREADS)
+ln_silu_fwd_kernel(const float* __restrict__ pre, int ld, const float* __restrict__ g,
+                   const float* __restrict__ b, float eps, int n, float* __restrict__ out,
+                   int ldo) {
+  __shared__ float red[4 * 32];
+  const float* row = pre + (size_t)blockIdx.x * ld;
+  float mean, rstd;
+  row_stats(row, n, eps, red, mean, rstd);
+  float* o = out + (size_t)blockIdx.x * ldo;
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    o[i] = siluf_(fmaf((row[i] - mean) * rstd, g[i], b[i]));
+}
+
+int ln_silu_fwd(const float* pre, int ld, const float* g, const float* b, float eps, int M, int n,
+                float* out, int ldo, cudaStream_t st) {
+  if (M <= 0) return 0;
+  ln_silu_fwd_kernel<<<M, ROW_THREADS, 0, st>>>(pre, ld, g, b, eps, n, out, ldo);
+  DV3_CHECK_LAUNCH("ln_silu_fwd_kernel");
+  return 0;
+}
+
+// d_ln  = d_out * silu'(v)                 (gradient w.r.t. the LayerNorm affine output v)
+// d_pre = rstd * (dx - mean(dx) - xhat * mean(dx*xhat)),  dx = d_ln * gamma
+__global__ void __launch_bounds__(ROW_THREADS)
+ln_silu_bwd_kernel(const float* __restrict__ pre, int ld, const float* __restrict__ g,
+                   const float* __restrict__ b, float eps, const float* __restrict__ d_out,
+                   int ldd, int n, float* __restrict__ d_pre, int ldp, float* __restrict__ d_ln,
+                   int ldl) {
+  __shared__ float red[4 * 32];
+  const float* row = pre + (size_t)blockIdx.x * ld;
+  const float* dor = d_out + (size_t)blockIdx.x * ldd;
+  float mean, rstd;
+  row_stats(row, n, eps, red, mean, rstd);
+  float acc[2] = {0.f, 0.f};
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float xh = (row[i] - mean) * rstd;
+    const float v = fmaf(xh, g[i], b[i]);
+    const float dv = dor[i] * silu_grad(v);
+    const float dx = dv * g[i];
+    acc[0] += dx;
+    acc[1] = fmaf(dx, xh, acc[1]);
+    if (d_ln) d_ln[(size_t)blockIdx.x * ldl + i] = dv;
+  }
+  block_sum<2>(acc, red);
+  const float m1 = acc[0] / (float)n, m2 = acc[1] / (float)n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float xh = (row[i] - mean) * rstd;
+    const float v = fmaf(xh, g[i], b[i]);
+    const float dx = dor[i] * silu_grad(v) * g[i];
+    d_pre[(size_t)blockIdx.x * ldp + i] = rstd * (dx - m1 - xh * m2);
+  }
+}
+
+int ln_silu_bwd(const float* pre, int ld, const float* g, const float* b, float eps,
+                const float* d_out, int ldd, int M, int n, float* d_pre, int ldp, float* d_ln,
+                int ldl, cudaStream_t st) {
+  if (M <= 0) return 0;
+  ln_silu_bwd_kernel<<<M, ROW_THREADS, 0, st>>>(pre, ld, g, b, eps, d_out, ldd, n, d_pre, ldp,
+                                                d_ln, ldl);
+  DV3_CHECK_LAUNCH("ln_silu_bwd_kernel");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// one-hot "Linear": the stoch input is one-hot per group, so  W [s, a]  is a sum of S rows of
+// W^T plus a tiny dense part for the action.  Fused with LayerNorm+SiLU.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ROW_THREADS)
+gather_ln_silu_kernel(const int32_t* __restrict__ idx, int ldi, int S, int C,
+                      const float* __restrict__ act, int lda, int A, const float* __restrict__ WT,
+                      const float* __restrict__ addend, int ldadd, const float* __restrict__ g,
+                      const float* __restrict__ b, float eps, int n, float* __restrict__ pre,
+                      int ldp, float* __restrict__ out, int ldo) {
+  extern __shared__ float sm[];
+  float* rowbuf = sm;                                   // n
+  float* red = sm + n;                                  // 128
+  int* sidx = reinterpret_cast<int*>(red + 4 * 32);     // S
+  float* sact = reinterpret_cast<float*>(sidx + S);     // A
+  const int r = blockIdx.x;
+  for (int i = threadIdx.x; i < S; i += blockDim.x) sidx[i] = idx[(size_t)r * ldi + i] + i * C;
+  for (int i = threadIdx.x; i < A; i += blockDim.x) sact[i] = act ? act[(size_t)r * lda + i] : 0.f;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float acc = addend ? addend[(size_t)r * ldadd + i] : 0.f;
+    for (int s = 0; s < S; ++s) acc += WT[(size_t)sidx[s] * n + i];
+    const float* wa = WT + (size_t)S * C * n + i;
+    for (int a = 0; a < A; ++a) acc = fmaf(sact[a], wa[(size_t)a * n], acc);
+    rowbuf[i] = acc;
+    pre[(size_t)r * ldp + i] = acc;
+  }
+  __syncthreads();
+  float mean, rstd;
+  row_stats(rowbuf, n, eps, red, mean, rstd);
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    out[(size_t)r * ldo + i] = siluf_(fmaf((rowbuf[i] - mean) * rstd, g[i], b[i]));
+}
+
+int gather_ln_silu(const int32_t* idx, int ldi, int S, int C, const float* act, int lda, int A,
+                   const float* WT, const float* addend, int ldadd, const float* g, const float* b,
+                   float eps, int M, int n, float* pre, int ldp, float* out, int ldo,
+                   cudaStream_t st) {
+  if (M <= 0) return 0;
+  const size_t smem = (size_t)(n + 4 * 32 + S + A) * 4;
+  DV3_REQUIRE(smem <= 48 * 1024, DV3_ERR_BAD_SHAPE, "gather_ln_silu: row of %d too wide", n);
+  gather_ln_silu_kernel<<<M, ROW_THREADS, smem, st>>>(idx, ldi, S, C, act, lda, A, WT, addend,
+                                                      ldadd, g, b, eps, n, pre, ldp, out, ldo);
+  DV3_CHECK_LAUNCH("gather_ln_silu_kernel");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm-GRU gate block.  parts = LN_{3D}(g_pre); r=sig(p0); c=tanh(r*p1); u=sig(p2-1);
+// h' = u*c + (1-u)*h.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ROW_THREADS)
+gru_gates_fwd_kernel(const float* __restrict__ g_pre, int ldg, const float* __restrict__ g,
+                     const float* __restrict__ b, float eps, const float* __restrict__ h, int ldh,
+                     int D, float* __restrict__ h_new, int ldn) {
+  __shared__ float red[4 * 32];
+  const float* row = g_pre + (size_t)blockIdx.x * ldg;
+  float mean, rstd;
+  row_stats(row, 3 * D, eps, red, mean, rstd);
+  for (int j = threadIdx.x; j < D; j += blockDim.x) {
+    const float pr = fmaf((row[j] - mean) * rstd, g[j], b[j]);
+    const float pc = fmaf((row[D + j] - mean) * rstd, g[D + j], b[D + j]);
+    const float pu = fmaf((row[2 * D + j] - mean) * rstd, g[2 * D + j], b[2 * D + j]);
+    const float r = sigmoidf_(pr);
+    const float c = tanhf(r * pc);
+    const float u = sigmoidf_(pu - 1.f);
+    const float hp = h[(size_t)blockIdx.x * ldh + j];
+    h_new[(size_t)blockIdx.x * ldn + j] = u * c + (1.f - u) * hp;
+  }
+}
+
+int gru_gates_fwd(const float* g_pre, int ldg, const float* g, const float* b, float eps,
+                  const float* h, int ldh, int M, int D, float* h_new, int ldn, cudaStream_t st) {
+  if (M <= 0) return 0;
+  gru_gates_fwd_kernel<<<M, ROW_THREADS, 0, st>>>(g_pre, ldg, g, b, eps, h, ldh, D, h_new, ldn);
+  DV3_CHECK_LAUNCH("gru_gates_fwd_kernel");
+  return 0;
+}
+
+struct DhIn {
+  const float* p[4];
+  int ld[4];
+};
+
+__global__ void __launch_bounds__(ROW_THREADS)
+gru_gates_bwd_kernel(const float* __restrict__ g_pre, int ldg, const float* __restrict__ g,
+                     const float* __restrict__ b, float eps, const float* __restrict__ h, int ldh,
+                     DhIn dh, int D, float* __restrict__ d_g_pre, int ldp,
+                     float* __restrict__ d_g_ln, int ldl, float* __restrict__ dh_direct, int ldd) {
+  extern __shared__ float sm[];
+  float* dparts = sm;             // 3D: gradient w.r.t. the LN affine output
+  float* red = sm + 3 * D;        // 128
+  const int r = blockIdx.x;
+  const float* row = g_pre + (size_t)r * ldg;
+  float mean, rstd;
+  row_stats(row, 3 * D, eps, red, mean, rstd);
+  for (int j = threadIdx.x; j < D; j += blockDim.x) {
+    const float pr = fmaf((row[j] - mean) * rstd, g[j], b[j]);
+    const float pc = fmaf((row[D + j] - mean) * rstd, g[D + j], b[D + j]);
+    const float pu = fmaf((row[2 * D + j] - mean) * rstd, g[2 * D + j], b[2 * D + j]);
+    const float rg = sigmoidf_(pr);
+    const float c = tanhf(rg * pc);
+    const float u = sigmoidf_(pu - 1.f);
+    const float hp = h[(size_t)r * ldh + j];
+    float d = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (dh.p[q]) d += dh.p[q][(size_t)r * dh.ld[q] + j];
+    const float du = d * (c - hp);
+    const float dc = d * u;
+    const float drc = dc * (1.f - c * c);
+    dparts[j] = drc * pc * rg * (1.f - rg);
+    dparts[D + j] = drc * rg;
+    dparts[2 * D + j] = du * u * (1.f - u);
+    dh_direct[(size_t)r * ldd + j] = d * (1.f - u);
+  }
+  __syncthreads();
+  float acc[2] = {0.f, 0.f};
+  for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) {
+    const float xh = (row[i] - mean) * rstd;
+    const float dx = dparts[i] * g[i];
+    acc[0] += dx;
+    acc[1] = fmaf(dx, xh, acc[1]);
+    if (d_g_ln) d_g_ln[(size_t)r * ldl + i] = dparts[i];
+  }
+  block_sum<2>(acc, red);
+  const float m1 = acc[0] / (float)(3 * D), m2 = acc[1] / (float)(3 * D);
+  for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) {
+    const float xh = (row[i] - mean) * rstd;
+    d_g_pre[(size_t)r * ldp + i] = rstd * (dparts[i] * g[i] - m1 - xh * m2);
+  }
+}
+
+int gru_gates_bwd(const float* g_pre, int ldg, const float* g, const float* b, float eps,
+                  const float* h, int ldh, const float* const dh_in[4], const int ld_in[4], int M,
+                  int D, float* d_g_pre, int ldp, float* d_g_ln, int ldl, float* dh_direct,
+                  int ldd, cudaStream_t st) {
+  if (M <= 0) return 0;
+  DhIn dh;
+  for (int q = 0; q < 4; ++q) { dh.p[q] = dh_in[q]; dh.ld[q] = ld_in[q]; }
+  const size_t smem = (size_t)(3 * D + 4 * 32) * 4;
+  static bool attr_set = false;
+  if (smem > 48 * 1024 && !attr_set) {
+    DV3_CHECK_CUDA(cudaFuncSetAttribute(gru_gates_bwd_kernel,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  DV3_REQUIRE(smem <= 200 * 1024, DV3_ERR_BAD_SHAPE, "gru_gates_bwd: deter %d too wide", D);
+  gru_gates_bwd_kernel<<<M, ROW_THREADS, smem, st>>>(g_pre, ldg, g, b, eps, h, ldh, dh, D, d_g_pre,
+                                                     ldp, d_g_ln, ldl, dh_direct, ldd);
+  DV3_CHECK_LAUNCH("gru_gates_bwd_kernel");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// unimix categorical: one warp per (row, group), lane k = class k.
+// probs are built exactly along the reference's chain so the supplied-uniform argmax matches:
+//   p = softmax(l); p = (1-r)p + r/C; l' = log p            tools.py:439-441
+//   norm = l' - logsumexp(l'); probs = softmax(norm)        torch Categorical (logits -> probs)
+//   idx = argmax_k probs_k / (-log u_k)                     ATen multinomial n=1
+// ------------------------------------------------------------------------------------------
+struct Unimix {
+  float p;      // softmax(l)
+  float norm;   // normalised log-prob after unimix
+  float probs;  // softmax(norm)
+};
+
+__device__ __forceinline__ Unimix unimix_probs(float l, bool valid, int C, float unimix) {
+  Unimix o;
+  const float NEG = -INFINITY;
+  float m = warp_max(valid ? l : NEG);
+  float e = valid ? expf(l - m) : 0.f;
+  float s = warp_sum(e);
+  o.p = e / s;
+  float lp = l;
+  if (unimix > 0.f) {
+    const float pm = o.p * (1.f - unimix) + unimix / (float)C;
+    lp = logf(pm);
+  }
+  float m2 = warp_max(valid ? lp : NEG);
+  float s2 = warp_sum(valid ? expf(lp - m2) : 0.f);
+  o.norm = lp - (m2 + logf(s2));
+  float m3 = warp_max(valid ? o.norm : NEG);
+  float e3 = valid ? expf(o.norm - m3) : 0.f;
+  float s3 = warp_sum(e3);
+  o.probs = e3 / s3;
+  return o;
+}
+
+// first-index argmax across the warp
+__device__ __forceinline__ int warp_argmax(float v, bool valid, int lane) {
+  float bv = valid ? v : -INFINITY;
+  int bi = valid ? lane : 0x7fffffff;
+  if (valid && v != v) bv = -INFINITY;  // NaN never wins
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(FULL, bv, o);
+    const int oi = __shfl_xor_sync(FULL, bi, o);
+    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+  }
+  return bi;
+}
+
+__global__ void __launch_bounds__(256)
+onehot_sample_kernel(const float* __restrict__ logits, int ldl, const float* __restrict__ u,
+                     int ldu, int permT, int permB, float unimix, int M, int S, int C,
+                     int32_t* __restrict__ idx, int ldi, float* __restrict__ onehot, int ldo) {
+  const int lane = threadIdx.x & 31;
+  const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= (long long)M * S) return;
+  const int r = (int)(w / S), s = (int)(w % S);
+  const bool valid = lane < C;
+  const float l = valid ? logits[(size_t)r * ldl + s * C + lane] : 0.f;
+  const Unimix um = unimix_probs(l, valid, C, unimix);
+  float score;
+  if (u) {
+    const int ur = permT > 0 ? (r % permT) * permB + r / permT : r;
+    const float uu = valid ? u[(size_t)ur * ldu + s * C + lane] : 1.f;
+    score = um.probs / (-logf(uu));
+  } else {
+    score = um.norm;
+  }
+  const int k = warp_argmax(score, valid, lane);
+  if (idx && lane == 0) idx[(size_t)r * ldi + s] = k;
+  if (onehot && valid) onehot[(size_t)r * ldo + s * C + lane] = (lane == k) ? 1.f : 0.f;
+}
+
+int onehot_sample(const float* logits, int ldl, const float* u, int ldu, int permT, int permB,
+                  float unimix, int M, int S, int C, int32_t* idx, int ldi, float* onehot, int ldo,
+                  cudaStream_t st) {
+  if (M <= 0) return 0;
+  DV3_REQUIRE(C >= 1 && C <= 32, DV3_ERR_BAD_SHAPE, "onehot_sample: classes=%d (max 32)", C);
+  const long long warps = (long long)M * S;
+  const int grid = (int)((warps + 7) / 8);
+  onehot_sample_kernel<<<grid, 256, 0, st>>>(logits, ldl, u, ldu, permT, permB, unimix, M, S, C,
+                                             idx, ldi, onehot, ldo);
+  DV3_CHECK_LAUNCH("onehot_sample_kernel");
+  return 0;
+}
+
+// straight-through backward of sample = hard + probs - sg(probs):
+//   q = (1-r) softmax(l) + r/C  (== probs);  gq = g - <g,q>;  d l = (1-r) p (gq - <gq,p>) + ext
+__global__ void __launch_bounds__(256)
+onehot_st_bwd_kernel(const float* __restrict__ logits, int ldl, const float* __restrict__ g1,
+                     int ldg1, const float* __restrict__ g2, int ldg2,
+                     const float* __restrict__ ext, int lde, float unimix, int M, int S, int C,
+                     float* __restrict__ d_logits, int ldd) {
+  const int lane = threadIdx.x & 31;
+  const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= (long long)M * S) return;
+  const int r = (int)(w / S), s = (int)(w % S);
+  const bool valid = lane < C;
+  const int col = s * C + lane;
+  const float l = valid ? logits[(size_t)r * ldl + col] : 0.f;
+  float g = 0.f;
+  if (valid && g1) g += g1[(size_t)r * ldg1 + col];
+  if (valid && g2) g += g2[(size_t)r * ldg2 + col];
+  const float m = warp_max(valid ? l : -INFINITY);
+  const float e = valid ? expf(l - m) : 0.f;
+  const float p = e / warp_sum(e);
+  const float q = valid ? (p * (1.f - unimix) + unimix / (float)C) : 0.f;
+  const float gq = g - warp_sum(g * q);
+  const float dot = warp_sum(valid ? gq * p : 0.f);
+  float d = (1.f - unimix) * p * (gq - dot);
+  if (valid) {
+    if (ext) d += ext[(size_t)r * lde + col];
+    d_logits[(size_t)r * ldd + col] = d;
+  }
+}
+
+int onehot_st_bwd(const float* logits, int ldl, const float* g1, int ldg1, const float* g2,
+                  int ldg2, const float* ext, int lde, float unimix, int M, int S, int C,
+                  float* d_logits, int ldd, cudaStream_t st) {
+  if (M <= 0) return 0;
+  DV3_REQUIRE(C >= 1 && C <= 32, DV3_ERR_BAD_SHAPE, "onehot_st_bwd: classes=%d (max 32)", C);
+  const long long warps = (long long)M * S;
+  const int grid = (int)((warps + 7) / 8);
+  onehot_st_bwd_kernel<<<grid, 256, 0, st>>>(logits, ldl, g1, ldg1, g2, ldg2, ext, lde, unimix, M,
+                                             S, C, d_logits, ldd);
+  DV3_CHECK_LAUNCH("onehot_st_bwd_kernel");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// small data movers
+// ------------------------------------------------------------------------------------------
+__global__ void idx_to_onehot_kernel(const int32_t* __restrict__ idx, int ldi, int M, int S, int C,
+                                     float* __restrict__ out, int ld) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long tot = (long long)M * S * C;
+  if (i >= tot) return;
+  const int c = (int)(i % C);
+  const int s = (int)((i / C) % S);
+  const int r = (int)(i / ((long long)S * C));
+  out[(size_t)r * ld + s * C + c] = (idx[(size_t)r * ldi + s] == c) ? 1.f : 0.f;
+}
+
+int idx_to_onehot(const int32_t* idx, int ldi, int M, int S, int C, float* out, int ld,
+                  cudaStream_t st) {
+  const long long tot = (long long)M * S * C;
+  if (tot <= 0) return 0;
+  idx_to_onehot_kernel<<<(int)((tot + 255) / 256), 256, 0, st>>>(idx, ldi, M, S, C, out, ld);
+  DV3_CHECK_LAUNCH("idx_to_onehot_kernel");
+  return 0;
+}
+
+template <typename T>
+__global__ void copy_rows_kernel(const T* __restrict__ in, int ldi, int M, int n,
+                                 T* __restrict__ out, int ldo) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)M * n) return;
+  const int r = (int)(i / n), c = (int)(i % n);
+  out[(size_t)r * ldo + c] = in[(size_t)r * ldi + c];
+}
+
+int copy_rows(const float* in, int ldi, int M, int n, float* out, int ldo, cudaStream_t st) {
+  const long long tot = (long long)M * n;
+  if (tot <= 0) return 0;
+  copy_rows_kernel<float><<<(int)((tot + 255) / 256), 256, 0, st>>>(in, ldi, M, n, out, ldo);
+  DV3_CHECK_LAUNCH("copy_rows_kernel");
+  return 0;
+}
+
+int copy_rows_i32(const int32_t* in, int ldi, int M, int n, int32_t* out, int ldo,
+                  cudaStream_t st) {
+  const long long tot = (long long)M * n;
+  if (tot <= 0) return 0;
+  copy_rows_kernel<int32_t><<<(int)((tot + 255) / 256), 256, 0, st>>>(in, ldi, M, n, out, ldo);
+  DV3_CHECK_LAUNCH("copy_rows_kernel");
+  return 0;
+}
+
+__global__ void tanh_kernel(const float* __restrict__ in, int n, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = tanhf(in[i]);
+}
+
+int tanh_vec(const float* in, int n, float* out, cudaStream_t st) {
+  if (n <= 0) return 0;
+  tanh_kernel<<<(n + 255) / 256, 256, 0, st>>>(in, n, out);
+  DV3_CHECK_LAUNCH("tanh_kernel");
+  return 0;
+}
+
+int fill_zero(void* p, size_t bytes, cudaStream_t st) {
+  if (!p || bytes == 0) return 0;
+  DV3_CHECK_CUDA(cudaMemsetAsync(p, 0, bytes, st));
+  return 0;
+}
+
+}  // namespace dv3
+
+// ------------------------------------------------------------------------------------------
+// C ABI: the building blocks, individually testable against the oracle
+// ------------------------------------------------------------------------------------------
+using namespace dv3;
+#define ST(s) static_cast<cudaStream_t>(s)
+
+extern "C" int dv3_ln_silu_fwd(const float* pre, int32_t ld, const float* g, const float* b,
+                               float eps, int32_t M, int32_t n, float* out, int32_t ldo,
+                               void* stream) {
+  DV3_REQUIRE(pre && g && b && out, DV3_ERR_NULL, "ln_silu_fwd: null pointer");
+  return ln_silu_fwd(pre, ld, g, b, eps, M, n, out, ldo, ST(stream));
+}
+
+extern "C" int dv3_ln_silu_bwd(const float* pre, int32_t ld, const float* g, const float* b,
+                               float eps, const float* d_out, int32_t ldd, int32_t M, int32_t n,
+                               float* d_pre, float* d_ln, int32_t ldp, void* stream) {
+  DV3_REQUIRE(pre && g && b && d_out && d_pre, DV3_ERR_NULL, "ln_silu_bwd: null pointer");
+  return ln_silu_bwd(pre, ld, g, b, eps, d_out, ldd, M, n, d_pre, ldp, d_ln, ldp, ST(stream));
+}
+
+extern "C" int dv3_gru_gates_fwd(const float* g_pre, int32_t ldg, const float* g, const float* b,
+                                 float eps, const float* h, int32_t ldh, int32_t M, int32_t D,
+                                 float* h_new, int32_t ldn, void* stream) {
+  DV3_REQUIRE(g_pre && g && b && h && h_new, DV3_ERR_NULL, "gru_gates_fwd: null pointer");
+  return gru_gates_fwd(g_pre, ldg, g, b, eps, h, ldh, M, D, h_new, ldn, ST(stream));
+}
+
+extern "C" int dv3_gru_gates_bwd(const float* g_pre, int32_t ldg, const float* g, const float* b,
+                                 float eps, const float* h, int32_t ldh, const float* d_h_new,
+                                 int32_t ldd, int32_t M, int32_t D, float* d_g_pre, float* d_g_ln,
+                                 int32_t ldp, float* d_h, int32_t ldo, void* stream) {
+  DV3_REQUIRE(g_pre && g && b && h && d_h_new && d_g_pre && d_h, DV3_ERR_NULL,
+              "gru_gates_bwd: null pointer");
+  const float* in[4] = {d_h_new, nullptr, nullptr, nullptr};
+  const int lds[4] = {ldd, 0, 0, 0};
+  return gru_gates_bwd(g_pre, ldg, g, b, eps, h, ldh, in, lds, M, D, d_g_pre, ldp, d_g_ln, ldp,
+                       d_h, ldo, ST(stream));
+}
+
+extern "C" int dv3_onehot_linear_ln_silu(const int32_t* idx, int32_t S, int32_t C,
+                                         const float* act, int32_t A, const float* WT,
+                                         const float* addend, const float* g, const float* b,
+                                         float eps, int32_t M, int32_t n, float* pre, float* out,
+                                         void* stream) {
+  DV3_REQUIRE(idx && WT && g && b && pre && out, DV3_ERR_NULL, "onehot_linear: null pointer");
+  return gather_ln_silu(idx, S, S, C, act, A, act ? A : 0, WT, addend, n, g, b, eps, M, n, pre, n,
+                        out, n, ST(stream));
+}
+
+extern "C" int dv3_onehot_sample(const float* logits, const float* u, float unimix, int32_t M,
+                                 int32_t S, int32_t C, int32_t* idx, float* onehot,
+                                 int32_t ld_onehot, void* stream) {
+  DV3_REQUIRE(logits && (idx || onehot), DV3_ERR_NULL, "onehot_sample: null pointer");
+  return onehot_sample(logits, S * C, u, S * C, 0, 0, unimix, M, S, C, idx, S, onehot, ld_onehot,
+                       ST(stream));
+}
+
+extern "C" int dv3_onehot_st_bwd(const float* logits, const float* g_sample, const float* ext,
+                                 float unimix, int32_t M, int32_t S, int32_t C, float* d_logits,
+                                 void* stream) {
+  DV3_REQUIRE(logits && d_logits, DV3_ERR_NULL, "onehot_st_bwd: null pointer");
+  return onehot_st_bwd(logits, S * C, g_sample, S * C, nullptr, 0, ext, S * C, unimix, M, S, C,
+                       d_logits, S * C, ST(stream));
+}
+
+extern "C" int dv3_idx_to_onehot(const int32_t* idx, int32_t M, int32_t S, int32_t C, float* out,
+                                 int32_t ld, void* stream) {
+  DV3_REQUIRE(idx && out, DV3_ERR_NULL, "idx_to_onehot: null pointer");
+  return idx_to_onehot(idx, S, M, S, C, out, ld, ST(stream));
+}

@@ -1,0 +1,310 @@
+"""Host-side mirror of the reference's ``models`` surface: ``WorldModel`` and ``ImagBehavior``
+with the same constructors, ``_train`` / ``_imagine`` signatures, return tuples, metric keys and
+``state_dict`` names (reference models.py:29-213, 218-689).
+
+The rollouts (RSSM.observe, the actor-in-the-loop imagination), the KL balance, the two-hot
+heads' log-probs / means and the lambda-return run on libdv3_b200.so.  Both ``_train`` methods
+take an optional ``noise`` argument so the caller can supply the uniforms / normals (parity
+tests); without it they are drawn from torch's generator.
+"""
+from __future__ import annotations
+
+import copy
+
+import torch
+from torch import nn
+
+from . import kernels as K
+from . import networks
+from . import tools
+
+
+class RewardEMA:
+    """5/95-percentile EMA normaliser (reference models.py:11-26)."""
+
+    def __init__(self, device, alpha=1e-2):
+        self.alpha = alpha
+        self.range = torch.tensor([0.05, 0.95], device=device)
+
+    def __call__(self, x, ema_vals):
+        q = torch.quantile(x.detach().flatten(), self.range)
+        ema_vals[:] = self.alpha * q + (1 - self.alpha) * ema_vals
+        scale = torch.clip(ema_vals[1] - ema_vals[0], min=1.0)
+        return ema_vals[0].detach(), scale.detach()
+
+
+class WorldModel(nn.Module):
+    def __init__(self, obs_space, act_space, step, config, grad_sync=None):
+        super().__init__()
+        if config.precision != 32:
+            raise NotImplementedError("precision: 32 is the contract of the B200 path")
+        self._step = step
+        self._config = config
+        shapes = {k: tuple(v.shape) for k, v in obs_space.spaces.items()}
+        self.encoder = networks.MultiEncoder(shapes, **config.encoder)
+        self.embed_size = self.encoder.outdim
+        self.dynamics = networks.RSSM(
+            config.dyn_stoch, config.dyn_deter, config.dyn_hidden, config.dyn_rec_depth,
+            config.dyn_discrete, config.act, config.norm, config.dyn_mean_act, config.dyn_std_act,
+            config.dyn_min_std, config.unimix_ratio, config.initial, config.num_actions,
+            self.embed_size, config.device)
+        feat_size = config.dyn_stoch * config.dyn_discrete + config.dyn_deter
+        self.heads = nn.ModuleDict()
+        self.heads["decoder"] = networks.MultiDecoder(feat_size, shapes, **config.decoder)
+        self.heads["reward"] = networks.MLP(
+            feat_size, (255,) if config.reward_head["dist"] == "symlog_disc" else (),
+            config.reward_head["layers"], config.units, config.act, config.norm,
+            dist=config.reward_head["dist"], outscale=config.reward_head["outscale"],
+            name="Reward")
+        self.heads["cont"] = networks.MLP(
+            feat_size, (), config.cont_head["layers"], config.units, config.act, config.norm,
+            dist="binary", outscale=config.cont_head["outscale"], name="Cont")
+        for name in config.grad_heads:
+            if name not in self.heads:
+                raise AssertionError(name)
+        self.to(config.device)
+        self._model_opt = tools.Optimizer(
+            "model", self.parameters(), config.model_lr, config.opt_eps, config.grad_clip,
+            config.weight_decay, opt=config.opt, grad_sync=grad_sync)
+        self._scales = dict(reward=config.reward_head["loss_scale"],
+                            cont=config.cont_head["loss_scale"])
+        self.requires_grad_(False)
+
+    def preprocess(self, obs):
+        """numpy / CPU tensors -> fp32 device tensors (reference models.py:174-190); pinned host
+        tensors are copied asynchronously."""
+        dev = self._config.device
+        out = {}
+        for k, v in obs.items():
+            t = v if torch.is_tensor(v) else torch.as_tensor(v)
+            out[k] = t.to(dev, non_blocking=True).to(torch.float32)
+        if "image" in out:
+            out["image"] = out["image"] / 255.0
+        if "discount" in out:
+            out["discount"] = (out["discount"] * self._config.discount).unsqueeze(-1)
+        if "is_first" not in out or "is_terminal" not in out:
+            raise AssertionError("batch needs is_first and is_terminal")
+        out["cont"] = (1.0 - out["is_terminal"]).unsqueeze(-1)
+        return out
+
+    def loss(self, data, noise=None):
+        """Forward of the world-model step -> (mean loss, post, aux); no optimizer."""
+        cfg = self._config
+        embed = self.encoder(data)
+        post, prior = self.dynamics.observe(embed, data["action"], data["is_first"], noise=noise)
+        kl_loss, kl_value, dyn_loss, rep_loss, post_ent, prior_ent = \
+            self.dynamics.kl_loss_with_entropy(post, prior, cfg.kl_free, cfg.dyn_scale,
+                                               cfg.rep_scale)
+        if kl_loss.shape != embed.shape[:2]:
+            raise AssertionError(kl_loss.shape)
+        feat = self.dynamics.get_feat(post)
+        preds = {}
+        for name, head in self.heads.items():
+            pred = head(feat if name in cfg.grad_heads else feat.detach())
+            if isinstance(pred, dict):
+                preds.update(pred)
+            else:
+                preds[name] = pred
+        losses = {}
+        for name, pred in preds.items():
+            loss = -pred.log_prob(data[name])
+            if loss.shape != embed.shape[:2]:
+                raise AssertionError((name, loss.shape))
+            losses[name] = loss
+        model_loss = sum(v * self._scales.get(k, 1.0) for k, v in losses.items()) + kl_loss
+        aux = dict(embed=embed, feat=feat, prior=prior, losses=losses, kl_value=kl_value,
+                   dyn_loss=dyn_loss, rep_loss=rep_loss, post_ent=post_ent, prior_ent=prior_ent)
+        return torch.mean(model_loss), post, aux
+
+    def _train(self, data, noise=None):
+        cfg = self._config
+        data = self.preprocess(data)
+        with tools.RequiresGrad(self):
+            loss, post, aux = self.loss(data, noise)
+            metrics = self._model_opt(loss, self.parameters())
+        metrics.update({f"{k}_loss": v.detach() for k, v in aux["losses"].items()})
+        metrics["kl_free"] = cfg.kl_free
+        metrics["dyn_scale"] = cfg.dyn_scale
+        metrics["rep_scale"] = cfg.rep_scale
+        metrics["dyn_loss"] = aux["dyn_loss"]
+        metrics["rep_loss"] = aux["rep_loss"]
+        metrics["kl"] = torch.mean(aux["kl_value"])
+        metrics["prior_ent"] = torch.mean(aux["prior_ent"])
+        metrics["post_ent"] = torch.mean(aux["post_ent"])
+        context = dict(embed=aux["embed"], feat=aux["feat"], kl=aux["kl_value"],
+                       postent=aux["post_ent"])
+        post = {k: v.detach() for k, v in post.items()}
+        if not getattr(cfg, "device_metrics", False):
+            metrics = tools.to_host(metrics)
+        return post, context, metrics
+
+    def video_pred(self, data):
+        data = self.preprocess(data)
+        embed = self.encoder(data)
+        states, _ = self.dynamics.observe(embed[:6, :5], data["action"][:6, :5].clone(),
+                                          data["is_first"][:6, :5])
+        dec = self.heads["decoder"]
+        recon = dec(self.dynamics.get_feat(states))["image"].mode()[:6]
+        init = {k: v[:, -1] for k, v in states.items()}
+        prior = self.dynamics.imagine_with_action(data["action"][:6, 5:], init)
+        openl = dec(self.dynamics.get_feat(prior))["image"].mode()
+        model = torch.cat([recon[:, :5], openl], 1)
+        truth = data["image"][:6]
+        return torch.cat([truth, model, (model - truth + 1.0) / 2.0], 2)
+
+
+class ImagBehavior(nn.Module):
+    def __init__(self, config, world_model, future_predictor=None, grad_sync=None):
+        super().__init__()
+        self._config = config
+        self._world_model = world_model
+        feat_size = config.dyn_stoch * config.dyn_discrete + config.dyn_deter
+        self.actor = networks.MLP(
+            feat_size, (config.num_actions,), config.actor["layers"], config.units, config.act,
+            config.norm, config.actor["dist"], config.actor["std"], config.actor["min_std"],
+            config.actor["max_std"], absmax=1.0, temp=config.actor["temp"],
+            unimix_ratio=config.actor["unimix_ratio"], outscale=config.actor["outscale"],
+            name="Actor")
+        self.value = networks.MLP(
+            feat_size, (255,) if config.critic["dist"] == "symlog_disc" else (),
+            config.critic["layers"], config.units, config.act, config.norm, config.critic["dist"],
+            outscale=config.critic["outscale"], name="Value")
+        if config.critic["slow_target"]:
+            self._slow_value = copy.deepcopy(self.value)
+            self._updates = 0
+        if config.reward_EMA:
+            self.register_buffer("ema_vals", torch.zeros((2,)))
+            self.reward_ema = RewardEMA(device=config.device)
+        self.to(config.device)
+        kw = dict(wd=config.weight_decay, opt=config.opt, grad_sync=grad_sync)
+        self._actor_opt = tools.Optimizer("actor", self.actor.parameters(), config.actor["lr"],
+                                          config.actor["eps"], config.actor["grad_clip"], **kw)
+        self._value_opt = tools.Optimizer("value", self.value.parameters(), config.critic["lr"],
+                                          config.critic["eps"], config.critic["grad_clip"], **kw)
+        self.actor.requires_grad_(False)
+        self.value.requires_grad_(False)
+        if config.critic["slow_target"]:
+            self._slow_value.requires_grad_(False)
+
+    # ---- rollout -------------------------------------------------------------------------
+    def _imagine(self, start, policy, horizon, noise=None):
+        """start: dict of [B,T,...] posterior tensors -> (feats [H,N,F] detached, states dict of
+        [H,N,...], actions [H,N,A]); reference models.py:448-548.  ``noise`` = (act_noise
+        [H,N,A], u_state [H,N,S,C])."""
+        dyn = self._world_model.dynamics
+        S, Cc = dyn._stoch, dyn._discrete
+        flat = {k: v.reshape([-1] + list(v.shape[2:])) for k, v in start.items()}
+        N = flat["deter"].shape[0]
+        dev = flat["deter"].device
+        spec = policy.actor_spec()
+        if noise is None:
+            A = dyn._num_actions
+            an = (torch.randn(horizon, N, A, device=dev) if spec.dist == "normal"
+                  else torch.rand(horizon, N, A, device=dev))
+            noise = (an, torch.rand(horizon, N, S, Cc, device=dev))
+        feat, logit, action, _ = K.imagine(
+            dyn._to_idx(flat["stoch"]), flat["deter"].detach(), noise[0], noise[1], None, horizon,
+            dyn.dims, spec, dyn.kernel_params(), policy.actor_params(),
+            start_logit=flat.get("logit"))
+        SC = S * Cc
+        states = dict(stoch=feat[..., :SC].reshape(horizon, N, S, Cc), deter=feat[..., SC:],
+                      logit=logit)
+        return feat.detach(), states, action
+
+    # ---- training step -------------------------------------------------------------------
+    def _train(self, start, objective, noise=None):
+        cfg = self._config
+        self._update_slow_target()
+        metrics = {}
+        with tools.RequiresGrad(self.actor):
+            imag_feat, imag_state, imag_action = self._imagine(start, self.actor,
+                                                               cfg.imag_horizon, noise)
+            reward = objective(imag_feat, imag_state, imag_action)
+            policy = self.actor(imag_feat)
+            actor_ent = policy.entropy()
+            target, weights, base = self._compute_target(imag_feat, imag_state, reward)
+            actor_loss, mets = self._compute_actor_loss(imag_feat, imag_action, target, weights,
+                                                        base, policy)
+            actor_loss = actor_loss - cfg.actor["entropy"] * actor_ent[:-1, ..., None]
+            actor_loss = torch.mean(actor_loss)
+            metrics.update(mets)
+        with tools.RequiresGrad(self.value):
+            value = self.value(imag_feat[:-1].detach())
+            value_loss = -value.log_prob(target.detach())
+            if cfg.critic["slow_target"]:
+                slow = self._slow_value(imag_feat[:-1].detach())
+                value_loss = value_loss - value.log_prob(slow.mode().detach())
+            value_loss = torch.mean(weights[:-1] * value_loss[:, :, None])
+        metrics.update(tools.tensorstats(value.mode(), "value"))
+        metrics.update(tools.tensorstats(target, "target"))
+        metrics.update(tools.tensorstats(reward, "imag_reward"))
+        if cfg.actor["dist"] in ["onehot"]:
+            metrics.update(tools.tensorstats(torch.argmax(imag_action, dim=-1).float(),
+                                             "imag_action"))
+        else:
+            metrics.update(tools.tensorstats(imag_action, "imag_action"))
+        metrics["actor_entropy"] = torch.mean(actor_ent.detach())
+        with tools.RequiresGrad(self):
+            metrics.update(self._actor_opt(actor_loss, self.actor.parameters()))
+            metrics.update(self._value_opt(value_loss, self.value.parameters()))
+        if not getattr(cfg, "device_metrics", False):
+            metrics = tools.to_host(metrics)
+        return imag_feat, imag_state, imag_action, weights, metrics
+
+    def _compute_target(self, imag_feat, imag_state, reward):
+        """reference models.py:620-638; the target comes back stacked [H-1,N,1]."""
+        cfg = self._config
+        wm = self._world_model
+        if "cont" in wm.heads:
+            inp = wm.dynamics.get_feat(imag_state)
+            discount = cfg.discount * wm.heads["cont"](inp).mean
+        else:
+            discount = cfg.discount * torch.ones_like(reward)
+        value = self.value(imag_feat).mode()
+        target = tools.lambda_return_stacked(reward[1:], value[:-1], discount[1:], value[-1],
+                                             cfg.discount_lambda)
+        weights = torch.cumprod(torch.cat([torch.ones_like(discount[:1]), discount[:-1]], 0),
+                                0).detach()
+        return target, weights, value[:-1]
+
+    def _compute_actor_loss(self, imag_feat, imag_action, target, weights, base, policy=None):
+        cfg = self._config
+        metrics = {}
+        if policy is None:
+            policy = self.actor(imag_feat.detach())
+        if torch.is_tensor(target) is False:
+            target = torch.stack(target, dim=1)
+        if cfg.reward_EMA:
+            offset, scale = self.reward_ema(target, self.ema_vals)
+            normed_target = (target - offset) / scale
+            normed_base = (base - offset) / scale
+            adv = normed_target - normed_base
+            metrics.update(tools.tensorstats(normed_target, "normed_target"))
+            metrics["EMA_005"] = self.ema_vals[0].clone()
+            metrics["EMA_095"] = self.ema_vals[1].clone()
+        else:
+            adv = target - base
+        if cfg.imag_gradient == "dynamics":
+            actor_target = adv
+        elif cfg.imag_gradient in ("reinforce", "both"):
+            actor_target = (policy.log_prob(imag_action)[:-1][:, :, None]
+                            * (target - self.value(imag_feat[:-1]).mode()).detach())
+            if cfg.imag_gradient == "both":
+                mix = cfg.imag_gradient_mix
+                actor_target = mix * target + (1 - mix) * actor_target
+                metrics["imag_gradient_mix"] = mix
+        else:
+            raise NotImplementedError(cfg.imag_gradient)
+        return -weights[:-1] * actor_target, metrics
+
+    def _update_slow_target(self):
+        cfg = self._config
+        if cfg.critic["slow_target"]:
+            if self._updates % cfg.critic["slow_target_update"] == 0:
+                mix = cfg.critic["slow_target_fraction"]
+                with torch.no_grad():
+                    src = list(self.value.parameters())
+                    dst = list(self._slow_value.parameters())
+                    torch._foreach_mul_(dst, 1 - mix)
+                    torch._foreach_add_(dst, src, alpha=mix)
+            self._updates += 1

@@ -1,0 +1,408 @@
+"""Host-side mirror of the reference's ``tools`` surface that sits on the training hot path.
+
+Same call signatures and return conventions as the reference (file:line cited per item), with
+the loops and the distribution arithmetic running in the sm_100a kernels of libdv3_b200.so:
+
+* ``lambda_return``          reference tools.py:702-728 (+682-699): returns a tuple of N [T,1]
+* ``DiscDist``               reference tools.py:463-517 (symlog two-hot head)
+* ``OneHotDist``             reference tools.py:436-460 (unimix categorical, straight-through)
+* ``Optimizer``              reference tools.py:731-783, plus the data-parallel gradient allreduce
+* ``symlog`` / ``symexp``    reference tools.py:22-27
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import kernels as K
+
+
+def symlog(x):
+    return torch.sign(x) * torch.log(torch.abs(x) + 1.0)
+
+
+def symexp(x):
+    return torch.sign(x) * (torch.exp(torch.abs(x)) - 1.0)
+
+
+# --------------------------------------------------------------------------------------
+# lambda return
+# --------------------------------------------------------------------------------------
+def lambda_return_stacked(reward, value, pcont, bootstrap, lambda_):
+    """Time-major [H,N,1] (or [H,N]) in -> same shape out; one kernel, differentiable."""
+    shape = reward.shape
+    H = shape[0]
+    if isinstance(pcont, (int, float)):
+        pcont = pcont * torch.ones_like(reward)
+    if bootstrap is None:
+        bootstrap = torch.zeros_like(value[-1])
+    ret = K.lambda_return_hn(reward.reshape(H, -1), value.reshape(H, -1), pcont.reshape(H, -1),
+                             bootstrap.reshape(-1), lambda_)
+    return ret.reshape(shape)
+
+
+def lambda_return(reward, value, pcont, bootstrap, lambda_, axis):
+    """Drop-in for the reference call: a tuple of N tensors of shape [T,1] (its callers re-stack
+    them with ``torch.stack(target, dim=1)``).  Only the layout the reference produces is
+    supported: time on ``axis`` 0 with [T,N,1] operands (models.py:627-634)."""
+    if len(reward.shape) != len(value.shape):
+        raise AssertionError((reward.shape, value.shape))
+    if axis != 0:
+        perm = list(range(reward.dim()))
+        perm[0], perm[axis] = perm[axis], perm[0]
+        reward, value = reward.permute(perm), value.permute(perm)
+        if not isinstance(pcont, (int, float)):
+            pcont = pcont.permute(perm)
+    if reward.dim() != 3 or reward.shape[-1] != 1:
+        raise NotImplementedError(f"lambda_return expects [T,N,1] operands, got {tuple(reward.shape)}")
+    ret = lambda_return_stacked(reward, value, pcont, bootstrap, lambda_)   # [T,N,1]
+    return torch.unbind(ret.permute(1, 0, 2), dim=0)
+
+
+# --------------------------------------------------------------------------------------
+# distributions
+# --------------------------------------------------------------------------------------
+_BUCKETS = {}
+
+
+def _buckets(device, low=-20.0, high=20.0, steps=255):
+    key = (str(device), low, high, steps)
+    if key not in _BUCKETS:
+        # built with torch.linspace so the values are the ones the reference's own tensor holds
+        _BUCKETS[key] = torch.linspace(low, high, steps=steps, device=device)
+    return _BUCKETS[key]
+
+
+class DiscDist:
+    """255-bucket two-hot regression head over symlog space (reference tools.py:463-517)."""
+
+    def __init__(self, logits, low=-20.0, high=20.0, transfwd=symlog, transbwd=symexp, device=None):
+        if transfwd is not symlog or transbwd is not symexp:
+            raise NotImplementedError("the kernel implements the symlog/symexp transform pair")
+        self.logits = logits
+        self.buckets = _buckets(logits.device, low, high)
+
+    @property
+    def probs(self):
+        return torch.softmax(self.logits, -1)
+
+    def mean(self):
+        return K.twohot_mean(self.logits, self.buckets)
+
+    def mode(self):
+        return K.twohot_mean(self.logits, self.buckets)
+
+    def log_prob(self, x):
+        # x is [...] (reward, models.py:140) or [..., 1] (value target, models.py:423)
+        lead = tuple(self.logits.shape[:-1])
+        if tuple(x.shape) not in (lead, lead + (1,)):
+            raise AssertionError((x.shape, self.logits.shape))
+        return K.twohot_logprob(self.logits, x.reshape(lead), self.buckets)
+
+
+class OneHotDist:
+    """unimix categorical over the last axis (reference tools.py:436-460).
+
+    ``sample`` draws with supplied or freshly generated uniforms: idx = argmax probs/(-log u),
+    the algorithm behind torch.multinomial(n=1)."""
+
+    def __init__(self, logits, unimix_ratio=0.0):
+        self._raw = logits
+        self._unimix = float(unimix_ratio)
+        lg = logits
+        if self._unimix > 0.0:
+            pr = F.softmax(lg, -1) * (1.0 - self._unimix) + self._unimix / lg.shape[-1]
+            lg = torch.log(pr)
+        self.logits = lg - torch.logsumexp(lg, -1, keepdim=True)
+
+    @property
+    def probs(self):
+        return F.softmax(self.logits, -1)
+
+    def mode(self):
+        hard = F.one_hot(torch.argmax(self.logits, -1), self.logits.shape[-1]).to(self.logits.dtype)
+        return hard.detach() + self.logits - self.logits.detach()
+
+    def sample(self, sample_shape=(), u=None):
+        if tuple(sample_shape) != ():
+            raise NotImplementedError("sample_shape")
+        shape = self._raw.shape
+        if u is None:
+            u = torch.rand(shape, device=self._raw.device)
+        lg3 = self._raw.detach().reshape(-1, 1, shape[-1]).contiguous().float()
+        _, hot = K.onehot_sample(lg3, u.reshape(lg3.shape).contiguous().float(), self._unimix)
+        probs = self.probs
+        return hot.reshape(shape) + (probs - probs.detach())
+
+    def entropy(self):
+        lg = torch.clamp(self.logits, min=torch.finfo(self.logits.dtype).min)
+        return -(lg * self.probs).sum(-1)
+
+    def log_prob(self, value):
+        idx = value.max(-1)[1]
+        return self.logits.gather(-1, idx[..., None])[..., 0]
+
+
+class IndependentOneHot:
+    """Independent(OneHotDist, 1): sums entropy / log_prob over the group axis."""
+
+    def __init__(self, logits, unimix_ratio):
+        self.base = OneHotDist(logits, unimix_ratio)
+
+    def mode(self):
+        return self.base.mode()
+
+    def sample(self, u=None):
+        lg = self.base._raw
+        flat = OneHotDist(lg.reshape(-1, lg.shape[-1]), self.base._unimix)
+        return flat.sample(u=None if u is None else u.reshape(-1, lg.shape[-1])).reshape(lg.shape)
+
+    def entropy(self):
+        return self.base.entropy().sum(-1)
+
+    def log_prob(self, value):
+        return self.base.log_prob(value).sum(-1)
+
+
+class NormalTanhMean:
+    """actor 'normal': Normal(tanh(mean), (max-min)*sigmoid(std+2)+min) with the absmax clip on
+    samples (reference networks.py:693-700 + tools.py:575-601)."""
+
+    def __init__(self, mean_raw, std_raw, min_std, max_std, absmax=None):
+        self.mean = torch.tanh(mean_raw)
+        self.std = (max_std - min_std) * torch.sigmoid(std_raw + 2.0) + min_std
+        self.absmax = absmax
+
+    def _clip(self, out):
+        if self.absmax is None:
+            return out
+        return out * (self.absmax / torch.clip(torch.abs(out), min=self.absmax)).detach()
+
+    def mode(self):
+        return self._clip(self.mean)
+
+    def sample(self, sample_shape=(), eps=None):
+        if eps is None:
+            eps = torch.randn_like(self.mean)
+        return self._clip(self.mean + self.std * eps)
+
+    def entropy(self):
+        return (0.5 + 0.5 * math.log(2 * math.pi) + torch.log(self.std)).sum(-1)
+
+    def log_prob(self, x):
+        var = self.std ** 2
+        return (-((x - self.mean) ** 2) / (2 * var) - torch.log(self.std)
+                - math.log(math.sqrt(2 * math.pi))).sum(-1)
+
+
+class Bernoulli:
+    """cont head (reference tools.py:604-628)."""
+
+    def __init__(self, logits):
+        self.logits = logits
+        self.mean = torch.sigmoid(logits)
+
+    def mode(self):
+        m = torch.round(self.mean)
+        return m.detach() + self.mean - self.mean.detach()
+
+    def log_prob(self, x):
+        return torch.sum(-F.softplus(self.logits) * (1 - x) - F.softplus(-self.logits) * x, -1)
+
+    def entropy(self):
+        p = self.mean
+        return (F.softplus(self.logits) - p * self.logits).sum(-1)
+
+
+class MSEDist:
+    """image decoder head (reference tools.py:520-543)."""
+
+    def __init__(self, mode):
+        self._mode = mode
+
+    def mode(self):
+        return self._mode
+
+    def mean(self):
+        return self._mode
+
+    def log_prob(self, value):
+        if self._mode.shape != value.shape:
+            raise AssertionError((self._mode.shape, value.shape))
+        return -((self._mode - value) ** 2).flatten(2).sum(-1)
+
+
+class SymlogDist:
+    """vector decoder head (reference tools.py:546-572), 'mse' distance, 'sum' aggregation."""
+
+    def __init__(self, mode, tol=1e-8):
+        self._mode = mode
+        self._tol = tol
+
+    def mode(self):
+        return symexp(self._mode)
+
+    def mean(self):
+        return symexp(self._mode)
+
+    def log_prob(self, value):
+        if self._mode.shape != value.shape:
+            raise AssertionError((self._mode.shape, value.shape))
+        dist = (self._mode - symlog(value)) ** 2.0
+        dist = torch.where(dist < self._tol, torch.zeros_like(dist), dist)
+        return -dist.flatten(2).sum(-1)
+
+
+# --------------------------------------------------------------------------------------
+# training utilities
+# --------------------------------------------------------------------------------------
+class RequiresGrad:
+    def __init__(self, model):
+        self._model = model
+
+    def __enter__(self):
+        self._model.requires_grad_(True)
+
+    def __exit__(self, *exc):
+        self._model.requires_grad_(False)
+
+
+def tensorstats(tensor, prefix=None):
+    """mean/std/min/max as device scalars (the reference syncs four times here,
+    tools.py:949-958; the host copy happens once per step in ``to_host``)."""
+    t = tensor.detach().float()
+    out = {"mean": t.mean(), "std": t.std(), "min": t.min(), "max": t.max()}
+    return {f"{prefix}_{k}" if prefix else k: v for k, v in out.items()}
+
+
+def to_host(metrics):
+    """One device->host transfer for all scalar metrics; arrays go individually."""
+    scalars = {k: v for k, v in metrics.items() if torch.is_tensor(v) and v.numel() == 1}
+    out = {}
+    if scalars:
+        flat = torch.stack([v.detach().reshape(()).float() for v in scalars.values()]).cpu().numpy()
+        for k, x in zip(scalars.keys(), flat):
+            out[k] = np.asarray(x)
+    for k, v in metrics.items():
+        if k in out:
+            continue
+        out[k] = v.detach().cpu().numpy() if torch.is_tensor(v) else v
+    return {k: out[k] for k in metrics}
+
+
+class GradSync:
+    """Data-parallel gradient averaging: one flat bucket per optimizer, allreduce(sum)/world
+    over NCCL (gloo in the CPU tests) between backward and clip_grad_norm_, where the reference's
+    single-process Optimizer has nothing (tools.py:765-768)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+
+    def __call__(self, params):
+        if self.world == 1:
+            return
+        grads = [p.grad for p in params if p.grad is not None]
+        if not grads:
+            return
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        self.dist.all_reduce(flat, op=self.dist.ReduceOp.SUM, group=self.group)
+        flat.div_(self.world)
+        off = 0
+        for g in grads:
+            n = g.numel()
+            g.copy_(flat[off:off + n].view_as(g))
+            off += n
+
+
+class Optimizer:
+    """Adam + global-norm clip, the reference's tools.Optimizer call sequence
+    (tools.py:760-776): zero_grad -> backward -> [DP allreduce] -> clip -> (wd) -> step."""
+
+    def __init__(self, name, parameters, lr, eps=1e-4, clip=None, wd=None, wd_pattern=r".*",
+                 opt="adam", use_amp=False, grad_sync=None):
+        if use_amp:
+            raise NotImplementedError("fp32 is the contract of the B200 path (precision: 32)")
+        if opt != "adam":
+            raise NotImplementedError(opt)
+        if wd_pattern != r".*":
+            raise NotImplementedError("wd_pattern")
+        self._name = name
+        self._params = list(parameters)
+        self._clip = clip
+        self._wd = wd
+        fused = bool(self._params) and self._params[0].is_cuda
+        self._opt = torch.optim.Adam(self._params, lr=lr, eps=eps, fused=fused)
+        self._sync = grad_sync
+
+    def set_grad_sync(self, sync):
+        self._sync = sync
+
+    def state_dict(self):
+        return self._opt.state_dict()
+
+    def load_state_dict(self, sd):
+        self._opt.load_state_dict(sd)
+
+    def __call__(self, loss, params=None, retain_graph=False):
+        if loss.dim() != 0:
+            raise AssertionError(loss.shape)
+        params = self._params
+        metrics = {f"{self._name}_loss": loss.detach()}
+        self._opt.zero_grad(set_to_none=True)
+        loss.backward(retain_graph=retain_graph)
+        if self._sync is not None:
+            self._sync(params)
+        norm = nn.utils.clip_grad_norm_(params, self._clip)
+        if self._wd:
+            with torch.no_grad():
+                for p in params:
+                    p.mul_(1 - self._wd)
+        self._opt.step()
+        self._opt.zero_grad(set_to_none=True)
+        metrics[f"{self._name}_grad_norm"] = norm.detach()
+        return metrics
+
+
+# --------------------------------------------------------------------------------------
+# initialisers (reference tools.py:890-946): truncated-normal variance scaling / uniform outscale
+# --------------------------------------------------------------------------------------
+def _fans(m):
+    if isinstance(m, nn.Linear):
+        return m.in_features, m.out_features
+    space = m.kernel_size[0] * m.kernel_size[1]
+    return space * m.in_channels, space * m.out_channels
+
+
+def weight_init(m):
+    if isinstance(m, (nn.Linear, nn.Conv2d, nn.ConvTranspose2d)):
+        fin, fout = _fans(m)
+        std = math.sqrt(2.0 / (fin + fout)) / 0.87962566103423978
+        nn.init.trunc_normal_(m.weight.data, mean=0.0, std=std, a=-2.0 * std, b=2.0 * std)
+        if m.bias is not None:
+            m.bias.data.zero_()
+    elif isinstance(m, nn.LayerNorm):
+        m.weight.data.fill_(1.0)
+        if m.bias is not None:
+            m.bias.data.zero_()
+
+
+def uniform_weight_init(given_scale):
+    def init(m):
+        if isinstance(m, (nn.Linear, nn.Conv2d, nn.ConvTranspose2d)):
+            fin, fout = _fans(m)
+            limit = math.sqrt(3 * given_scale * 2.0 / (fin + fout))
+            nn.init.uniform_(m.weight.data, a=-limit, b=limit)
+            if m.bias is not None:
+                m.bias.data.zero_()
+        elif isinstance(m, nn.LayerNorm):
+            m.weight.data.fill_(1.0)
+            if m.bias is not None:
+                m.bias.data.zero_()
+    return init

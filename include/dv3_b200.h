@@ -1,0 +1,365 @@
+/* dv3_b200.h -- C ABI of the B200-native DreamerV3 training hot path (libdv3_b200.so).
+ *
+ * The reference (ChenFengTsai/dreamerv3-torch) has no FFI: its boundary is the Python method
+ * surface RSSM.observe / imagine_with_action, ImagBehavior._imagine, tools.lambda_return,
+ * tools.DiscDist and RSSM.kl_loss.  Each entry point below names the reference code it
+ * replaces (file:line relative to the reference tree).  INTEGRATION.md shows the ctypes stub a
+ * reference maintainer would add.
+ *
+ * Conventions
+ *  - plain C: pointers and sizes only, no torch types.  All tensors are contiguous fp32 in
+ *    device memory (HBM) unless stated (int32 class indices), 16-byte aligned.
+ *  - the caller allocates every input / output / workspace buffer; the library owns no memory
+ *    and keeps no state between calls; parameters are read from the caller's storage each call.
+ *  - `stream` is a cudaStream_t passed as void*; every call only enqueues work on it (no host
+ *    sync) and is re-entrant per stream.
+ *  - return value: 0 on success, negative dv3_status otherwise; dv3_last_error() gives a
+ *    thread-local message.
+ *  - noise (uniforms / normals) is always an explicit input ("supplied uniforms" contract):
+ *    categorical draw idx = argmax_k probs_k / (-log u_k).
+ */
+#ifndef DV3_B200_H
+#define DV3_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DV3_ABI_VERSION 1
+
+typedef enum {
+  DV3_OK = 0,
+  DV3_ERR_BAD_SHAPE = -1,    /* unsupported / inconsistent dims */
+  DV3_ERR_NULL = -2,         /* required pointer is NULL */
+  DV3_ERR_CUDA = -3,         /* a CUDA runtime call failed (message has the cudaError string) */
+  DV3_ERR_WORKSPACE = -4     /* workspace too small */
+} dv3_status;
+
+int dv3_version(void);
+const char* dv3_last_error(void);
+/* compute capability major*10+minor of the current device, or negative on error */
+int dv3_device_arch(void);
+
+/* ------------------------------------------------------------------------------------------
+ * RSSM description (networks.py:13-97).  Weight layouts are PyTorch's [out, in] row-major,
+ * exactly the tensors in the reference state_dict.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t stoch;    /* S: number of categorical groups (dyn_stoch, 32)          */
+  int32_t classes;  /* C: classes per group (dyn_discrete, 32; must be <= 32)   */
+  int32_t deter;    /* D: GRU state width (dyn_deter)                           */
+  int32_t hidden;   /* Hd: dyn_hidden                                           */
+  int32_t actions;  /* A                                                        */
+  int32_t embed;    /* E: encoder output width                                  */
+  float unimix;     /* 0.01                                                     */
+  float ln_eps;     /* 1e-3                                                     */
+} dv3_rssm_dims;
+
+typedef struct {
+  const float* w_in;      /* _img_in_layers.0.weight        [Hd, S*C+A]  */
+  const float* ln_in_g;   /* _img_in_layers.1.weight        [Hd]         */
+  const float* ln_in_b;   /* _img_in_layers.1.bias          [Hd]         */
+  const float* w_gru;     /* _cell.layers.GRU_linear.weight [3D, Hd+D]   */
+  const float* ln_gru_g;  /* _cell.layers.GRU_norm.weight   [3D]         */
+  const float* ln_gru_b;  /* _cell.layers.GRU_norm.bias     [3D]         */
+  const float* w_out;     /* _img_out_layers.0.weight       [Hd, D]      */
+  const float* ln_out_g;  /* _img_out_layers.1.weight       [Hd]         */
+  const float* ln_out_b;  /* _img_out_layers.1.bias         [Hd]         */
+  const float* w_ims;     /* _imgs_stat_layer.weight        [S*C, Hd]    */
+  const float* b_ims;     /* _imgs_stat_layer.bias          [S*C]        */
+  const float* w_obs;     /* _obs_out_layers.0.weight       [Hd, D+E]    */
+  const float* ln_obs_g;  /* _obs_out_layers.1.weight       [Hd]         */
+  const float* ln_obs_b;  /* _obs_out_layers.1.bias         [Hd]         */
+  const float* w_os;      /* _obs_stat_layer.weight         [S*C, Hd]    */
+  const float* b_os;      /* _obs_stat_layer.bias           [S*C]        */
+  const float* w_init;    /* W                              [1, D]       */
+} dv3_rssm_params;
+
+/* ------------------------------------------------------------------------------------------
+ * observe: T-step posterior rollout.  Replaces RSSM.observe (networks.py:127-143) =
+ * tools.static_scan (tools.py:806-850) over RSSM.obs_step (networks.py:174-206), which calls
+ * RSSM.img_step (208-233), GRUCell.forward (760-768), _suff_stats_layer (241-250) and
+ * OneHotDist.sample (tools.py:452-460).
+ *
+ * Public tensors are batch-major [B,T,...] like the reference API; noise is time-major.
+ * The `sv_*` tensors are activations saved for dv3_observe_bwd (all [B,T,...] batch-major).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t B, T;
+  /* inputs */
+  const float* embed;      /* [B,T,E]   */
+  const float* action;     /* [B,T,A]   (never written; the reference zeroes is_first rows in place) */
+  const float* is_first;   /* [B,T]     0/1 */
+  const float* u_prior;    /* [T,B,S,C] uniforms in (0,1] for the prior draw  */
+  const float* u_post;     /* [T,B,S,C] uniforms for the posterior draw       */
+  const int32_t* state_idx;  /* optional [B,S]: class indices of a caller-supplied previous stoch, or NULL */
+  const float* state_deter;  /* optional [B,D], or NULL (=> step 0 starts from RSSM.initial for every row) */
+  /* outputs */
+  float* post_stoch;   /* [B,T,S,C] one-hot */
+  float* post_logit;   /* [B,T,S,C] */
+  float* prior_stoch;  /* [B,T,S,C] one-hot */
+  float* prior_logit;  /* [B,T,S,C] */
+  float* deter;        /* [B,T,D]   */
+  /* saved for backward */
+  int32_t* post_idx;   /* [B,T,S] */
+  int32_t* prior_idx;  /* [B,T,S] */
+  float* first_eff;    /* [B,T]    effective reset mask: is_first, and every row at t=0 if no state */
+  int32_t* sprev_idx;  /* [B,T,S]  previous-step stoch after the is_first mix */
+  float* hprev;        /* [B,T,D]  previous deter after the mix */
+  float* aprev;        /* [B,T,A]  action after the is_first zeroing */
+  float* x_pre;        /* [B,T,Hd] W_in [s,a] (pre LayerNorm) */
+  float* x;            /* [B,T,Hd] SiLU(LN(x_pre)) */
+  float* g_pre;        /* [B,T,3D] W_gru [x,h] (pre LayerNorm) */
+  float* y_pre;        /* [B,T,Hd] */
+  float* y;            /* [B,T,Hd] */
+  float* z_pre;        /* [B,T,Hd] */
+  float* z;            /* [B,T,Hd] */
+  /* RSSM.initial (networks.py:99-125) intermediates, one row */
+  float* init_deter;   /* [D]   tanh(W) */
+  float* init_ypre;    /* [Hd]  */
+  float* init_y;       /* [Hd]  */
+  float* init_logit;   /* [S*C] */
+  int32_t* init_idx;   /* [S]   argmax = mode */
+  /* scratch */
+  void* workspace;
+  size_t workspace_bytes;
+} dv3_observe_io;
+
+size_t dv3_observe_workspace_bytes(const dv3_rssm_dims* d, int32_t B, int32_t T);
+int dv3_observe_fwd(const dv3_rssm_dims* d, const dv3_rssm_params* p, const dv3_observe_io* io,
+                    void* stream);
+
+/* Backward of observe: BPTT through the T steps.  Consumes upstream gradients of the five
+ * public outputs (any may be NULL = zero) and produces d embed plus, for every Linear /
+ * LayerNorm on the path, the gradient w.r.t. its OUTPUT for all B*T rows ("deltas").  The
+ * caller turns deltas into parameter gradients with plain GEMMs (dW = delta^T @ input) --
+ * contractions over B*T = 1024 rows that do not sit inside the time loop.
+ * Straight-through estimator, unimix and the renormalisation inside torch's Categorical are
+ * differentiated exactly as autograd does for tools.py:436-460. */
+typedef struct {
+  int32_t B, T;
+  /* saved forward state: same tensors as dv3_observe_io */
+  const float* first_eff;
+  const float* post_logit;
+  const float* prior_logit;
+  const float* hprev;
+  const float* x_pre;
+  const float* g_pre;
+  const float* y_pre;
+  const float* z_pre;
+  /* upstream gradients, batch-major, NULL = zeros */
+  const float* g_post_stoch;   /* [B,T,S,C] */
+  const float* g_post_logit;   /* [B,T,S,C] */
+  const float* g_prior_stoch;  /* [B,T,S,C] */
+  const float* g_prior_logit;  /* [B,T,S,C] */
+  const float* g_deter;        /* [B,T,D]   */
+  /* outputs */
+  float* d_embed;      /* [B,T,E] */
+  float* d_x_pre;      /* [B,T,Hd]  delta of _img_in_layers.0 output   */
+  float* d_x_ln;       /* [B,T,Hd]  grad wrt LayerNorm affine output   */
+  float* d_g_pre;      /* [B,T,3D]  delta of GRU_linear output         */
+  float* d_g_ln;       /* [B,T,3D]  */
+  float* d_y_pre;      /* [B,T,Hd]  */
+  float* d_y_ln;       /* [B,T,Hd]  */
+  float* d_z_pre;      /* [B,T,Hd]  */
+  float* d_z_ln;       /* [B,T,Hd]  */
+  float* d_post_logit; /* [B,T,S*C] delta of _obs_stat_layer output    */
+  float* d_prior_logit;/* [B,T,S*C] delta of _imgs_stat_layer output   */
+  float* d_init_stoch; /* [S*C]  summed grad reaching RSSM.initial's stoch */
+  float* d_init_deter; /* [D]    summed grad reaching RSSM.initial's deter */
+  float* d_state_deter;/* optional [B,D]: grad wrt caller-supplied state deter, or NULL */
+  float* d_state_stoch;/* optional [B,S*C]: grad wrt caller-supplied state stoch, or NULL */
+  void* workspace;
+  size_t workspace_bytes;
+} dv3_observe_bwd_io;
+
+size_t dv3_observe_bwd_workspace_bytes(const dv3_rssm_dims* d, int32_t B, int32_t T);
+int dv3_observe_bwd(const dv3_rssm_dims* d, const dv3_rssm_params* p,
+                    const dv3_observe_bwd_io* io, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * imagine: H-step actor-in-the-loop prior rollout from N start states.  Replaces
+ * ImagBehavior._imagine (models.py:448-548) with policy = actor MLP (networks.py:657-700);
+ * with actor == NULL and given actions it is RSSM.imagine_with_action (networks.py:145-152).
+ * Time-major [H,N,...] like the reference.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t layers;        /* trunk layers (2 or 5) */
+  int32_t units;         /* U */
+  int32_t dist;          /* 0 = 'normal' (tanh mean, learned std, clip 1.0), 1 = 'onehot' */
+  float min_std, max_std;/* 0.1, 1.0 */
+  float unimix;          /* 0.01 (onehot) */
+  const float* const* w;     /* [layers] Actor_linear{i}.weight: [U, F] then [U, U]  */
+  const float* const* ln_g;  /* [layers] Actor_norm{i}.weight [U] */
+  const float* const* ln_b;  /* [layers] */
+  const float* w_mean; const float* b_mean;  /* mean_layer [A, U], [A] */
+  const float* w_std;  const float* b_std;   /* std_layer  [A, U], [A] (normal only) */
+} dv3_actor;
+
+typedef struct {
+  int32_t N, H;
+  /* inputs */
+  const int32_t* start_idx;   /* [N,S]  class indices of the (one-hot) start stoch */
+  const float* start_deter;   /* [N,D]  */
+  const float* act_noise;     /* [H,N,A] N(0,1) draws (normal) or uniforms (onehot); unused if actor==NULL */
+  const float* u_state;       /* [H,N,S,C] uniforms for the prior draws (last step's are not consumed) */
+  const float* given_action;  /* [H-1,N,A] when actor == NULL (action k drives state k -> k+1) */
+  /* outputs: state k for k=0..H-1 where state 0 = start, action k, feat k */
+  float* feat;        /* [H,N,S*C+D] = [one-hot stoch | deter]  (row k is also states.stoch/deter k) */
+  float* logit;       /* [H,N,S,C]  rows 1..H-1 (row 0 is the caller's start logit, not written) */
+  float* action;      /* [H,N,A] */
+  int32_t* idx;       /* [H,N,S]  class indices of state k (row 0 copies start_idx) */
+  /* saved for backward (rows k = step k, i.e. the transition state k -> k+1; row H-1 unused) */
+  float* x_pre; float* x;        /* [H,N,Hd] */
+  float* g_pre;                  /* [H,N,3D] */
+  float* y_pre; float* y;        /* [H,N,Hd] */
+  float* a_pre;       /* [layers,H,N,U] actor trunk pre-LN */
+  float* a_act;       /* [layers,H,N,U] actor trunk post-SiLU */
+  float* a_mean_raw;  /* [H,N,A] mean_layer output (logits for onehot) */
+  float* a_std_raw;   /* [H,N,A] (normal only) */
+  void* workspace; size_t workspace_bytes;
+} dv3_imagine_io;
+
+/* single steps, exported for teacher-forced parity checks and for acting:
+ *   dv3_obs_step_fwd = RSSM.obs_step (networks.py:174-206): observe io with T == 1 + state
+ *   dv3_img_step_fwd = RSSM.img_step (networks.py:208-233): imagine io with H == 2, given_action */
+int dv3_obs_step_fwd(const dv3_rssm_dims* d, const dv3_rssm_params* p, const dv3_observe_io* io,
+                     void* stream);
+size_t dv3_imagine_workspace_bytes(const dv3_rssm_dims* d, const dv3_actor* a, int32_t N, int32_t H);
+int dv3_imagine_fwd(const dv3_rssm_dims* d, const dv3_rssm_params* p, const dv3_actor* a,
+                    const dv3_imagine_io* io, void* stream);
+int dv3_img_step_fwd(const dv3_rssm_dims* d, const dv3_rssm_params* p, const dv3_imagine_io* io,
+                     void* stream);
+
+/* Backward of imagine ('dynamics' gradient, models.py:513-517 with feat detached): BPTT through
+ * img_step w.r.t. activations, producing the gradient reaching each sampled action and from it
+ * the deltas of the actor heads.  RSSM deltas are produced too (for callers that train the
+ * world model through imagination); the actor trunk backward is not recurrent (its input is
+ * detached) and is done by the caller in bulk over H*N rows. */
+typedef struct {
+  int32_t N, H;
+  const float* logit;          /* [H,N,S,C] as written by imagine_fwd (row 0 unused) */
+  const float* feat;           /* [H,N,F] */
+  const float* x_pre; const float* g_pre; const float* y_pre;
+  const float* a_mean_raw; const float* a_std_raw; const float* act_noise;
+  /* upstream grads (time-major, NULL = zeros) */
+  const float* g_stoch;   /* [H,N,S,C] grad wrt states.stoch */
+  const float* g_deter;   /* [H,N,D]   grad wrt states.deter */
+  const float* g_logit;   /* [H,N,S,C] grad wrt states.logit (rows >= 1) */
+  const float* g_action;  /* [H,N,A]   grad wrt returned actions */
+  /* outputs */
+  float* d_mean_raw;      /* [H,N,A] delta of actor mean_layer output */
+  float* d_std_raw;       /* [H,N,A] */
+  float* d_x_pre; float* d_x_ln;   /* [H,N,Hd] (rows 0..H-2) */
+  float* d_g_pre; float* d_g_ln;   /* [H,N,3D] */
+  float* d_y_pre; float* d_y_ln;   /* [H,N,Hd] */
+  float* d_logit;                  /* [H,N,S*C] delta of _imgs_stat_layer output (rows 1..H-1) */
+  float* d_start_stoch;            /* [N,S*C] grad wrt start stoch */
+  float* d_start_deter;            /* [N,D]   */
+  void* workspace; size_t workspace_bytes;
+} dv3_imagine_bwd_io;
+
+size_t dv3_imagine_bwd_workspace_bytes(const dv3_rssm_dims* d, const dv3_actor* a, int32_t N, int32_t H);
+int dv3_imagine_bwd(const dv3_rssm_dims* d, const dv3_rssm_params* p, const dv3_actor* a,
+                    const dv3_imagine_bwd_io* io, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * lambda return.  Replaces tools.lambda_return + static_scan_for_lambda_return
+ * (tools.py:682-728).  Time-major [H,N]; bootstrap [N].
+ *   R_t = r_t + c_t * ((1-lambda) * v_{t+1} + lambda * R_{t+1}),  v_H = R_H = bootstrap.
+ * lambda_ is a double so that (1-lambda) is rounded to fp32 once, as the reference's Python
+ * scalar is (bit-identical fp32 results).
+ * ---------------------------------------------------------------------------------------- */
+int dv3_lambda_return_fwd(const float* reward, const float* value, const float* pcont,
+                          const float* bootstrap, double lambda_, int32_t H, int32_t N,
+                          float* ret, void* stream);
+int dv3_lambda_return_bwd(const float* value, const float* pcont, const float* bootstrap,
+                          const float* ret, const float* g_ret, double lambda_, int32_t H,
+                          int32_t N, float* d_reward, float* d_value, float* d_pcont,
+                          float* d_bootstrap, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * symlog two-hot head.  Replaces tools.DiscDist.log_prob / mean / mode (tools.py:463-513) with
+ * tools.symlog / symexp (22-27).  logits [R,K] (K = 255), x [R], buckets [K] (pass the tensor
+ * torch.linspace(-20,20,255) built so bucket values are bit-identical to the reference's).
+ * ---------------------------------------------------------------------------------------- */
+int dv3_twohot_logprob_fwd(const float* logits, const float* x, const float* buckets, int32_t R,
+                           int32_t K, float* logprob, void* stream);
+int dv3_twohot_logprob_bwd(const float* logits, const float* x, const float* buckets,
+                           const float* g_logprob, int32_t R, int32_t K, float* d_logits,
+                           void* stream);
+int dv3_twohot_mean_fwd(const float* logits, const float* buckets, int32_t R, int32_t K,
+                        float* mean, void* stream);
+int dv3_twohot_mean_bwd(const float* logits, const float* buckets, const float* g_mean, int32_t R,
+                        int32_t K, float* d_logits, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * KL balance.  Replaces RSSM.kl_loss (networks.py:272-290) over
+ * Independent(OneHotDist(unimix),1) with torch's categorical KL.  logits [R,S,C].
+ * outputs [R]: loss = dyn_scale*max(dyn,free) + rep_scale*max(rep,free); value = raw KL;
+ * post_ent / prior_ent = entropies (the metrics of models.py:156-168).  Backward takes the
+ * gradient of `loss` only (value/dyn/rep/entropies are metrics).
+ * ---------------------------------------------------------------------------------------- */
+int dv3_kl_balance_fwd(const float* post_logit, const float* prior_logit, int32_t R, int32_t S,
+                       int32_t C, float unimix, float free_nats, float dyn_scale, float rep_scale,
+                       float* loss, float* value, float* dyn, float* rep, float* post_ent,
+                       float* prior_ent, void* stream);
+int dv3_kl_balance_bwd(const float* post_logit, const float* prior_logit, const float* g_loss,
+                       int32_t R, int32_t S, int32_t C, float unimix, float free_nats,
+                       float dyn_scale, float rep_scale, float* d_post_logit,
+                       float* d_prior_logit, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Building blocks (the kernels the ops above are made of), exported so that the host side can
+ * run the non-recurrent bulk parts (actor trunk backward over H*N rows, parameter-gradient
+ * reductions) and so that each kernel is testable against the oracle in isolation.
+ * ---------------------------------------------------------------------------------------- */
+/* C[M,N] (ldc) = [A1|A2] W^T + bias + addend;  W = [W1|W2] given as two K-segments of one
+ * [N, *] row-major weight (A2/W2 may be NULL).  accumulate != 0 adds into C.  K1,K2 % 4 == 0. */
+int dv3_linear_fwd(const float* A1, int32_t lda1, const float* W1, int32_t ldw1, int32_t K1,
+                   const float* A2, int32_t lda2, const float* W2, int32_t ldw2, int32_t K2,
+                   const float* bias, const float* addend, int32_t ldadd, float* C, int32_t ldc,
+                   int32_t M, int32_t N, int32_t accumulate, void* stream);
+/* out[C,R] = in[R,C]^T  (in has row stride ld) */
+int dv3_transpose(const float* in, int32_t ld, int32_t R, int32_t C, float* out, void* stream);
+/* out = SiLU(LayerNorm(pre)) row-wise; networks.py:48-58 (Linear->LN->SiLU blocks) */
+int dv3_ln_silu_fwd(const float* pre, int32_t ld, const float* g, const float* b, float eps,
+                    int32_t M, int32_t n, float* out, int32_t ldo, void* stream);
+int dv3_ln_silu_bwd(const float* pre, int32_t ld, const float* g, const float* b, float eps,
+                    const float* d_out, int32_t ldd, int32_t M, int32_t n, float* d_pre,
+                    float* d_ln, int32_t ldp, void* stream);
+/* LayerNorm-GRU gate block (networks.py:760-768): parts = LN_3D(g_pre); r = sig(p0);
+ * c = tanh(r*p1); u = sig(p2 - 1); h_new = u*c + (1-u)*h.  bwd also returns d_g_ln (gradient
+ * w.r.t. the LayerNorm affine output) and d_h = the direct (1-u) path only. */
+int dv3_gru_gates_fwd(const float* g_pre, int32_t ldg, const float* g, const float* b, float eps,
+                      const float* h, int32_t ldh, int32_t M, int32_t D, float* h_new, int32_t ldn,
+                      void* stream);
+int dv3_gru_gates_bwd(const float* g_pre, int32_t ldg, const float* g, const float* b, float eps,
+                      const float* h, int32_t ldh, const float* d_h_new, int32_t ldd, int32_t M,
+                      int32_t D, float* d_g_pre, float* d_g_ln, int32_t ldp, float* d_h,
+                      int32_t ldo, void* stream);
+/* Linear over a one-hot input fused with LN+SiLU: pre = addend + sum_s WT[s*C+idx[s]] +
+ * act @ WT[S*C:], out = SiLU(LN(pre)).  WT is the TRANSPOSED weight [S*C+A, n]; idx [M,S];
+ * act [M,A] or NULL; addend [M,n] or NULL.  (networks.py:48-58 applied to cat(one-hot, action)) */
+int dv3_onehot_linear_ln_silu(const int32_t* idx, int32_t S, int32_t C, const float* act,
+                              int32_t A, const float* WT, const float* addend, const float* g,
+                              const float* b, float eps, int32_t M, int32_t n, float* pre,
+                              float* out, void* stream);
+/* unimix categorical draw / mode for logits [M,S,C] (C<=32): idx [M,S] and optional one-hot.
+ * u == NULL -> mode (first argmax).  tools.py:436-460 */
+int dv3_onehot_sample(const float* logits, const float* u, float unimix, int32_t M, int32_t S,
+                      int32_t C, int32_t* idx, float* onehot, int32_t ld_onehot, void* stream);
+/* d_logits = ext + straight-through backward of a sample whose value-grad is g_sample */
+int dv3_onehot_st_bwd(const float* logits, const float* g_sample, const float* ext, float unimix,
+                      int32_t M, int32_t S, int32_t C, float* d_logits, void* stream);
+/* one-hot fp32 [M,S*C] (row stride ld) from indices [M,S] */
+int dv3_idx_to_onehot(const int32_t* idx, int32_t M, int32_t S, int32_t C, float* out, int32_t ld,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DV3_B200_H */

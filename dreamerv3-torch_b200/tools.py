@@ -40,8 +40,9 @@ def lambda_return_stacked(reward, value, pcont, bootstrap, lambda_):
         pcont = pcont * torch.ones_like(reward)
     if bootstrap is None:
         bootstrap = torch.zeros_like(value[-1])
-    ret = K.lambda_return_hn(reward.reshape(H, -1), value.reshape(H, -1), pcont.reshape(H, -1),
-                             bootstrap.reshape(-1), lambda_)
+    N = int(np.prod(shape[1:])) if len(shape) > 1 else 1
+    ret = K.lambda_return_hn(reward.reshape(H, N), value.reshape(H, N), pcont.reshape(H, N),
+                             bootstrap.reshape(N), lambda_)
     return ret.reshape(shape)
 
 

@@ -64,13 +64,13 @@ def lambda_return_case(pkg, device, H=14, N=1024, seed=0):
     dev = [t.clone().to(device).requires_grad_(True) for t in (r, v, c, b)]
     out = pkg.tools.lambda_return_stacked(*dev, 0.95)
     (out * w.to(device)).sum().backward()
-    res = {"ret_maxabs": float((out.cpu() - ref).abs().max())}
+    res = {"ret_maxabs": float((out.detach().cpu() - ref.detach()).abs().max())}
     for name, a, bb in zip(("d_reward", "d_value", "d_pcont", "d_bootstrap"), dev, cpu):
         res[name] = rel(a.grad, bb.grad)
     tup = pkg.tools.lambda_return(dev[0], dev[1], dev[2], dev[3], 0.95, axis=0)
     res["tuple_len"] = len(tup)
     res["tuple_shape"] = tuple(tup[0].shape)
-    res["tuple_maxabs"] = float((torch.stack(tup, dim=1).cpu() - ref).abs().max())
+    res["tuple_maxabs"] = float((torch.stack(tup, dim=1).detach().cpu() - ref.detach()).abs().max())
     return res
 
 

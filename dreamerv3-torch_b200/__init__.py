@@ -13,6 +13,6 @@ ImagBehavior).  ``kernels`` holds the autograd bindings and ``_lib`` the ctypes 
 libdv3_b200.so; there is no CPU fallback -- calling a hot-path op without the built library
 raises ``_lib.Dv3Error``.
 """
-from . import _lib, kernels, tools, networks, models  # noqa: F401
+from . import _lib, kernels, tools, networks, models, configs  # noqa: F401
 
-__all__ = ["_lib", "kernels", "tools", "networks", "models"]
+__all__ = ["_lib", "kernels", "tools", "networks", "models", "configs"]

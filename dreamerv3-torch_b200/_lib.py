@@ -122,6 +122,9 @@ SIGNATURES = {
     "dv3_version": (C.c_int, []),
     "dv3_last_error": (C.c_char_p, []),
     "dv3_device_arch": (C.c_int, []),
+    "dv3_launch_count": (C.c_longlong, []),
+    "dv3_prof_enable": (None, [C.c_int]),
+    "dv3_prof_read": (C.c_int, [_P(C.c_double), _P(C.c_double), _P(C.c_longlong)]),
     "dv3_observe_workspace_bytes": (C.c_size_t, [_P(RssmDims), _i32, _i32]),
     "dv3_observe_fwd": (C.c_int, [_P(RssmDims), _P(RssmParams), _P(ObserveIO), _v]),
     "dv3_obs_step_fwd": (C.c_int, [_P(RssmDims), _P(RssmParams), _P(ObserveIO), _v]),

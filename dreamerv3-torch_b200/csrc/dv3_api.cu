@@ -1,6 +1,9 @@
 // Library-level entry points: version, thread-local error text, device probe, and the
 // single-step wrappers (obs_step / img_step) over the sequence kernels.
 #include <stdarg.h>
+#include <atomic>
+#include <mutex>
+#include <vector>
 #include "dv3_common.cuh"
 
 namespace dv3 {
@@ -19,7 +22,61 @@ int cuda_fail(cudaError_t e, const char* what) {
   return DV3_ERR_CUDA;
 }
 
+// ---- launch counter + optional GEMM timing --------------------------------------------
+static std::atomic<long long> g_launches{0};
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+struct ProfRec { cudaEvent_t a, b; int kind; double flops; };
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static std::vector<cudaEvent_t> g_pool;
+static cudaEvent_t g_cur = nullptr;
+
+static cudaEvent_t take_event() {
+  if (!g_pool.empty()) { cudaEvent_t e = g_pool.back(); g_pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+bool prof_on() { return g_prof_on; }
+void prof_begin(cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_cur = take_event();
+  cudaEventRecord(g_cur, st);
+}
+void prof_end(cudaStream_t st, int kind, double flops) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  cudaEvent_t b = take_event();
+  cudaEventRecord(b, st);
+  g_prof.push_back({g_cur, b, kind, flops});
+  g_cur = nullptr;
+}
+
 }  // namespace dv3
+
+extern "C" long long dv3_launch_count(void) { return dv3::g_launches.load(); }
+
+extern "C" void dv3_prof_enable(int on) {
+  std::lock_guard<std::mutex> lk(dv3::g_prof_mu);
+  dv3::g_prof_on = on != 0;
+}
+
+// Sums the CUDA-event durations recorded since the last read, per GEMM kind (0 skinny, 1 tiled),
+// waits for the recorded events, and clears the record.  Arrays have 2 entries.
+extern "C" int dv3_prof_read(double* ms, double* flops, long long* launches) {
+  std::lock_guard<std::mutex> lk(dv3::g_prof_mu);
+  for (int k = 0; k < 2; ++k) { ms[k] = 0; flops[k] = 0; launches[k] = 0; }
+  for (auto& r : dv3::g_prof) {
+    DV3_CHECK_CUDA(cudaEventSynchronize(r.b));
+    float t = 0.f;
+    DV3_CHECK_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+    ms[r.kind] += t; flops[r.kind] += r.flops; launches[r.kind] += 1;
+    dv3::g_pool.push_back(r.a); dv3::g_pool.push_back(r.b);
+  }
+  dv3::g_prof.clear();
+  return 0;
+}
 
 extern "C" int dv3_version(void) { return DV3_ABI_VERSION; }
 

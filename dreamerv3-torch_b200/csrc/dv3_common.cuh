@@ -14,6 +14,11 @@ namespace dv3 {
 
 // ---- host error state -------------------------------------------------------------------
 void set_error(const char* fmt, ...);
+void note_launch();
+// optional CUDA-event timing of the GEMM launches (dv3_prof_*): kind 0 = skinny, 1 = tiled
+bool prof_on();
+void prof_begin(cudaStream_t st);
+void prof_end(cudaStream_t st, int kind, double flops);
 int cuda_fail(cudaError_t e, const char* what);
 
 #define DV3_CHECK_CUDA(expr)                                   \
@@ -22,10 +27,12 @@ int cuda_fail(cudaError_t e, const char* what);
     if (_e != cudaSuccess) return ::dv3::cuda_fail(_e, #expr); \
   } while (0)
 
+// every kernel launch of the library goes through this macro: error check + launch counter
 #define DV3_CHECK_LAUNCH(name)                                   \
   do {                                                           \
     cudaError_t _e = cudaGetLastError();                         \
     if (_e != cudaSuccess) return ::dv3::cuda_fail(_e, name);    \
+    ::dv3::note_launch();                                        \
   } while (0)
 
 #define DV3_REQUIRE(cond, code, ...)   \

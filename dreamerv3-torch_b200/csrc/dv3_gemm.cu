@@ -229,17 +229,23 @@ int launch_linear(const LinearArgs& g, cudaStream_t st) {
     vec = vec && (g.K[s] % 4 == 0) && (g.lda[s] % 4 == 0) && (g.ldw[s] % 4 == 0) &&
           aligned16(g.A[s]) && aligned16(g.W[s]);
   }
+  const bool prof = prof_on();
+  const double flops = 2.0 * g.M * g.N * ((g.A[0] ? g.K[0] : 0) + (g.A[1] ? g.K[1] : 0));
   if (g.M <= 2 * SK_ROWS && vec) {
     dim3 grid((g.N + SK_WARPS * SK_CPW - 1) / (SK_WARPS * SK_CPW), (g.M + SK_ROWS - 1) / SK_ROWS);
+    if (prof) prof_begin(st);
     linear_skinny_kernel<<<grid, SK_WARPS * 32, 0, st>>>(g);
+    if (prof) prof_end(st, 0, flops);
     DV3_CHECK_LAUNCH("linear_skinny_kernel");
     return 0;
   }
   dim3 grid((g.N + TB_N - 1) / TB_N, (g.M + TB_M - 1) / TB_M);
+  if (prof) prof_begin(st);
   if (vec)
     linear_tiled_kernel<true><<<grid, 256, 0, st>>>(g);
   else
     linear_tiled_kernel<false><<<grid, 256, 0, st>>>(g);
+  if (prof) prof_end(st, 1, flops);
   DV3_CHECK_LAUNCH("linear_tiled_kernel");
   return 0;
 }

@@ -377,10 +377,10 @@ using namespace dv3;
 extern "C" int dv3_lambda_return_fwd(const float* reward, const float* value, const float* pcont,
                                      const float* bootstrap, double lambda_, int32_t H, int32_t N,
                                      float* ret, void* stream) {
+  DV3_REQUIRE(H >= 0 && N >= 0, DV3_ERR_BAD_SHAPE, "lambda_return_fwd: H=%d N=%d", H, N);
+  if (H == 0 || N == 0) return 0;  // empty horizon / batch: nothing to write
   DV3_REQUIRE(reward && value && pcont && bootstrap && ret, DV3_ERR_NULL,
               "lambda_return_fwd: null pointer");
-  DV3_REQUIRE(H >= 0 && N >= 0, DV3_ERR_BAD_SHAPE, "lambda_return_fwd: H=%d N=%d", H, N);
-  if (H == 0 || N == 0) return 0;
   lambda_return_fwd_kernel<<<(N + 127) / 128, 128, 0, ST(stream)>>>(reward, value, pcont,
                                                                     bootstrap, (float)lambda_,
                                                                     (float)(1.0 - lambda_), H, N,
@@ -394,10 +394,10 @@ extern "C" int dv3_lambda_return_bwd(const float* value, const float* pcont,
                                      double lambda_, int32_t H, int32_t N, float* d_reward,
                                      float* d_value, float* d_pcont, float* d_bootstrap,
                                      void* stream) {
-  DV3_REQUIRE(value && pcont && bootstrap && ret && g_ret, DV3_ERR_NULL,
-              "lambda_return_bwd: null pointer");
   DV3_REQUIRE(H >= 0 && N >= 0, DV3_ERR_BAD_SHAPE, "lambda_return_bwd: H=%d N=%d", H, N);
   if (H == 0 || N == 0) return 0;
+  DV3_REQUIRE(value && pcont && bootstrap && ret && g_ret, DV3_ERR_NULL,
+              "lambda_return_bwd: null pointer");
   lambda_return_bwd_kernel<<<(N + 127) / 128, 128, 0, ST(stream)>>>(
       value, pcont, bootstrap, ret, g_ret, (float)lambda_, (float)(1.0 - lambda_), H, N, d_reward,
       d_value, d_pcont, d_bootstrap);
@@ -407,17 +407,17 @@ extern "C" int dv3_lambda_return_bwd(const float* value, const float* pcont,
 
 static int twohot_check(const void* a, const void* b, const void* c, int R, int K,
                         const char* who) {
-  DV3_REQUIRE(a && b && c, DV3_ERR_NULL, "%s: null pointer", who);
   DV3_REQUIRE(R >= 0 && K >= 2 && K <= 32 * TH_MAXPER, DV3_ERR_BAD_SHAPE, "%s: R=%d K=%d (K<=256)",
               who, R, K);
+  DV3_REQUIRE(R == 0 || (a && b && c), DV3_ERR_NULL, "%s: null pointer", who);
   return 0;
 }
 
 extern "C" int dv3_twohot_logprob_fwd(const float* logits, const float* x, const float* buckets,
                                       int32_t R, int32_t K, float* logprob, void* stream) {
   DV3_TRY(twohot_check(logits, x, buckets, R, K, "twohot_logprob_fwd"));
-  DV3_REQUIRE(logprob, DV3_ERR_NULL, "twohot_logprob_fwd: null output");
   if (R == 0) return 0;
+  DV3_REQUIRE(logprob, DV3_ERR_NULL, "twohot_logprob_fwd: null output");
   twohot_logprob_fwd_kernel<<<(R + 7) / 8, 256, 0, ST(stream)>>>(logits, x, buckets, R, K, logprob);
   DV3_CHECK_LAUNCH("twohot_logprob_fwd_kernel");
   return 0;
@@ -427,8 +427,8 @@ extern "C" int dv3_twohot_logprob_bwd(const float* logits, const float* x, const
                                       const float* g_logprob, int32_t R, int32_t K,
                                       float* d_logits, void* stream) {
   DV3_TRY(twohot_check(logits, x, buckets, R, K, "twohot_logprob_bwd"));
-  DV3_REQUIRE(g_logprob && d_logits, DV3_ERR_NULL, "twohot_logprob_bwd: null pointer");
   if (R == 0) return 0;
+  DV3_REQUIRE(g_logprob && d_logits, DV3_ERR_NULL, "twohot_logprob_bwd: null pointer");
   twohot_logprob_bwd_kernel<<<(R + 7) / 8, 256, 0, ST(stream)>>>(logits, x, buckets, g_logprob, R,
                                                                  K, d_logits);
   DV3_CHECK_LAUNCH("twohot_logprob_bwd_kernel");
@@ -447,8 +447,8 @@ extern "C" int dv3_twohot_mean_fwd(const float* logits, const float* buckets, in
 extern "C" int dv3_twohot_mean_bwd(const float* logits, const float* buckets, const float* g_mean,
                                    int32_t R, int32_t K, float* d_logits, void* stream) {
   DV3_TRY(twohot_check(logits, buckets, g_mean, R, K, "twohot_mean_bwd"));
-  DV3_REQUIRE(d_logits, DV3_ERR_NULL, "twohot_mean_bwd: null output");
   if (R == 0) return 0;
+  DV3_REQUIRE(d_logits, DV3_ERR_NULL, "twohot_mean_bwd: null output");
   twohot_mean_bwd_kernel<<<(R + 7) / 8, 256, 0, ST(stream)>>>(logits, buckets, g_mean, R, K,
                                                               d_logits);
   DV3_CHECK_LAUNCH("twohot_mean_bwd_kernel");
@@ -460,10 +460,10 @@ extern "C" int dv3_kl_balance_fwd(const float* post_logit, const float* prior_lo
                                   float dyn_scale, float rep_scale, float* loss, float* value,
                                   float* dyn, float* rep, float* post_ent, float* prior_ent,
                                   void* stream) {
-  DV3_REQUIRE(post_logit && prior_logit, DV3_ERR_NULL, "kl_balance_fwd: null pointer");
   DV3_REQUIRE(R >= 0 && S >= 1 && S <= 32 && C >= 1 && C <= 32, DV3_ERR_BAD_SHAPE,
               "kl_balance_fwd: R=%d S=%d C=%d (S,C <= 32)", R, S, C);
   if (R == 0) return 0;
+  DV3_REQUIRE(post_logit && prior_logit, DV3_ERR_NULL, "kl_balance_fwd: null pointer");
   kl_balance_fwd_kernel<<<R, S * 32, 0, ST(stream)>>>(post_logit, prior_logit, S, C, unimix,
                                                       free_nats, dyn_scale, rep_scale, loss, value,
                                                       dyn, rep, post_ent, prior_ent);
@@ -475,10 +475,10 @@ extern "C" int dv3_kl_balance_bwd(const float* post_logit, const float* prior_lo
                                   const float* g_loss, int32_t R, int32_t S, int32_t C,
                                   float unimix, float free_nats, float dyn_scale, float rep_scale,
                                   float* d_post_logit, float* d_prior_logit, void* stream) {
-  DV3_REQUIRE(post_logit && prior_logit && g_loss, DV3_ERR_NULL, "kl_balance_bwd: null pointer");
   DV3_REQUIRE(R >= 0 && S >= 1 && S <= 32 && C >= 1 && C <= 32, DV3_ERR_BAD_SHAPE,
               "kl_balance_bwd: R=%d S=%d C=%d (S,C <= 32)", R, S, C);
   if (R == 0) return 0;
+  DV3_REQUIRE(post_logit && prior_logit && g_loss, DV3_ERR_NULL, "kl_balance_bwd: null pointer");
   kl_balance_bwd_kernel<<<R, S * 32, 0, ST(stream)>>>(post_logit, prior_logit, g_loss, S, C,
                                                       unimix, free_nats, dyn_scale, rep_scale,
                                                       d_post_logit, d_prior_logit);

@@ -212,9 +212,10 @@ class ImagBehavior(nn.Module):
         return feat.detach(), states, action
 
     # ---- training step -------------------------------------------------------------------
-    def _train(self, start, objective, noise=None):
+    def losses(self, start, objective, noise=None):
+        """Forward of the behaviour step (reference models.py:327-429) without the optimizer
+        calls -> (actor_loss, value_loss, rollout tuple, metrics of device tensors, aux)."""
         cfg = self._config
-        self._update_slow_target()
         metrics = {}
         with tools.RequiresGrad(self.actor):
             imag_feat, imag_state, imag_action = self._imagine(start, self.actor,
@@ -244,9 +245,17 @@ class ImagBehavior(nn.Module):
         else:
             metrics.update(tools.tensorstats(imag_action, "imag_action"))
         metrics["actor_entropy"] = torch.mean(actor_ent.detach())
+        aux = dict(reward=reward, target=target, value=value)
+        return actor_loss, value_loss, (imag_feat, imag_state, imag_action, weights), metrics, aux
+
+    def _train(self, start, objective, noise=None):
+        cfg = self._config
+        self._update_slow_target()
+        actor_loss, value_loss, roll, metrics, _ = self.losses(start, objective, noise)
         with tools.RequiresGrad(self):
             metrics.update(self._actor_opt(actor_loss, self.actor.parameters()))
             metrics.update(self._value_opt(value_loss, self.value.parameters()))
+        imag_feat, imag_state, imag_action, weights = roll
         if not getattr(cfg, "device_metrics", False):
             metrics = tools.to_host(metrics)
         return imag_feat, imag_state, imag_action, weights, metrics

@@ -42,6 +42,14 @@ int dv3_version(void);
 const char* dv3_last_error(void);
 /* compute capability major*10+minor of the current device, or negative on error */
 int dv3_device_arch(void);
+/* number of kernels this library has launched in this process (all entry points) */
+long long dv3_launch_count(void);
+/* measurement aid for bench.py: when enabled, every GEMM launch is bracketed by CUDA events on
+ * the caller's stream; dv3_prof_read waits for them and returns, per GEMM kind (index 0 = skinny
+ * M<=32 kernel, 1 = tiled kernel), the summed device time in ms, the summed 2*M*N*K flops and
+ * the launch count since the previous read.  Not capturable into a CUDA graph while enabled. */
+void dv3_prof_enable(int on);
+int dv3_prof_read(double* ms, double* flops, long long* launches);
 
 /* ------------------------------------------------------------------------------------------
  * RSSM description (networks.py:13-97).  Weight layouts are PyTorch's [out, in] row-major,

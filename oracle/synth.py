@@ -124,3 +124,66 @@ def imagine_inputs(d: RSSMDims, N, H, seed=0, actor_dist="normal"):
         act_noise = uniforms(g, H, N, d.actions)
     u_state = uniforms(g, H, N, d.stoch, d.classes)
     return start, act_noise, u_state
+
+
+# --------------------------------------------------------------------------------------
+# whole-agent parameter sets (reference state_dict keys of WorldModel / actor / value)
+# --------------------------------------------------------------------------------------
+PROPRIO_KEYS = {"orientations": 14, "height": 1, "velocity": 9}
+
+
+def agent_params(config="dmc_proprio", seed=0, enc_units=1024, enc_layers=5, head_layers=2):
+    """-> (P_wm, P_actor, P_value) for the proprio suites (MLP encoder / decoder)."""
+    c = CONFIGS[config]
+    d = dims_of(config)
+    F_ = d.flat + d.deter
+    U = c["units"]
+    g = torch.Generator().manual_seed(seed + 300)
+    P = {}
+    obs = sum(PROPRIO_KEYS.values())
+    enc = mlp_params("Encoder", obs, enc_units, enc_layers, 1, seed + 1)
+    P.update({"encoder._mlp." + k: v for k, v in enc.items() if not k.startswith("mean_layer")})
+    P.update({"dynamics." + k: v for k, v in rssm_params(d, seed).items()})
+    dec = mlp_params("Decoder", F_, enc_units, enc_layers, 1, seed + 2)
+    P.update({"heads.decoder._mlp." + k: v for k, v in dec.items()
+              if not k.startswith("mean_layer")})
+    for k, n in PROPRIO_KEYS.items():
+        P[f"heads.decoder._mlp.mean_layer.{k}.weight"] = _lin(g, n, enc_units)
+        P[f"heads.decoder._mlp.mean_layer.{k}.bias"] = 0.1 * torch.randn(n, generator=g)
+    P.update({"heads.reward." + k: v
+              for k, v in mlp_params("Reward", F_, U, head_layers, 255, seed + 3, out_scale=0.3).items()})
+    P.update({"heads.cont." + k: v
+              for k, v in mlp_params("Cont", F_, U, head_layers, 1, seed + 4).items()})
+    P_actor = actor_params(config, seed + 5)
+    P_value = mlp_params("Value", F_, U, head_layers, 255, seed + 6, out_scale=0.3)
+    return P, P_actor, P_value
+
+
+def replay_batch(d: RSSMDims, B=16, T=64, seed=0, resets=(), onehot_action=False):
+    """SURVEY.md 8d synthetic replay batch as a numpy dict (what the reference's dataset yields)."""
+    import numpy as np
+    rs = np.random.RandomState(seed)
+    data = {k: rs.randn(B, T, n).astype(np.float32) for k, n in PROPRIO_KEYS.items()}
+    if onehot_action:
+        data["action"] = np.eye(d.actions, dtype=np.float32)[rs.randint(0, d.actions, size=(B, T))]
+    else:
+        data["action"] = rs.uniform(-1, 1, size=(B, T, d.actions)).astype(np.float32)
+    data["reward"] = rs.randn(B, T).astype(np.float32)
+    data["discount"] = np.ones((B, T), np.float32)
+    data["is_terminal"] = np.zeros((B, T), np.float32)
+    first = np.zeros((B, T), np.float32)
+    first[:, 0] = 1.0
+    for b, t in resets:
+        first[b, t] = 1.0
+    data["is_first"] = first
+    return data
+
+
+def train_noise(d: RSSMDims, B, T, H, seed=0, actor_dist="normal"):
+    g = torch.Generator().manual_seed(seed + 400)
+    N = B * T
+    return dict(u_prior=uniforms(g, T, B, d.stoch, d.classes),
+                u_post=uniforms(g, T, B, d.stoch, d.classes),
+                act_noise=(torch.randn(H, N, d.actions, generator=g) if actor_dist == "normal"
+                           else uniforms(g, H, N, d.actions)),
+                u_state=uniforms(g, H, N, d.stoch, d.classes))

@@ -325,3 +325,85 @@ def run_smoke(pkg, device="cuda:0"):
         if bad:
             raise AssertionError(f"smoke {name}: {bad}")
     return lines
+
+
+# --------------------------------------------------------------------------------------
+# whole train step: WorldModel._train + ImagBehavior._train forward/backward vs the oracle
+# --------------------------------------------------------------------------------------
+def build_product_agent(pkg, device, config, P, Pa, Pv, **cfg_over):
+    cfgs = pkg.configs
+    suite = {"dmc_proprio": "dmc_proprio", "tiny": "dmc_proprio"}.get(config, config)
+    c = synth.CONFIGS[config]
+    d = synth.dims_of(config)
+    over = dict(device=device, device_metrics=True, num_actions=d.actions, dyn_stoch=d.stoch,
+                dyn_discrete=d.classes, dyn_deter=d.deter, dyn_hidden=d.hidden, units=c["units"])
+    over.update(cfg_over)
+    cfg = cfgs.make_config(suite, **over)
+    wm = pkg.models.WorldModel(cfgs.ObsSpace(cfgs.PROPRIO_SHAPES), None, 0, cfg)
+    wm.load_state_dict({k: v.to(device) for k, v in P.items()}, strict=True)
+    beh = pkg.models.ImagBehavior(cfg, wm)
+    beh.actor.load_state_dict({k: v.to(device) for k, v in Pa.items()}, strict=True)
+    beh.value.load_state_dict({k: v.to(device) for k, v in Pv.items()}, strict=True)
+    beh._slow_value.load_state_dict({k: v.to(device) for k, v in Pv.items()}, strict=True)
+    return cfg, wm, beh
+
+
+def train_step_case(pkg, device, config="dmc_proprio", B=16, T=64, H=15, seed=0):
+    import train_step as TS
+    d = synth.dims_of(config)
+    c = synth.CONFIGS[config]
+    enc_units = 1024 if config == "dmc_proprio" else 64
+    P, Pa, Pv = synth.agent_params(config, seed, enc_units=enc_units)
+    ocfg = TS.make_cfg(dyn_stoch=d.stoch, dyn_discrete=d.classes, units=c["units"],
+                       enc_units=enc_units, dec_units=enc_units, imag_horizon=H,
+                       actor_layers=c["actor_layers"], actor_dist=c["actor_dist"])
+    agent = TS.Agent(P, Pa, Pv, ocfg, d)
+    data = synth.replay_batch(d, B, T, seed, resets=((1, 3), (2, T // 2)))
+    noise = synth.train_noise(d, B, T, H, seed, c["actor_dist"])
+    ref = agent.train_step({k: v.copy() for k, v in data.items()}, noise, apply=False)
+
+    over = dict(imag_horizon=H)
+    over["encoder"] = dict(mlp_units=enc_units)
+    over["decoder"] = dict(mlp_units=enc_units)
+    cfg, wm, beh = build_product_agent(pkg, device, config, P, Pa, Pv, **over)
+    nd = {k: v.to(device) for k, v in noise.items()}
+    pdata = wm.preprocess(data)
+    with pkg.tools.RequiresGrad(wm):
+        loss, post, aux = wm.loss(pdata, (nd["u_prior"], nd["u_post"]))
+        names = [k for k, _ in wm.named_parameters()]
+        grads = torch.autograd.grad(loss, list(wm.parameters()), allow_unused=True)
+    res = {"model_loss": rel(loss, ref["model_loss"]),
+           "post_idx_mismatch": int((post["stoch"].argmax(-1).cpu()
+                                     != ref["post"]["stoch"].argmax(-1)).sum())}
+    for k, v in aux["losses"].items():
+        res[f"{k}_loss"] = rel(v, ref[f"{k}_loss"])
+    gn = torch.sqrt(sum((g.double() ** 2).sum() for g in grads if g is not None)).float()
+    res["model_grad_norm"] = rel(gn, ref["model_grad_norm"])
+    for k, g in zip(names, grads):
+        r = ref["grads"]["wm"][k]
+        if g is None:
+            res[f"dwm.{k}_maxabs"] = float(r.abs().max())
+        else:
+            res[f"dwm.{k}"] = rel(g, r)
+    start = {k: v.detach() for k, v in post.items()}
+    beh._update_slow_target()
+    reward_fn = lambda f, s, a: wm.heads["reward"](wm.dynamics.get_feat(s)).mode()
+    a_loss, v_loss, roll, mets, baux = beh.losses(start, reward_fn, (nd["act_noise"], nd["u_state"]))
+    with pkg.tools.RequiresGrad(beh):
+        ga = torch.autograd.grad(a_loss, list(beh.actor.parameters()), allow_unused=True)
+        gv = torch.autograd.grad(v_loss, list(beh.value.parameters()), allow_unused=True)
+    imag = ref["imag"]
+    res["imag_idx_mismatch"] = int((roll[1]["stoch"].argmax(-1).cpu()
+                                    != imag["states"]["stoch"].argmax(-1)).sum())
+    res["imag_feat"] = rel(roll[0], imag["feats"])
+    res["imag_action"] = rel(roll[2], imag["actions"])
+    res["imag_reward"] = rel(baux["reward"], imag["reward"])
+    res["target"] = rel(baux["target"], imag["target"])
+    res["weights"] = rel(roll[3], imag["weights"])
+    res["actor_loss"] = rel(a_loss, ref["actor_loss"])
+    res["value_loss"] = rel(v_loss, ref["value_loss"])
+    for (k, _), g in zip(beh.actor.named_parameters(), ga):
+        res[f"dactor.{k}"] = rel(g, ref["grads"]["actor"][k])
+    for (k, _), g in zip(beh.value.named_parameters(), gv):
+        res[f"dvalue.{k}"] = rel(g, ref["grads"]["value"][k])
+    return res

@@ -81,3 +81,41 @@ def test_bad_shapes_raise(pkg, device):
         pkg.kernels.onehot_sample(torch.zeros(2, 2, 40, device=device), None, 0.01)   # classes > 32
     with pytest.raises(pkg._lib.Dv3Error):
         pkg.kernels.ln_silu_fwd(torch.zeros(2, 8), torch.ones(8), torch.zeros(8))      # CPU tensor
+
+
+@pytest.mark.parametrize("config,B,T,H", [("tiny", 4, 6, 5), ("dmc_proprio", 16, 64, 15)])
+def test_whole_train_step(pkg, device, config, B, T, H):
+    """WorldModel.loss + ImagBehavior.losses (forward + backward, every parameter gradient)
+    against oracle/train_step.py with the same parameters, batch and noise."""
+    res = pc.train_step_case(pkg, device, config=config, B=B, T=T, H=H)
+    _assert(res)
+
+
+def test_train_api_runs_and_updates(pkg, device):
+    """_train drop-in surface: return tuples, metric keys, parameters move, action mutated."""
+    import numpy as np
+    import torch
+    d = pc.synth.dims_of("tiny")
+    P, Pa, Pv = pc.synth.agent_params("tiny", enc_units=64)
+    cfg, wm, beh = pc.build_product_agent(pkg, device, "tiny", P, Pa, Pv, device_metrics=False,
+                                          encoder=dict(mlp_units=64), decoder=dict(mlp_units=64),
+                                          imag_horizon=5)
+    data = pc.synth.replay_batch(d, 4, 6, resets=((1, 3),))
+    before = {k: v.clone() for k, v in wm.state_dict().items()}
+    post, context, metrics = wm._train(data)
+    assert set(post) == {"stoch", "deter", "logit"} and post["stoch"].shape == (4, 6, d.stoch, d.classes)
+    assert set(context) == {"embed", "feat", "kl", "postent"}
+    for k in ("model_loss", "model_grad_norm", "reward_loss", "cont_loss", "kl_free", "dyn_scale", "rep_scale",
+              "dyn_loss", "rep_loss", "kl", "prior_ent", "post_ent"):
+        assert k in metrics, k
+    assert isinstance(metrics["model_loss"], np.ndarray)
+    moved = sum(float((wm.state_dict()[k] - before[k]).abs().max()) > 0 for k in before)
+    assert moved == len(before)
+    reward_fn = lambda f, s, a: wm.heads["reward"](wm.dynamics.get_feat(s)).mode()
+    feat, state, action, weights, m2 = beh._train(post, reward_fn)
+    assert feat.shape == (5, 24, d.flat + d.deter) and not feat.requires_grad
+    assert action.shape == (5, 24, d.actions) and weights.shape == (5, 24, 1)
+    for k in ("actor_loss", "actor_grad_norm", "value_loss", "value_grad_norm", "actor_entropy", "EMA_005",
+              "EMA_095", "value_mean", "target_std", "imag_reward_min", "imag_action_max", "normed_target_mean"):
+        assert k in m2, k
+    assert all(np.isfinite(np.asarray(v)).all() for v in m2.values())

@@ -136,6 +136,7 @@ def agent_params(config="dmc_proprio", seed=0, enc_units=1024, enc_layers=5, hea
     """-> (P_wm, P_actor, P_value) for the proprio suites (MLP encoder / decoder)."""
     c = CONFIGS[config]
     d = dims_of(config)
+    assert enc_units == d.embed, "MLP encoder width must equal the RSSM embed width"
     F_ = d.flat + d.deter
     U = c["units"]
     g = torch.Generator().manual_seed(seed + 300)

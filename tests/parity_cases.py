@@ -352,7 +352,7 @@ def train_step_case(pkg, device, config="dmc_proprio", B=16, T=64, H=15, seed=0)
     import train_step as TS
     d = synth.dims_of(config)
     c = synth.CONFIGS[config]
-    enc_units = 1024 if config == "dmc_proprio" else 64
+    enc_units = d.embed        # the MLP encoder width is the RSSM embed width
     P, Pa, Pv = synth.agent_params(config, seed, enc_units=enc_units)
     ocfg = TS.make_cfg(dyn_stoch=d.stoch, dyn_discrete=d.classes, units=c["units"],
                        enc_units=enc_units, dec_units=enc_units, imag_horizon=H,

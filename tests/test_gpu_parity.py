@@ -96,9 +96,9 @@ def test_train_api_runs_and_updates(pkg, device):
     import numpy as np
     import torch
     d = pc.synth.dims_of("tiny")
-    P, Pa, Pv = pc.synth.agent_params("tiny", enc_units=64)
+    P, Pa, Pv = pc.synth.agent_params("tiny", enc_units=d.embed)
     cfg, wm, beh = pc.build_product_agent(pkg, device, "tiny", P, Pa, Pv, device_metrics=False,
-                                          encoder=dict(mlp_units=64), decoder=dict(mlp_units=64),
+                                          encoder=dict(mlp_units=d.embed), decoder=dict(mlp_units=d.embed),
                                           imag_horizon=5)
     data = pc.synth.replay_batch(d, 4, 6, resets=((1, 3),))
     before = {k: v.clone() for k, v in wm.state_dict().items()}

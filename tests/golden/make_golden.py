@@ -166,7 +166,8 @@ def golden_train(seed=0, steps=2):
             assert tp.pos == len(tape)
             rec["steps"].append(dict(
                 data=data, noise=noise,
-                metrics={k: torch.as_tensor(np.asarray(v)) for k, v in {**m1, **m2}.items()},
+                # np.array(copy): on CPU the reference's to_np() aliases live buffers (ema_vals)
+                metrics={k: torch.tensor(np.array(v, copy=True)) for k, v in {**m1, **m2}.items()},
                 post={k: v.detach().clone() for k, v in post.items()},
                 wm_after=sd(wm), actor_after=sd(beh.actor), value_after=sd(beh.value),
                 slow_after=sd(beh._slow_value), ema_after=beh.ema_vals.clone()))

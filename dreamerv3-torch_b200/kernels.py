@@ -204,6 +204,19 @@ def linear_fwd(a1, w1, a2=None, w2=None, bias=None, addend=None):
     return out
 
 
+def linear_tc_fwd(a, w, bias=None, addend=None):
+    """C = a w^T (+bias +addend) on the tcgen05 tensor cores (3xTF32 split, fp32-accurate)."""
+    M, Kd = a.shape
+    N = w.shape[0]
+    out = _empty(M, N, like=a)
+    nbytes = L.lib().dv3_linear_tc_scratch_bytes(M, N, Kd)
+    ws = _ws(nbytes, a.device)
+    L.check(L.lib().dv3_linear_tc_fwd(L.fptr(a), Kd, L.fptr(w), Kd, L.fptr(bias), L.fptr(addend), N,
+                                      L.fptr(out), N, M, N, Kd, C.c_void_p(ws.data_ptr()),
+                                      ws.numel(), L.stream_ptr()), "linear_tc_fwd")
+    return out
+
+
 def onehot_sample(logits, u, unimix):
     """logits [M,S,C], u [M,S,C] or None (mode) -> (idx int32 [M,S], onehot fp32 [M,S,C])."""
     M, S, Cc = logits.shape

@@ -331,6 +331,13 @@ int dv3_linear_fwd(const float* A1, int32_t lda1, const float* W1, int32_t ldw1,
                    const float* A2, int32_t lda2, const float* W2, int32_t ldw2, int32_t K2,
                    const float* bias, const float* addend, int32_t ldadd, float* C, int32_t ldc,
                    int32_t M, int32_t N, int32_t accumulate, void* stream);
+/* Same product on the tcgen05 tensor cores, fp32-accurate through a 3xTF32 split
+ * (hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM; TMA-staged 128B-swizzled operand tiles).
+ * K % 4 == 0.  scratch: dv3_linear_tc_scratch_bytes(M,N,K) bytes for the split operands. */
+size_t dv3_linear_tc_scratch_bytes(int32_t M, int32_t N, int32_t K);
+int dv3_linear_tc_fwd(const float* A, int32_t lda, const float* W, int32_t ldw, const float* bias,
+                      const float* addend, int32_t ldadd, float* C, int32_t ldc, int32_t M,
+                      int32_t N, int32_t K, void* scratch, size_t scratch_bytes, void* stream);
 /* out[C,R] = in[R,C]^T  (in has row stride ld) */
 int dv3_transpose(const float* in, int32_t ld, int32_t R, int32_t C, float* out, void* stream);
 /* out = SiLU(LayerNorm(pre)) row-wise; networks.py:48-58 (Linear->LN->SiLU blocks) */

@@ -141,6 +141,15 @@ int copy_rows_i32(const int32_t* in, int ldi, int M, int n, int32_t* out, int ld
 int tanh_vec(const float* in, int n, float* out, cudaStream_t st);
 int fill_zero(void* p, size_t bytes, cudaStream_t st);
 
+// ---- tensor-core Linear (dv3_umma.cu) -----------------------------------------------------
+int tc_split(const float* a1, int ld1, int K1, const float* a2, int ld2, int K2, int M, float* hi,
+             float* lo, cudaStream_t st);
+int tc_gemm(const float* Ah, const float* Al, const float* Wh, const float* Wl, const float* bias,
+            const float* addend, int ldadd, float* C, int ldc, int M, int N, int K, int accumulate,
+            cudaStream_t st);
+// rows below this go to the CUDA-core kernels (a 128-row MMA tile would be mostly padding)
+constexpr int TC_MIN_ROWS = 64;
+
 // bump allocator over the caller's workspace
 struct Arena {
   char* base; size_t size, used;
@@ -152,6 +161,42 @@ struct Arena {
     return r;
   }
   bool ok() const { return used <= size; }
+};
+
+// A Linear weight [N,K] (row stride ldw) with, optionally, its tf32 hi/lo split for the tensor
+// core path.  apply(): C = [A1|A2] W^T + bias + addend.
+struct LinW {
+  const float* W = nullptr;
+  int ldw = 0, N = 0, K = 0;
+  float* hi = nullptr;
+  float* lo = nullptr;
+  bool tc = false;
+
+  void reserve(Arena& a, bool use_tc, int n, int k) {
+    N = n; K = k; tc = use_tc && (k % 4 == 0);
+    if (tc) { hi = a.take<float>((size_t)n * k); lo = a.take<float>((size_t)n * k); }
+  }
+  int prepare(const float* w, int ld, cudaStream_t st) {
+    W = w; ldw = ld;
+    if (tc) return tc_split(w, ld, K, nullptr, 0, 0, N, hi, lo, st);
+    return 0;
+  }
+  // ascr: 2*M*K floats of scratch (only used on the tensor-core path)
+  int apply(const float* A1, int lda1, int K1, const float* A2, int lda2, int K2, const float* bias,
+            const float* addend, int ldadd, float* C, int ldc, int M, float* ascr,
+            cudaStream_t st) const {
+    if (tc) {
+      float* ah = ascr;
+      float* al = ascr + (size_t)M * K;
+      DV3_TRY(tc_split(A1, lda1, K1, A2, lda2, A2 ? K2 : 0, M, ah, al, st));
+      return tc_gemm(ah, al, hi, lo, bias, addend, ldadd, C, ldc, M, N, K, 0, st);
+    }
+    LinearArgs g{};
+    g.A[0] = A1; g.lda[0] = lda1; g.W[0] = W; g.ldw[0] = ldw; g.K[0] = K1;
+    if (A2) { g.A[1] = A2; g.lda[1] = lda2; g.W[1] = W + K1; g.ldw[1] = ldw; g.K[1] = K2; }
+    g.bias = bias; g.addend = addend; g.ldadd = ldadd; g.C = C; g.ldc = ldc; g.M = M; g.N = N;
+    return launch_linear(g, st);
+  }
 };
 
 }  // namespace dv3

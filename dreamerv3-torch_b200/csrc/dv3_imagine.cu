@@ -54,18 +54,30 @@ struct ImgFwdWs {
   float* WinT;   // [(SC+A), Hd]
   float* Wa0T;   // [F, U]
   float* a_add;  // [N, U]
+  float* ascr;   // split scratch for the tensor-core path: 2 * N * max K
+  LinW gru, out, ims, a0d, al[16];
 };
 
 static void carve_img_fwd(Arena& a, const dv3_rssm_dims* d, const dv3_actor* act, int N,
                           ImgFwdWs& w) {
-  const size_t SC = (size_t)d->stoch * d->classes;
-  w.WinT = a.take<float>((SC + d->actions) * d->hidden);
+  const int SC = d->stoch * d->classes, D = d->deter, Hd = d->hidden;
+  const bool tc = N >= TC_MIN_ROWS;
+  w.WinT = a.take<float>((size_t)(SC + d->actions) * Hd);
+  w.gru.reserve(a, tc, 3 * D, Hd + D);
+  w.out.reserve(a, tc, Hd, D);
+  w.ims.reserve(a, tc, SC, Hd);
+  int maxk = Hd + D;
   if (act) {
-    w.Wa0T = a.take<float>((SC + d->deter) * act->units);
-    w.a_add = a.take<float>((size_t)N * act->units);
+    const int U = act->units;
+    w.Wa0T = a.take<float>((size_t)(SC + D) * U);
+    w.a_add = a.take<float>((size_t)N * U);
+    w.a0d.reserve(a, tc, U, D);
+    for (int i = 1; i < act->layers; ++i) w.al[i].reserve(a, tc, U, U);
+    if (U > maxk) maxk = U;
   } else {
     w.Wa0T = w.a_add = nullptr;
   }
+  w.ascr = tc ? a.take<float>((size_t)2 * N * maxk) : nullptr;
 }
 
 static int check_actor(const dv3_rssm_dims* d, const dv3_actor* a, const char* who) {
@@ -132,7 +144,14 @@ extern "C" int dv3_imagine_fwd(const dv3_rssm_dims* d, const dv3_rssm_params* p,
   const int U = a ? a->units : 0, L = a ? a->layers : 0;
 
   DV3_TRY(launch_transpose(p->w_in, SC + A, Hd, SC + A, w.WinT, st));
-  if (a) DV3_TRY(launch_transpose(a->w[0], F, U, F, w.Wa0T, st));
+  DV3_TRY(w.gru.prepare(p->w_gru, Hd + D, st));
+  DV3_TRY(w.out.prepare(p->w_out, D, st));
+  DV3_TRY(w.ims.prepare(p->w_ims, Hd, st));
+  if (a) {
+    DV3_TRY(launch_transpose(a->w[0], F, U, F, w.Wa0T, st));
+    DV3_TRY(w.a0d.prepare(a->w[0] + SC, F, st));
+    for (int i = 1; i < L; ++i) DV3_TRY(w.al[i].prepare(a->w[i], U, st));
+  }
   // state 0
   DV3_TRY(copy_rows_i32(io->start_idx, S, N, S, io->idx, S, st));
   DV3_TRY(idx_to_onehot(io->start_idx, S, N, S, C, io->feat, F, st));
@@ -147,14 +166,16 @@ extern "C" int dv3_imagine_fwd(const dv3_rssm_dims* d, const dv3_rssm_params* p,
       float* pre0 = io->a_pre + (size_t)k * N * U;
       float* act0 = io->a_act + (size_t)k * N * U;
       // layer 0: deter columns dense, stoch columns gathered
-      DV3_TRY(linear1(featk + SC, F, a->w[0] + SC, F, D, nullptr, w.a_add, U, N, U, 0, st));
+      DV3_TRY(w.a0d.apply(featk + SC, F, D, nullptr, 0, 0, nullptr, nullptr, 0, w.a_add, U, N,
+                          w.ascr, st));
       DV3_TRY(gather_ln_silu(idxk, S, S, C, nullptr, 0, 0, w.Wa0T, w.a_add, U, a->ln_g[0],
                              a->ln_b[0], d->ln_eps, N, U, pre0, U, act0, U, st));
       for (int i = 1; i < L; ++i) {
         float* prei = io->a_pre + i * lstride + (size_t)k * N * U;
         float* acti = io->a_act + i * lstride + (size_t)k * N * U;
         const float* prev = io->a_act + (i - 1) * lstride + (size_t)k * N * U;
-        DV3_TRY(linear1(prev, U, a->w[i], U, U, nullptr, prei, U, N, U, 0, st));
+        DV3_TRY(w.al[i].apply(prev, U, U, nullptr, 0, 0, nullptr, nullptr, 0, prei, U, N, w.ascr,
+                              st));
         DV3_TRY(ln_silu_fwd(prei, U, a->ln_g[i], a->ln_b[i], d->ln_eps, N, U, acti, U, st));
       }
       const float* top = io->a_act + (L - 1) * lstride + (size_t)k * N * U;
@@ -187,16 +208,14 @@ extern "C" int dv3_imagine_fwd(const dv3_rssm_dims* d, const dv3_rssm_params* p,
     float* logn = io->logit + (size_t)(k + 1) * N * SC;
     DV3_TRY(gather_ln_silu(idxk, S, S, C, actk, A, A, w.WinT, nullptr, 0, p->ln_in_g, p->ln_in_b,
                            d->ln_eps, N, Hd, xpre, Hd, xk, Hd, st));
-    LinearArgs g{};
-    g.A[0] = xk; g.lda[0] = Hd; g.W[0] = p->w_gru; g.ldw[0] = Hd + D; g.K[0] = Hd;
-    g.A[1] = featk + SC; g.lda[1] = F; g.W[1] = p->w_gru + Hd; g.ldw[1] = Hd + D; g.K[1] = D;
-    g.C = gpre; g.ldc = 3 * D; g.M = N; g.N = 3 * D;
-    DV3_TRY(launch_linear(g, st));
+    DV3_TRY(w.gru.apply(xk, Hd, Hd, featk + SC, F, D, nullptr, nullptr, 0, gpre, 3 * D, N, w.ascr,
+                        st));
     DV3_TRY(gru_gates_fwd(gpre, 3 * D, p->ln_gru_g, p->ln_gru_b, d->ln_eps, featk + SC, F, N, D,
                           featn + SC, F, st));
-    DV3_TRY(linear1(featn + SC, F, p->w_out, D, D, nullptr, ypre, Hd, N, Hd, 0, st));
+    DV3_TRY(w.out.apply(featn + SC, F, D, nullptr, 0, 0, nullptr, nullptr, 0, ypre, Hd, N, w.ascr,
+                        st));
     DV3_TRY(ln_silu_fwd(ypre, Hd, p->ln_out_g, p->ln_out_b, d->ln_eps, N, Hd, yk, Hd, st));
-    DV3_TRY(linear1(yk, Hd, p->w_ims, Hd, Hd, p->b_ims, logn, SC, N, SC, 0, st));
+    DV3_TRY(w.ims.apply(yk, Hd, Hd, nullptr, 0, 0, p->b_ims, nullptr, 0, logn, SC, N, w.ascr, st));
     DV3_TRY(onehot_sample(logn, SC, io->u_state + (size_t)k * N * SC, SC, 0, 0, d->unimix, N, S, C,
                           io->idx + (size_t)(k + 1) * N * S, S, featn, F, st));
   }
@@ -210,7 +229,8 @@ namespace dv3 {
 
 struct ImgBwdWs {
   float *WimsT, *WoutT, *WgruT, *WinT;
-  float *d_y, *dh_y, *dxh, *dxh_add, *dsa;
+  float *d_y, *dh_y, *dxh, *dxh_add, *dsa, *ascr;
+  LinW ims, out, gru, in;   // over the transposed weights
 };
 
 static void carve_img_bwd(Arena& a, const dv3_rssm_dims* d, int N, ImgBwdWs& w) {
@@ -225,6 +245,14 @@ static void carve_img_bwd(Arena& a, const dv3_rssm_dims* d, int N, ImgBwdWs& w) 
   w.dxh = a.take<float>((size_t)N * (Hd + D));
   w.dxh_add = a.take<float>((size_t)N * (Hd + D));
   w.dsa = a.take<float>((size_t)N * (SC + A));
+  const bool tc = N >= TC_MIN_ROWS;
+  w.ims.reserve(a, tc, (int)Hd, (int)SC);           // d_y   = d_logit @ W_ims      (K = SC)
+  w.out.reserve(a, tc, (int)D, (int)Hd);            // dh_y  = d_y_pre @ W_out      (K = Hd)
+  w.gru.reserve(a, tc, (int)(Hd + D), (int)(3 * D)); // dxh  = d_g_pre @ W_gru      (K = 3D)
+  w.in.reserve(a, tc, (int)(SC + A), (int)Hd);      // dsa   = d_x_pre @ W_in       (K = Hd)
+  size_t maxk = SC > 3 * D ? SC : 3 * D;
+  if (Hd > maxk) maxk = Hd;
+  w.ascr = tc ? a.take<float>((size_t)2 * N * maxk) : nullptr;
 }
 
 __global__ void add2_rows_kernel(const float* __restrict__ a, int lda, const float* __restrict__ b,
@@ -279,6 +307,10 @@ extern "C" int dv3_imagine_bwd(const dv3_rssm_dims* d, const dv3_rssm_params* p,
   DV3_TRY(launch_transpose(p->w_out, D, Hd, D, w.WoutT, st));
   DV3_TRY(launch_transpose(p->w_gru, Hd + D, 3 * D, Hd + D, w.WgruT, st));
   DV3_TRY(launch_transpose(p->w_in, SC + A, Hd, SC + A, w.WinT, st));
+  DV3_TRY(w.ims.prepare(w.WimsT, SC, st));
+  DV3_TRY(w.out.prepare(w.WoutT, Hd, st));
+  DV3_TRY(w.gru.prepare(w.WgruT, 3 * D, st));
+  DV3_TRY(w.in.prepare(w.WinT, Hd, st));
   DV3_TRY(fill_zero(w.dxh_add, (size_t)N * (Hd + D) * 4, st));
 
   auto actor_bwd = [&](int k, const float* d_a, int ld, int col) -> int {
@@ -309,27 +341,25 @@ extern "C" int dv3_imagine_bwd(const dv3_rssm_dims* d, const dv3_rssm_params* p,
     float* dlog = io->d_logit + on * SC;
     DV3_TRY(onehot_st_bwd(io->logit + on * SC, SC, gs, SC, ds_rec, SC + A, gl, SC, d->unimix, N, S,
                           C, dlog, SC, st));
-    DV3_TRY(linear1(dlog, SC, w.WimsT, SC, SC, nullptr, w.d_y, Hd, N, Hd, 0, st));
+    DV3_TRY(w.ims.apply(dlog, SC, SC, nullptr, 0, 0, nullptr, nullptr, 0, w.d_y, Hd, N, w.ascr, st));
     const size_t ok = (size_t)k * N;
     DV3_TRY(ln_silu_bwd(io->y_pre + ok * Hd, Hd, p->ln_out_g, p->ln_out_b, d->ln_eps, w.d_y, Hd, N,
                         Hd, io->d_y_pre + ok * Hd, Hd, io->d_y_ln + ok * Hd, Hd, st));
-    DV3_TRY(linear1(io->d_y_pre + ok * Hd, Hd, w.WoutT, Hd, Hd, nullptr, w.dh_y, D, N, D, 0, st));
+    DV3_TRY(w.out.apply(io->d_y_pre + ok * Hd, Hd, Hd, nullptr, 0, 0, nullptr, nullptr, 0, w.dh_y, D,
+                        N, w.ascr, st));
     const float* dh_in[4] = {w.dh_y, io->g_deter ? io->g_deter + on * D : nullptr, dh_rec, nullptr};
     const int ld_in[4] = {D, D, Hd + D, 0};
     DV3_TRY(gru_gates_bwd(io->g_pre + ok * 3 * D, 3 * D, p->ln_gru_g, p->ln_gru_b, d->ln_eps,
                           io->feat + ok * F + SC, F, dh_in, ld_in, N, D, io->d_g_pre + ok * 3 * D,
                           3 * D, io->d_g_ln + ok * 3 * D, 3 * D, w.dxh_add + Hd, Hd + D, st));
-    LinearArgs g{};
-    g.A[0] = io->d_g_pre + ok * 3 * D; g.lda[0] = 3 * D; g.W[0] = w.WgruT; g.ldw[0] = 3 * D;
-    g.K[0] = 3 * D; g.addend = w.dxh_add; g.ldadd = Hd + D; g.C = w.dxh; g.ldc = Hd + D; g.M = N;
-    g.N = Hd + D;
-    DV3_TRY(launch_linear(g, st));
+    DV3_TRY(w.gru.apply(io->d_g_pre + ok * 3 * D, 3 * D, 3 * D, nullptr, 0, 0, nullptr, w.dxh_add,
+                        Hd + D, w.dxh, Hd + D, N, w.ascr, st));
     dh_rec = w.dxh + Hd;
     DV3_TRY(ln_silu_bwd(io->x_pre + ok * Hd, Hd, p->ln_in_g, p->ln_in_b, d->ln_eps, w.dxh, Hd + D,
                         N, Hd, io->d_x_pre + ok * Hd, Hd, io->d_x_ln + ok * Hd, Hd, st));
     // [d stoch_k | d action_k] = d_x_pre @ W_in
-    DV3_TRY(linear1(io->d_x_pre + ok * Hd, Hd, w.WinT, Hd, Hd, nullptr, w.dsa, SC + A, N, SC + A, 0,
-                    st));
+    DV3_TRY(w.in.apply(io->d_x_pre + ok * Hd, Hd, Hd, nullptr, 0, 0, nullptr, nullptr, 0, w.dsa,
+                       SC + A, N, w.ascr, st));
     ds_rec = w.dsa;
     DV3_TRY(actor_bwd(k, w.dsa, SC + A, SC));
   }

@@ -59,12 +59,21 @@ __global__ void obs_select_kernel(const float* __restrict__ first, int ldf,
 struct ObsFwdWs {
   float* WinT;   // [(S*C+A), Hd]
   float* pre_e;  // [B*T, Hd]
+  float* ascr;   // tensor-core split scratch for the bulk (B*T-row) products
+  LinW obs_e, out, ims;
 };
 
 static void carve_fwd(Arena& a, const dv3_rssm_dims* d, int B, int T, ObsFwdWs& w) {
-  const size_t SC = (size_t)d->stoch * d->classes;
-  w.WinT = a.take<float>((SC + d->actions) * d->hidden);
-  w.pre_e = a.take<float>((size_t)B * T * d->hidden);
+  const int SC = d->stoch * d->classes, D = d->deter, Hd = d->hidden, E = d->embed;
+  const bool tc = B * T >= TC_MIN_ROWS;
+  w.WinT = a.take<float>((size_t)(SC + d->actions) * Hd);
+  w.pre_e = a.take<float>((size_t)B * T * Hd);
+  w.obs_e.reserve(a, tc && E > 0, Hd, E);
+  w.out.reserve(a, tc, Hd, D);
+  w.ims.reserve(a, tc, SC, Hd);
+  int maxk = E > D ? E : D;
+  if (Hd > maxk) maxk = Hd;
+  w.ascr = tc ? a.take<float>((size_t)2 * B * T * maxk) : nullptr;
 }
 
 // RSSM.initial for one row: deter0 = tanh(W), stoch0 = mode(prior(deter0))
@@ -127,7 +136,11 @@ extern "C" int dv3_observe_fwd(const dv3_rssm_dims* d, const dv3_rssm_params* p,
 
   // ---- hoisted work ----
   DV3_TRY(launch_transpose(p->w_in, SC + A, Hd, SC + A, w.WinT, st));
-  DV3_TRY(linear1(io->embed, E, p->w_obs + D, D + E, E, nullptr, w.pre_e, Hd, BT, Hd, 0, st));
+  DV3_TRY(w.obs_e.prepare(p->w_obs + D, D + E, st));
+  DV3_TRY(w.out.prepare(p->w_out, D, st));
+  DV3_TRY(w.ims.prepare(p->w_ims, Hd, st));
+  DV3_TRY(w.obs_e.apply(io->embed, E, E, nullptr, 0, 0, nullptr, nullptr, 0, w.pre_e, Hd, BT, w.ascr,
+                        st));
   first_eff_kernel<<<(BT + 255) / 256, 256, 0, st>>>(io->is_first, B, T, has_state, io->first_eff);
   DV3_CHECK_LAUNCH("first_eff_kernel");
   DV3_TRY(rssm_initial(d, p, io->init_deter, io->init_ypre, io->init_y, io->init_logit,
@@ -175,9 +188,11 @@ extern "C" int dv3_observe_fwd(const dv3_rssm_dims* d, const dv3_rssm_params* p,
   }
 
   // ---- prior branch for all B*T rows ----
-  DV3_TRY(linear1(io->deter, D, p->w_out, D, D, nullptr, io->y_pre, Hd, BT, Hd, 0, st));
+  DV3_TRY(w.out.apply(io->deter, D, D, nullptr, 0, 0, nullptr, nullptr, 0, io->y_pre, Hd, BT, w.ascr,
+                      st));
   DV3_TRY(ln_silu_fwd(io->y_pre, Hd, p->ln_out_g, p->ln_out_b, d->ln_eps, BT, Hd, io->y, Hd, st));
-  DV3_TRY(linear1(io->y, Hd, p->w_ims, Hd, Hd, p->b_ims, io->prior_logit, SC, BT, SC, 0, st));
+  DV3_TRY(w.ims.apply(io->y, Hd, Hd, nullptr, 0, 0, p->b_ims, nullptr, 0, io->prior_logit, SC, BT,
+                      w.ascr, st));
   DV3_TRY(onehot_sample(io->prior_logit, SC, io->u_prior, SC, T, B, d->unimix, BT, S, C,
                         io->prior_idx, S, io->prior_stoch, SC, st));
   return 0;
@@ -195,6 +210,8 @@ struct ObsBwdWs {
   float *dxh, *dxh_add;            // [B, Hd+D]
   float *ds_tmp, *ds_rec, *dh_rec; // [B, SC], [B, SC], [B, D]
   float *dinit_s, *dinit_h;        // [B, SC], [B, D] per-row accumulators (deterministic)
+  float* ascr;
+  LinW ims, out, obs_e;            // bulk products over the transposed weights
 };
 
 static void carve_bwd(Arena& a, const dv3_rssm_dims* d, int B, int T, ObsBwdWs& w) {
@@ -217,6 +234,12 @@ static void carve_bwd(Arena& a, const dv3_rssm_dims* d, int B, int T, ObsBwdWs& 
   w.dh_rec = a.take<float>((size_t)B * D);
   w.dinit_s = a.take<float>((size_t)B * SC);
   w.dinit_h = a.take<float>((size_t)B * D);
+  const bool tc = B * T >= TC_MIN_ROWS;
+  w.ims.reserve(a, tc, (int)Hd, (int)SC);     // d_y      = d_prior_logit @ W_ims   (K = SC)
+  w.out.reserve(a, tc, (int)D, (int)Hd);      // dh_prior = d_y_pre @ W_out         (K = Hd)
+  w.obs_e.reserve(a, tc && E > 0, (int)E, (int)Hd);   // d_embed = d_z_pre @ W_obs[:, D:]   (K = Hd)
+  const size_t maxk = SC > Hd ? SC : Hd;
+  w.ascr = tc ? a.take<float>((size_t)2 * B * T * maxk) : nullptr;
 }
 
 // Route the gradients that reached step t's *input* state: rows that were reset at t send them
@@ -295,10 +318,15 @@ extern "C" int dv3_observe_bwd(const dv3_rssm_dims* d, const dv3_rssm_params* p,
   // ---- prior branch, all rows at once ----
   DV3_TRY(onehot_st_bwd(io->prior_logit, SC, io->g_prior_stoch, SC, nullptr, 0, io->g_prior_logit,
                         SC, d->unimix, BT, S, C, io->d_prior_logit, SC, st));
-  DV3_TRY(linear1(io->d_prior_logit, SC, w.WimsT, SC, SC, nullptr, w.d_y, Hd, BT, Hd, 0, st));
+  DV3_TRY(w.ims.prepare(w.WimsT, SC, st));
+  DV3_TRY(w.out.prepare(w.WoutT, Hd, st));
+  DV3_TRY(w.obs_e.prepare(w.WobsT + (size_t)D * Hd, Hd, st));
+  DV3_TRY(w.ims.apply(io->d_prior_logit, SC, SC, nullptr, 0, 0, nullptr, nullptr, 0, w.d_y, Hd, BT,
+                      w.ascr, st));
   DV3_TRY(ln_silu_bwd(io->y_pre, Hd, p->ln_out_g, p->ln_out_b, d->ln_eps, w.d_y, Hd, BT, Hd,
                       io->d_y_pre, Hd, io->d_y_ln, Hd, st));
-  DV3_TRY(linear1(io->d_y_pre, Hd, w.WoutT, Hd, Hd, nullptr, w.dh_prior, D, BT, D, 0, st));
+  DV3_TRY(w.out.apply(io->d_y_pre, Hd, Hd, nullptr, 0, 0, nullptr, nullptr, 0, w.dh_prior, D, BT,
+                      w.ascr, st));
 
   DV3_TRY(fill_zero(w.ds_rec, (size_t)B * SC * 4, st));
   DV3_TRY(fill_zero(w.dh_rec, (size_t)B * D * 4, st));
@@ -346,8 +374,9 @@ extern "C" int dv3_observe_bwd(const dv3_rssm_dims* d, const dv3_rssm_params* p,
   }
   // ---- after the loop ----
   // d embed = d_z_pre @ W_obs[:, D:]
-  DV3_TRY(linear1(io->d_z_pre, Hd, w.WobsT + (size_t)D * Hd, Hd, Hd, nullptr, io->d_embed, E, BT, E,
-                  0, st));
+  if (E > 0)
+    DV3_TRY(w.obs_e.apply(io->d_z_pre, Hd, Hd, nullptr, 0, 0, nullptr, nullptr, 0, io->d_embed, E, BT,
+                          w.ascr, st));
   colsum_kernel<<<(SC + 255) / 256, 256, 0, st>>>(w.dinit_s, B, SC, io->d_init_stoch);
   DV3_CHECK_LAUNCH("colsum_kernel");
   colsum_kernel<<<(D + 255) / 256, 256, 0, st>>>(w.dinit_h, B, D, io->d_init_deter);

@@ -143,7 +143,9 @@ int fill_zero(void* p, size_t bytes, cudaStream_t st);
 
 // ---- tensor-core Linear (dv3_umma.cu) -----------------------------------------------------
 int tc_split(const float* a1, int ld1, int K1, const float* a2, int ld2, int K2, int M, float* hi,
-             float* lo, cudaStream_t st);
+             float* lo, cudaStream_t st, int Kp = 0);
+int tc_split_t(const float* in, int ld, int R, int C, float* hi, float* lo, cudaStream_t st,
+               int Cp = 0);
 int tc_gemm(const float* Ah, const float* Al, const float* Wh, const float* Wl, const float* bias,
             const float* addend, int ldadd, float* C, int ldc, int M, int N, int K, int accumulate,
             cudaStream_t st);

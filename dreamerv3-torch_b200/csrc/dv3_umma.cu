@@ -272,25 +272,61 @@ umma_gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap mAh,
 }
 
 // hi = x with the low 13 mantissa bits cleared, lo = x - hi; two row segments packed side by side
+// (output rows have pitch Kp >= K1+K2, zero padded, so that the TMA row pitch is 16B-aligned)
 __global__ void split_tf32_kernel(const float* __restrict__ a1, int ld1, int K1,
-                                  const float* __restrict__ a2, int ld2, int K2, int M,
+                                  const float* __restrict__ a2, int ld2, int K2, int M, int Kp,
                                   float* __restrict__ hi, float* __restrict__ lo) {
-  const int K = K1 + K2;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)M * K) return;
-  const int r = (int)(i / K), c = (int)(i % K);
-  const float x = (c < K1) ? a1[(size_t)r * ld1 + c] : a2[(size_t)r * ld2 + (c - K1)];
+  if (i >= (long long)M * Kp) return;
+  const int r = (int)(i / Kp), c = (int)(i % Kp);
+  float x = 0.f;
+  if (c < K1) x = a1[(size_t)r * ld1 + c];
+  else if (c < K1 + K2) x = a2[(size_t)r * ld2 + (c - K1)];
   const float h = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
   hi[i] = h;
   lo[i] = x - h;
 }
 
+// transposing split: in is stored [C, R] (row stride ld); hi/lo are the dense [R, C] split of in^T
+__global__ void split_tf32_transpose_kernel(const float* __restrict__ in, int ld, int R, int C,
+                                            int Cp, float* __restrict__ hi,
+                                            float* __restrict__ lo) {
+  __shared__ float tile[32][33];
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;   // r indexes output rows = input columns
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && r < R) ? in[(size_t)c * ld + r] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    if (r < R && c < Cp) {
+      const float x = tile[threadIdx.x][i];
+      const float h = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+      hi[(size_t)r * Cp + c] = h;
+      lo[(size_t)r * Cp + c] = x - h;
+    }
+  }
+}
+
+int tc_split_t(const float* in, int ld, int R, int C, float* hi, float* lo, cudaStream_t st,
+               int Cp) {
+  if (R <= 0 || C <= 0) return 0;
+  if (Cp < C) Cp = C;
+  dim3 grid((Cp + 31) / 32, (R + 31) / 32), block(32, 8);
+  split_tf32_transpose_kernel<<<grid, block, 0, st>>>(in, ld, R, C, Cp, hi, lo);
+  DV3_CHECK_LAUNCH("split_tf32_transpose_kernel");
+  return 0;
+}
+
 int tc_split(const float* a1, int ld1, int K1, const float* a2, int ld2, int K2, int M, float* hi,
-             float* lo, cudaStream_t st) {
-  const long long tot = (long long)M * (K1 + (a2 ? K2 : 0));
+             float* lo, cudaStream_t st, int Kp) {
+  const int K = K1 + (a2 ? K2 : 0);
+  if (Kp < K) Kp = K;
+  const long long tot = (long long)M * Kp;
   if (tot <= 0) return 0;
   split_tf32_kernel<<<(int)((tot + 255) / 256), 256, 0, st>>>(a1, ld1, K1, a2, ld2, a2 ? K2 : 0, M,
-                                                              hi, lo);
+                                                              Kp, hi, lo);
   DV3_CHECK_LAUNCH("split_tf32_kernel");
   return 0;
 }
@@ -372,27 +408,32 @@ int tc_gemm(const float* Ah, const float* Al, const float* Wh, const float* Wl, 
 // C ABI: self-contained tensor-core Linear (splits both operands into the caller's scratch).
 // scratch: 2*(M+N)*K floats.
 extern "C" size_t dv3_linear_tc_scratch_bytes(int32_t M, int32_t N, int32_t K) {
-  return (size_t)2 * ((size_t)M + N) * K * sizeof(float) + 1024;
+  const size_t Kp = ((size_t)K + 3) & ~size_t(3);
+  return (size_t)2 * ((size_t)M + N) * Kp * sizeof(float) + 1024;
 }
 
-extern "C" int dv3_linear_tc_fwd(const float* A, int32_t lda, const float* W, int32_t ldw,
-                                 const float* bias, const float* addend, int32_t ldadd, float* C,
-                                 int32_t ldc, int32_t M, int32_t N, int32_t K, void* scratch,
+extern "C" int dv3_linear_tc_fwd(const float* A, int32_t lda, int32_t transA, const float* W,
+                                 int32_t ldw, int32_t transW, const float* bias,
+                                 const float* addend, int32_t ldadd, float* C, int32_t ldc,
+                                 int32_t M, int32_t N, int32_t K, void* scratch,
                                  size_t scratch_bytes, void* stream) {
   using namespace dv3;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  DV3_REQUIRE(M >= 0 && N >= 0 && K > 0 && K % 4 == 0, DV3_ERR_BAD_SHAPE,
-              "linear_tc_fwd: M=%d N=%d K=%d (K %% 4 == 0)", M, N, K);
+  DV3_REQUIRE(M >= 0 && N >= 0 && K > 0, DV3_ERR_BAD_SHAPE, "linear_tc_fwd: M=%d N=%d K=%d", M, N,
+              K);
   if (M == 0 || N == 0) return 0;
+  const int Kp = (K + 3) & ~3;   // split operands are zero padded to a 16-byte row pitch
   DV3_REQUIRE(A && W && C && scratch, DV3_ERR_NULL, "linear_tc_fwd: null pointer");
   DV3_REQUIRE(scratch_bytes >= dv3_linear_tc_scratch_bytes(M, N, K), DV3_ERR_WORKSPACE,
               "linear_tc_fwd: scratch too small");
   float* base = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(scratch) + 255) & ~uintptr_t(255));
   float* Ah = base;
-  float* Al = Ah + (size_t)M * K;
-  float* Wh = Al + (size_t)M * K;
-  float* Wl = Wh + (size_t)N * K;
-  DV3_TRY(tc_split(A, lda, K, nullptr, 0, 0, M, Ah, Al, st));
-  DV3_TRY(tc_split(W, ldw, K, nullptr, 0, 0, N, Wh, Wl, st));
-  return tc_gemm(Ah, Al, Wh, Wl, bias, addend, ldadd, C, ldc, M, N, K, 0, st);
+  float* Al = Ah + (size_t)M * Kp;
+  float* Wh = Al + (size_t)M * Kp;
+  float* Wl = Wh + (size_t)N * Kp;
+  if (transA) DV3_TRY(tc_split_t(A, lda, M, K, Ah, Al, st, Kp));
+  else DV3_TRY(tc_split(A, lda, K, nullptr, 0, 0, M, Ah, Al, st, Kp));
+  if (transW) DV3_TRY(tc_split_t(W, ldw, N, K, Wh, Wl, st, Kp));
+  else DV3_TRY(tc_split(W, ldw, K, nullptr, 0, 0, N, Wh, Wl, st, Kp));
+  return tc_gemm(Ah, Al, Wh, Wl, bias, addend, ldadd, C, ldc, M, N, Kp, 0, st);
 }

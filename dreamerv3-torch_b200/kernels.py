@@ -204,17 +204,88 @@ def linear_fwd(a1, w1, a2=None, w2=None, bias=None, addend=None):
     return out
 
 
-def linear_tc_fwd(a, w, bias=None, addend=None):
-    """C = a w^T (+bias +addend) on the tcgen05 tensor cores (3xTF32 split, fp32-accurate)."""
-    M, Kd = a.shape
-    N = w.shape[0]
+def linear_tc(a, w, bias=None, addend=None, trans_a=False, trans_w=False):
+    """C[M,N] = op(a) op(w)^T (+bias +addend) on the tcgen05 tensor cores (3xTF32 split,
+    fp32-accurate).  op(a) is [M,K] (a stored [K,M] when trans_a); op(w) is [N,K] (w stored [K,N]
+    when trans_w).  a / w must be contiguous 2-D."""
+    M, Kd = (a.shape[1], a.shape[0]) if trans_a else a.shape
+    N = w.shape[1] if trans_w else w.shape[0]
     out = _empty(M, N, like=a)
+    if M == 0 or N == 0:
+        return out
     nbytes = L.lib().dv3_linear_tc_scratch_bytes(M, N, Kd)
     ws = _ws(nbytes, a.device)
-    L.check(L.lib().dv3_linear_tc_fwd(L.fptr(a), Kd, L.fptr(w), Kd, L.fptr(bias), L.fptr(addend), N,
-                                      L.fptr(out), N, M, N, Kd, C.c_void_p(ws.data_ptr()),
-                                      ws.numel(), L.stream_ptr()), "linear_tc_fwd")
+    L.check(L.lib().dv3_linear_tc_fwd(L.fptr(a), a.shape[1], int(trans_a), L.fptr(w), w.shape[1],
+                                      int(trans_w), L.fptr(bias), L.fptr(addend), N, L.fptr(out),
+                                      N, M, N, Kd, C.c_void_p(ws.data_ptr()), ws.numel(),
+                                      L.stream_ptr()), "linear_tc_fwd")
     return out
+
+
+def linear_tc_fwd(a, w, bias=None, addend=None):
+    return linear_tc(a, w, bias, addend)
+
+
+class _DenseLnSilu(torch.autograd.Function):
+    """SiLU(LayerNorm(x W^T)) for x [M,K], W [U,K]: the Linear(no bias)+LN(eps 1e-3)+SiLU block of
+    the reference MLPs (networks.py:623-632).  All three contractions (y, dx, dW) run on the
+    tensor-core GEMM, LN/SiLU forward and backward on the row kernels."""
+
+    @staticmethod
+    def forward(ctx, x, W, g, b):
+        x, Wc = _f32(x), _c(W.detach())
+        pre = linear_tc(x, Wc)
+        out = ln_silu_fwd(pre, _c(g.detach()), _c(b.detach()))
+        ctx.save_for_backward(x, Wc, g.detach(), b.detach(), pre)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        x, W, g, b, pre = ctx.saved_tensors
+        d_pre, d_ln = ln_silu_bwd(pre, _c(g), _c(b), _f32(d_out))
+        dx = dW = dg = db = None
+        if ctx.needs_input_grad[0]:
+            dx = linear_tc(d_pre, W, trans_w=True)                   # dy W
+        if ctx.needs_input_grad[1]:
+            dW = linear_tc(d_pre, x, trans_a=True, trans_w=True)     # dy^T x
+        if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
+            dg, db = _ln_grads(pre, d_ln)
+        return dx, dW, dg, db
+
+
+class _LinearBias(torch.autograd.Function):
+    """x W^T + bias (the MLP output heads, networks.py:640-655) on the tensor-core GEMM."""
+
+    @staticmethod
+    def forward(ctx, x, W, bias):
+        x, Wc = _f32(x), _c(W.detach())
+        ctx.save_for_backward(x, Wc)
+        return linear_tc(x, Wc, None if bias is None else _c(bias.detach()))
+
+    @staticmethod
+    def backward(ctx, d_out):
+        x, W = ctx.saved_tensors
+        d_out = _f32(d_out)
+        dx = dW = db = None
+        if ctx.needs_input_grad[0]:
+            dx = linear_tc(d_out, W, trans_w=True)
+        if ctx.needs_input_grad[1]:
+            dW = linear_tc(d_out, x, trans_a=True, trans_w=True)
+        if ctx.needs_input_grad[2]:
+            db = d_out.sum(0)
+        return dx, dW, db
+
+
+def dense_ln_silu(x, W, g, b):
+    lead = x.shape[:-1]
+    out = _DenseLnSilu.apply(x.reshape(-1, x.shape[-1]), W, g, b)
+    return out.reshape(tuple(lead) + (W.shape[0],))
+
+
+def linear_bias(x, W, bias):
+    lead = x.shape[:-1]
+    out = _LinearBias.apply(x.reshape(-1, x.shape[-1]), W, bias)
+    return out.reshape(tuple(lead) + (W.shape[0],))
 
 
 def onehot_sample(logits, u, unimix):

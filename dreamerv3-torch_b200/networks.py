@@ -218,18 +218,30 @@ class MLP(nn.Module):
                 self.std_layer.apply(tools.uniform_weight_init(outscale))
 
     def trunk(self, features):
+        """[Linear(no bias) -> LayerNorm -> SiLU] x layers (networks.py:657-661) on the tensor-core
+        GEMM + LN/SiLU row kernels."""
         x = tools.symlog(features) if self._symlog_inputs else features
-        return self.layers(x)
+        if not x.is_cuda:
+            raise L.Dv3Error("MLP forward needs CUDA tensors: the B200 path has no CPU fallback")
+        for i in range(self._layers):
+            lin = getattr(self.layers, f"{self._name}_linear{i}")
+            nrm = getattr(self.layers, f"{self._name}_norm{i}")
+            x = K.dense_ln_silu(x, lin.weight, nrm.weight, nrm.bias)
+        return x
+
+    @staticmethod
+    def _head(layer, x):
+        return K.linear_bias(x, layer.weight, layer.bias)
 
     def forward(self, features, dtype=None):
         out = self.trunk(features)
         if self._shape is None:
             return out
         if isinstance(self._shape, dict):
-            return {k: self.dist(self._dist, self.mean_layer[k](out), self._std, shp)
+            return {k: self.dist(self._dist, self._head(self.mean_layer[k], out), self._std, shp)
                     for k, shp in self._shape.items()}
-        std = self.std_layer(out) if self._std == "learned" else self._std
-        return self.dist(self._dist, self.mean_layer(out), std, self._shape)
+        std = self._head(self.std_layer, out) if self._std == "learned" else self._std
+        return self.dist(self._dist, self._head(self.mean_layer, out), std, self._shape)
 
     def dist(self, dist, mean, std, shape):
         if dist == "normal":

@@ -331,13 +331,18 @@ int dv3_linear_fwd(const float* A1, int32_t lda1, const float* W1, int32_t ldw1,
                    const float* A2, int32_t lda2, const float* W2, int32_t ldw2, int32_t K2,
                    const float* bias, const float* addend, int32_t ldadd, float* C, int32_t ldc,
                    int32_t M, int32_t N, int32_t accumulate, void* stream);
-/* Same product on the tcgen05 tensor cores, fp32-accurate through a 3xTF32 split
- * (hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM; TMA-staged 128B-swizzled operand tiles).
- * K % 4 == 0.  scratch: dv3_linear_tc_scratch_bytes(M,N,K) bytes for the split operands. */
+/* C[M,N] = op(A) op(W)^T + bias + addend on the tcgen05 tensor cores, fp32-accurate through a
+ * 3xTF32 split (hi*hi + hi*lo + lo*hi; fp32 accumulation in TMEM, promoted every 128 k to fp32
+ * registers because the tensor core truncates its accumulator adds; TMA-staged 128B-swizzled
+ * operand tiles).  op(A) is [M,K]: transA == 0 -> A is stored [M,K] (row stride lda), transA != 0
+ * -> A is stored [K,M].  op(W) is [N,K]: transW == 0 -> stored [N,K] (the nn.Linear layout),
+ * transW != 0 -> stored [K,N].  This covers y = x W^T, dx = dy W (transW) and dW = dy^T x (both).
+ * scratch: dv3_linear_tc_scratch_bytes(M,N,K) bytes for the split (zero-padded) operands. */
 size_t dv3_linear_tc_scratch_bytes(int32_t M, int32_t N, int32_t K);
-int dv3_linear_tc_fwd(const float* A, int32_t lda, const float* W, int32_t ldw, const float* bias,
-                      const float* addend, int32_t ldadd, float* C, int32_t ldc, int32_t M,
-                      int32_t N, int32_t K, void* scratch, size_t scratch_bytes, void* stream);
+int dv3_linear_tc_fwd(const float* A, int32_t lda, int32_t transA, const float* W, int32_t ldw,
+                      int32_t transW, const float* bias, const float* addend, int32_t ldadd,
+                      float* C, int32_t ldc, int32_t M, int32_t N, int32_t K, void* scratch,
+                      size_t scratch_bytes, void* stream);
 /* out[C,R] = in[R,C]^T  (in has row stride ld) */
 int dv3_transpose(const float* in, int32_t ld, int32_t R, int32_t C, float* out, void* stream);
 /* out = SiLU(LayerNorm(pre)) row-wise; networks.py:48-58 (Linear->LN->SiLU blocks) */

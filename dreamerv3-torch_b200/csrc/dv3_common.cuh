@@ -92,6 +92,51 @@ __device__ __forceinline__ float silu_grad(float x) {
   return s * (1.f + x * (1.f - s));
 }
 
+// ---- unimix categorical helpers (one class per lane) ---------------------------------------
+// probs are built exactly along the reference's chain (tools.py:439-441 + torch Categorical):
+//   p = softmax(l); p = (1-r)p + r/C; l' = log p; norm = l' - logsumexp(l'); probs = softmax(norm)
+struct Unimix {
+  float p;      // softmax(l)
+  float norm;   // normalised log-prob after unimix
+  float probs;  // softmax(norm)
+};
+
+__device__ __forceinline__ Unimix unimix_probs(float l, bool valid, int C, float unimix) {
+  Unimix o;
+  const float NEG = -INFINITY;
+  float m = warp_max(valid ? l : NEG);
+  float e = valid ? expf(l - m) : 0.f;
+  float s = warp_sum(e);
+  o.p = e / s;
+  float lp = l;
+  if (unimix > 0.f) {
+    const float pm = o.p * (1.f - unimix) + unimix / (float)C;
+    lp = logf(pm);
+  }
+  float m2 = warp_max(valid ? lp : NEG);
+  float s2 = warp_sum(valid ? expf(lp - m2) : 0.f);
+  o.norm = lp - (m2 + logf(s2));
+  float m3 = warp_max(valid ? o.norm : NEG);
+  float e3 = valid ? expf(o.norm - m3) : 0.f;
+  float s3 = warp_sum(e3);
+  o.probs = e3 / s3;
+  return o;
+}
+
+// first-index argmax across the warp
+__device__ __forceinline__ int warp_argmax(float v, bool valid, int lane) {
+  float bv = valid ? v : -INFINITY;
+  int bi = valid ? lane : 0x7fffffff;
+  if (valid && v != v) bv = -INFINITY;  // NaN never wins
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(FULL, bv, o);
+    const int oi = __shfl_xor_sync(FULL, bi, o);
+    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+  }
+  return bi;
+}
+
 // ---- internal host launchers (definitions spread over the .cu files) ----------------------
 struct LinearArgs {
   const float* A[2];
@@ -149,6 +194,11 @@ int tc_split_t(const float* in, int ld, int R, int C, float* hi, float* lo, cuda
 int tc_gemm(const float* Ah, const float* Al, const float* Wh, const float* Wl, const float* bias,
             const float* addend, int ldadd, float* C, int ldc, int M, int N, int K, int accumulate,
             cudaStream_t st);
+// persistent (single cooperative launch) forward recurrence of observe; *used == false -> not
+// applicable for these shapes, run the stepwise launches instead (dv3_observe_persistent.cu)
+int observe_fwd_persistent(const dv3_rssm_dims* d, const dv3_rssm_params* p,
+                           const dv3_observe_io* io, const float* WinT, const float* pre_e,
+                           unsigned* bar, cudaStream_t st, bool* used);
 // rows below this go to the CUDA-core kernels (a 128-row MMA tile would be mostly padding)
 constexpr int TC_MIN_ROWS = 64;
 

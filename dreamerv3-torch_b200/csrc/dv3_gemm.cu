@@ -2,11 +2,8 @@
 //
 // Two shapes of problem appear on the path:
 //   * M = 16 rows (observe, B=16): a GEMV-like, weight-bandwidth/latency-bound product.
-//     -> linear_skinny_kernel: each warp owns 4 output columns, splits K over its lanes, reads
-//        its weight rows straight from L2/HBM with 128-bit coalesced loads (issued before the
-//        activation tile is staged so they are in flight during the staging), activations staged
-//        once per CTA in shared memory, 64 partial sums per lane folded with a 62-shuffle
-//        butterfly.
+//     -> linear_skinny_kernel: 8 output columns per CTA, K split over all 256 threads, every
+//        128-bit weight / activation load of the CTA in flight at once, butterfly + smem fold.
 //   * M = 1024+ rows (imagination, bulk backward): a real contraction.
 //     -> linear_tiled_kernel: 128x64x16 register-tiled SIMT GEMM (8x4 per thread), register
 //        staged double buffering.  This is the exact-fp32 path used for parity; the tcgen05
@@ -17,82 +14,59 @@ namespace dv3 {
 
 
 // ------------------------------------------------------------------------------------------
-// skinny: M-tile of 16 rows
+// skinny: M-tile of 16 rows, 8 output columns per CTA, K split over all 256 threads.
+// Every thread issues its 8 weight + 16 activation 128-bit loads up front (one L2 round trip for
+// the whole CTA), does 16x8x4 FMAs per float4 of K, then the 128 partial sums per thread are
+// folded with a shuffle butterfly (124 shuffles) and an 8-way shared-memory add.
 // ------------------------------------------------------------------------------------------
 constexpr int SK_ROWS = 16;
-constexpr int SK_KC = 512;          // K chunk staged in smem (16*512*4 = 32 KB)
-constexpr int SK_CPW = 4;           // columns per warp
-constexpr int SK_WARPS = 4;
-constexpr int SK_ITERS = SK_KC / 128;
+constexpr int SK_COLS = 8;
+constexpr int SK_THREADS = 256;
+constexpr int SK_NV = SK_ROWS * SK_COLS;   // 128 accumulators per thread
 
-__global__ void __launch_bounds__(SK_WARPS * 32)
+__global__ void __launch_bounds__(SK_THREADS)
 linear_skinny_kernel(LinearArgs g) {
-  __shared__ __align__(16) float As[SK_ROWS][SK_KC];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int m0 = blockIdx.y * SK_ROWS;
-  const int n0 = (blockIdx.x * SK_WARPS + warp) * SK_CPW;
+  __shared__ float part[SK_THREADS / 32][SK_NV];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int m0 = blockIdx.y * SK_ROWS, n0 = blockIdx.x * SK_COLS;
+  const int K1 = g.A[0] ? g.K[0] : 0, K2 = g.A[1] ? g.K[1] : 0;
+  const int Q1 = K1 >> 2, Q = (K1 + K2) >> 2;
 
-  float acc[SK_ROWS * SK_CPW];
+  float acc[SK_NV];
 #pragma unroll
-  for (int i = 0; i < SK_ROWS * SK_CPW; ++i) acc[i] = 0.f;
+  for (int i = 0; i < SK_NV; ++i) acc[i] = 0.f;
 
 #pragma unroll 1
-  for (int seg = 0; seg < 2; ++seg) {
-    const float* __restrict__ A = g.A[seg];
-    const float* __restrict__ W = g.W[seg];
-    const int K = g.K[seg];
-    if (A == nullptr || K == 0) continue;
+  for (int q = tid; q < Q; q += SK_THREADS) {
+    const int seg = q >= Q1;
+    const int k = (seg ? q - Q1 : q) << 2;
+    const float* __restrict__ A = g.A[seg] + k;
+    const float* __restrict__ W = g.W[seg] + k;
     const int lda = g.lda[seg], ldw = g.ldw[seg];
-#pragma unroll 1
-    for (int kc = 0; kc < K; kc += SK_KC) {
-      const int klen = min(SK_KC, K - kc);
-      // (1) weight loads first: they do not depend on the staged activations
-      float4 wreg[SK_ITERS][SK_CPW];
+    float4 w[SK_COLS], a[SK_ROWS];
 #pragma unroll
-      for (int it = 0; it < SK_ITERS; ++it) {
-        const int kk = it * 128 + lane * 4;
+    for (int c = 0; c < SK_COLS; ++c)
+      w[c] = (n0 + c < g.N) ? __ldg(reinterpret_cast<const float4*>(W + (size_t)(n0 + c) * ldw))
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int c = 0; c < SK_CPW; ++c) {
-          const int n = n0 + c;
-          if (kk < klen && n < g.N)
-            wreg[it][c] = __ldg(reinterpret_cast<const float4*>(W + (size_t)n * ldw + kc + kk));
-          else
-            wreg[it][c] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+    for (int m = 0; m < SK_ROWS; ++m)
+      a[m] = (m0 + m < g.M) ? *reinterpret_cast<const float4*>(A + (size_t)(m0 + m) * lda)
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int m = 0; m < SK_ROWS; ++m)
+#pragma unroll
+      for (int c = 0; c < SK_COLS; ++c) {
+        float s = acc[m * SK_COLS + c];
+        s = fmaf(a[m].x, w[c].x, s);
+        s = fmaf(a[m].y, w[c].y, s);
+        s = fmaf(a[m].z, w[c].z, s);
+        s = fmaf(a[m].w, w[c].w, s);
+        acc[m * SK_COLS + c] = s;
       }
-      // (2) stage the activation chunk
-      __syncthreads();  // previous chunk fully consumed
-      for (int i = threadIdx.x; i < SK_ROWS * (SK_KC / 4); i += blockDim.x) {
-        const int r = i / (SK_KC / 4), k4 = (i % (SK_KC / 4)) * 4;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (m0 + r < g.M && k4 < klen)
-          v = *reinterpret_cast<const float4*>(A + (size_t)(m0 + r) * lda + kc + k4);
-        *reinterpret_cast<float4*>(&As[r][k4]) = v;
-      }
-      __syncthreads();
-      // (3) FMA
-#pragma unroll
-      for (int it = 0; it < SK_ITERS; ++it) {
-        const int kk = it * 128 + lane * 4;
-#pragma unroll
-        for (int m = 0; m < SK_ROWS; ++m) {
-          const float4 a = *reinterpret_cast<const float4*>(&As[m][kk]);
-#pragma unroll
-          for (int c = 0; c < SK_CPW; ++c) {
-            float s = acc[m * SK_CPW + c];
-            s = fmaf(a.x, wreg[it][c].x, s);
-            s = fmaf(a.y, wreg[it][c].y, s);
-            s = fmaf(a.z, wreg[it][c].z, s);
-            s = fmaf(a.w, wreg[it][c].w, s);
-            acc[m * SK_CPW + c] = s;
-          }
-        }
-      }
-    }
   }
-  // butterfly fold: 64 values x 32 lanes -> lane L ends with values 2L, 2L+1
+  // butterfly fold: 128 values x 32 lanes -> lane L ends with values 4L .. 4L+3
 #pragma unroll
-  for (int off = 16, nv = SK_ROWS * SK_CPW; off > 0; off >>= 1, nv >>= 1) {
+  for (int off = 16, nv = SK_NV; off > 0; off >>= 1, nv >>= 1) {
     const bool up = (lane & off) != 0;
     const int half = nv >> 1;
 #pragma unroll
@@ -102,12 +76,17 @@ linear_skinny_kernel(LinearArgs g) {
       acc[i] = keep + __shfl_xor_sync(FULL, send, off);
     }
   }
+  // after the fold lane L holds, in acc[0..3], the values whose index has bit pattern
+  // (lane bit4, bit3, bit2, bit1, bit0) as its top five bits: index = L*4 + j
 #pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    const int v = 2 * lane + j;
-    const int m = m0 + v / SK_CPW, n = n0 + v % SK_CPW;
+  for (int j = 0; j < 4; ++j) part[warp][lane * 4 + j] = acc[j];
+  __syncthreads();
+  if (tid < SK_NV) {
+    float r = 0.f;
+#pragma unroll
+    for (int w2 = 0; w2 < SK_THREADS / 32; ++w2) r += part[w2][tid];
+    const int m = m0 + tid / SK_COLS, n = n0 + tid % SK_COLS;
     if (m < g.M && n < g.N) {
-      float r = acc[j];
       if (g.bias) r += g.bias[n];
       if (g.addend) r += g.addend[(size_t)m * g.ldadd + n];
       float* c = g.C + (size_t)m * g.ldc + n;
@@ -232,9 +211,9 @@ int launch_linear(const LinearArgs& g, cudaStream_t st) {
   const bool prof = prof_on();
   const double flops = 2.0 * g.M * g.N * ((g.A[0] ? g.K[0] : 0) + (g.A[1] ? g.K[1] : 0));
   if (g.M <= 2 * SK_ROWS && vec) {
-    dim3 grid((g.N + SK_WARPS * SK_CPW - 1) / (SK_WARPS * SK_CPW), (g.M + SK_ROWS - 1) / SK_ROWS);
+    dim3 grid((g.N + SK_COLS - 1) / SK_COLS, (g.M + SK_ROWS - 1) / SK_ROWS);
     if (prof) prof_begin(st);
-    linear_skinny_kernel<<<grid, SK_WARPS * 32, 0, st>>>(g);
+    linear_skinny_kernel<<<grid, SK_THREADS, 0, st>>>(g);
     if (prof) prof_end(st, 0, flops);
     DV3_CHECK_LAUNCH("linear_skinny_kernel");
     return 0;

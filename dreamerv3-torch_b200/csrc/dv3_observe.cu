@@ -60,6 +60,7 @@ struct ObsFwdWs {
   float* WinT;   // [(S*C+A), Hd]
   float* pre_e;  // [B*T, Hd]
   float* ascr;   // tensor-core split scratch for the bulk (B*T-row) products
+  unsigned* bar; // grid-barrier words of the persistent kernel
   LinW obs_e, out, ims;
 };
 
@@ -68,6 +69,7 @@ static void carve_fwd(Arena& a, const dv3_rssm_dims* d, int B, int T, ObsFwdWs& 
   const bool tc = B * T >= TC_MIN_ROWS;
   w.WinT = a.take<float>((size_t)(SC + d->actions) * Hd);
   w.pre_e = a.take<float>((size_t)B * T * Hd);
+  w.bar = a.take<unsigned>(64);
   w.obs_e.reserve(a, tc && E > 0, Hd, E);
   w.out.reserve(a, tc, Hd, D);
   w.ims.reserve(a, tc, SC, Hd);
@@ -146,8 +148,10 @@ extern "C" int dv3_observe_fwd(const dv3_rssm_dims* d, const dv3_rssm_params* p,
   DV3_TRY(rssm_initial(d, p, io->init_deter, io->init_ypre, io->init_y, io->init_logit,
                        io->init_idx, st));
 
-  // ---- the recurrence ----
-  for (int t = 0; t < T; ++t) {
+  // ---- the recurrence: one persistent kernel when the shapes allow, else a launch sequence ----
+  bool persistent = false;
+  DV3_TRY(observe_fwd_persistent(d, p, io, w.WinT, w.pre_e, w.bar, st, &persistent));
+  for (int t = 0; t < T && !persistent; ++t) {
     const int32_t* prev_idx = t ? io->post_idx + (size_t)(t - 1) * S : io->state_idx;
     const int ldpi = t ? T * S : S;
     const float* prev_h = t ? io->deter + (size_t)(t - 1) * D : io->state_deter;

@@ -1,0 +1,406 @@
+// Persistent forward kernel of RSSM.observe for the latency-bound small-batch case (B <= 16).
+//
+// One cooperative launch runs all T steps.  The recurrent weights stay resident in shared memory
+// for the whole sequence, column-sharded over the grid:
+//     W_gru   [3D, Hd+D]  -> ceil(3D/G) output columns per CTA            (48 KB at D=Hd=512, G=128)
+//     W_obs[:, :D] [Hd,D] -> ceil(Hd/G) columns per CTA                   ( 8 KB)
+//     W_os    [S*C, Hd]   -> one categorical group (C columns) per CTA g < S   (64 KB)
+// A step is four phases separated by a grid barrier (an atomic counter + generation flag in L2):
+//   A  CTA b < B: previous-state select (is_first mix), one-hot gather of W_in^T, LN+SiLU -> x
+//   B  all CTAs: g_pre[:, own columns] = W_gru [x, h]              (inputs read from L2)
+//   C+D all CTAs: LN_3D + GRU gates for all rows (redundantly, rows kept in registers) -> h' in
+//      smem; z_pre[:, own columns] = W_obs_d h' + (embed part, precomputed)
+//   E  CTA g < S: LN+SiLU of z rows -> smem, logits of group g, unimix categorical draw
+// Activations cross CTAs through global memory (L2) with .cg loads; every per-step tensor has its
+// own address per t, so nothing stale can sit in L1.  All saved tensors of the stepwise path are
+// written identically, so dv3_observe_bwd is unchanged.
+//
+// Reference: networks.py:174-206 (obs_step), 208-233 (img_step), 760-768 (GRUCell),
+// tools.py:436-460 (OneHotDist), tools.py:806-850 (static_scan).
+#include <cstdlib>
+#include "dv3_common.cuh"
+
+namespace dv3 {
+
+constexpr int PO_THREADS = 256;
+constexpr int PO_WARPS = PO_THREADS / 32;
+constexpr int PO_ROWS = 16;
+constexpr int PO_CP = 6;                    // output columns per GEMV pass
+constexpr int PO_NV = PO_ROWS * PO_CP;      // 96 partial sums per thread
+
+struct PoArgs {
+  int B, T, S, C, D, Hd, A, E;
+  float unimix, eps;
+  const float *w_gru, *ln_gru_g, *ln_gru_b, *w_obs, *ln_obs_g, *ln_obs_b, *w_os, *b_os, *ln_in_g,
+      *ln_in_b;
+  const float *WinT, *pre_e;
+  const float *action, *first_eff, *u_post;
+  const int32_t* state_idx;
+  const float* state_deter;
+  const int32_t* init_idx;
+  const float* init_deter;
+  float *post_stoch, *post_logit, *deter, *hprev, *aprev, *x_pre, *x, *g_pre, *z_pre, *z;
+  int32_t *post_idx, *sprev_idx;
+  unsigned* bar;
+  int ncg, nco, bufw;
+};
+
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned nblocks, unsigned& gen) {
+  __syncthreads();
+  const unsigned next = gen + 1;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&bar[0], 1u) == nblocks - 1) {
+      bar[0] = 0;
+      __threadfence();
+      atomicExch(&bar[1], next);
+    } else {
+      while (*reinterpret_cast<volatile unsigned*>(&bar[1]) != next) {
+      }
+    }
+    __threadfence();
+  }
+  gen = next;
+  __syncthreads();
+}
+
+template <bool GLOBAL_IN>
+__device__ __forceinline__ float4 load4(const float* p) {
+  if (GLOBAL_IN) return __ldcg(reinterpret_cast<const float4*>(p));
+  return *reinterpret_cast<const float4*>(p);
+}
+
+// out[m][c] = sum_k Ws[c*K + k] * in[m][k] for m < B <= 16, c < ncols; in = [in1 (K1) | in2];
+// K split over all threads, weights from smem, 96 partials folded by butterfly + smem.
+template <bool GLOBAL_IN, typename Epi>
+__device__ __forceinline__ void gemv16(const float* Ws, int ncols, int K, const float* in1, int ld1,
+                                       int K1, const float* in2, int ld2, int B, float* part,
+                                       Epi epi) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int cb = 0; cb < ncols; cb += PO_CP) {
+    float acc[PO_NV];
+#pragma unroll
+    for (int i = 0; i < PO_NV; ++i) acc[i] = 0.f;
+#pragma unroll 1
+    for (int q = tid; q < (K >> 2); q += PO_THREADS) {
+      const int k = q << 2;
+      const float* src;
+      int ld;
+      if (k < K1) { src = in1 + k; ld = ld1; } else { src = in2 + (k - K1); ld = ld2; }
+      float4 a[PO_ROWS];
+#pragma unroll
+      for (int m = 0; m < PO_ROWS; ++m)
+        a[m] = (m < B) ? load4<GLOBAL_IN>(src + (size_t)m * ld) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int c = 0; c < PO_CP; ++c) {
+        const float4 w = (cb + c < ncols)
+                             ? *reinterpret_cast<const float4*>(Ws + (size_t)(cb + c) * K + k)
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int m = 0; m < PO_ROWS; ++m) {
+          float s = acc[m * PO_CP + c];
+          s = fmaf(a[m].x, w.x, s);
+          s = fmaf(a[m].y, w.y, s);
+          s = fmaf(a[m].z, w.z, s);
+          s = fmaf(a[m].w, w.w, s);
+          acc[m * PO_CP + c] = s;
+        }
+      }
+    }
+    // butterfly fold 96 -> 3 per lane (lane L ends with indices 3L .. 3L+2)
+#pragma unroll
+    for (int off = 16, nv = PO_NV; off > 0; off >>= 1, nv >>= 1) {
+      const bool up = (lane & off) != 0;
+      const int half = nv >> 1;
+#pragma unroll
+      for (int i = 0; i < half; ++i) {
+        const float send = up ? acc[i] : acc[i + half];
+        const float keep = up ? acc[i + half] : acc[i];
+        acc[i] = keep + __shfl_xor_sync(FULL, send, off);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) part[warp * PO_NV + lane * 3 + j] = acc[j];
+    __syncthreads();
+    if (tid < PO_NV) {
+      float r = 0.f;
+#pragma unroll
+      for (int w2 = 0; w2 < PO_WARPS; ++w2) r += part[w2 * PO_NV + tid];
+      const int m = tid / PO_CP, c = cb + tid % PO_CP;
+      if (m < B && c < ncols) epi(m, c, r);
+    }
+    __syncthreads();
+  }
+}
+
+template <int DV>   // DV = D / 32
+__global__ void __launch_bounds__(PO_THREADS, 1) observe_persistent_fwd_kernel(PoArgs p) {
+  extern __shared__ __align__(16) float smf[];
+  const int G = gridDim.x, cta = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int B = p.B, T = p.T, S = p.S, C = p.C, D = p.D, Hd = p.Hd, A = p.A, E = p.E;
+  const int SC = S * C, Kg = Hd + D, D3 = 3 * D;
+  float* Wg = smf;
+  float* Wo = Wg + (size_t)p.ncg * Kg;
+  float* Ws = Wo + (size_t)p.nco * D;
+  float* buf = Ws + (size_t)C * Hd;
+  float* part = buf + (size_t)PO_ROWS * p.bufw;
+  float* lg = part + PO_WARPS * PO_NV;
+  float* red = lg + PO_ROWS * 32;
+  int* sidx = reinterpret_cast<int*>(red + 128);
+  float* sact = reinterpret_cast<float*>(sidx + ((S + 3) & ~3));
+
+  const int g0 = min(cta * p.ncg, D3), gn = min(p.ncg, D3 - g0);
+  const int o0 = min(cta * p.nco, Hd), on = min(p.nco, Hd - o0);
+  const bool owns_group = cta < S;
+
+  // resident weight slices
+  for (int i = tid * 4; i < gn * Kg; i += PO_THREADS * 4)
+    *reinterpret_cast<float4*>(Wg + i) =
+        __ldg(reinterpret_cast<const float4*>(p.w_gru + (size_t)g0 * Kg + i));
+  for (int i = tid * 4; i < on * D; i += PO_THREADS * 4) {
+    const int r = i / D, k = i % D;
+    *reinterpret_cast<float4*>(Wo + i) =
+        __ldg(reinterpret_cast<const float4*>(p.w_obs + (size_t)(o0 + r) * (D + E) + k));
+  }
+  if (owns_group)
+    for (int i = tid * 4; i < C * Hd; i += PO_THREADS * 4)
+      *reinterpret_cast<float4*>(Ws + i) =
+          __ldg(reinterpret_cast<const float4*>(p.w_os + (size_t)cta * C * Hd + i));
+  __syncthreads();
+
+  unsigned gen = 0;
+  for (int t = 0; t < T; ++t) {
+    // ---------------- phase A: row b = cta ----------------
+    if (cta < B) {
+      const int b = cta;
+      const size_t bt = (size_t)b * T + t;
+      const bool first = p.first_eff[bt] != 0.f;
+      const int32_t* pidx = t ? p.post_idx + (bt - 1) * S : (p.state_idx ? p.state_idx + (size_t)b * S : nullptr);
+      const float* ph = t ? p.deter + (bt - 1) * D : (p.state_deter ? p.state_deter + (size_t)b * D : nullptr);
+      for (int i = tid; i < S; i += PO_THREADS) {
+        const int v = first ? p.init_idx[i] : __ldcg(pidx + i);
+        p.sprev_idx[bt * S + i] = v;
+        sidx[i] = v + i * C;
+      }
+      for (int j = tid; j < D; j += PO_THREADS)
+        p.hprev[bt * D + j] = first ? p.init_deter[j] : __ldcg(ph + j);
+      for (int a = tid; a < A; a += PO_THREADS) {
+        const float v = first ? 0.f : p.action[bt * A + a];
+        p.aprev[bt * A + a] = v;
+        sact[a] = v;
+      }
+      __syncthreads();
+      for (int i = tid; i < Hd; i += PO_THREADS) {
+        float acc = 0.f;
+        for (int s = 0; s < S; ++s) acc += p.WinT[(size_t)sidx[s] * Hd + i];
+        const float* wa = p.WinT + (size_t)SC * Hd + i;
+        for (int a = 0; a < A; ++a) acc = fmaf(sact[a], wa[(size_t)a * Hd], acc);
+        buf[i] = acc;
+        p.x_pre[bt * Hd + i] = acc;
+      }
+      __syncthreads();
+      float s1[1] = {0.f};
+      for (int i = tid; i < Hd; i += PO_THREADS) s1[0] += buf[i];
+      block_sum<1>(s1, red);
+      const float mean = s1[0] / (float)Hd;
+      float s2[1] = {0.f};
+      for (int i = tid; i < Hd; i += PO_THREADS) {
+        const float dd = buf[i] - mean;
+        s2[0] = fmaf(dd, dd, s2[0]);
+      }
+      block_sum<1>(s2, red);
+      const float rstd = 1.f / sqrtf(s2[0] / (float)Hd + p.eps);
+      for (int i = tid; i < Hd; i += PO_THREADS)
+        p.x[bt * Hd + i] = siluf_(fmaf((buf[i] - mean) * rstd, p.ln_in_g[i], p.ln_in_b[i]));
+    }
+    grid_barrier(p.bar, G, gen);
+
+    // ---------------- phase B: GRU pre-activations, own columns ----------------
+    if (gn > 0) {
+      float* gp = p.g_pre;
+      gemv16<true>(Wg, gn, Kg, p.x + (size_t)t * Hd, T * Hd, Hd, p.hprev + (size_t)t * D, T * D, B,
+                   part, [&](int m, int c, float r) {
+                     gp[((size_t)m * T + t) * D3 + g0 + c] = r;
+                   });
+    }
+    grid_barrier(p.bar, G, gen);
+
+    // ---------------- phase C: LN_3D + gates for every row (redundant), h' -> smem ----------------
+#pragma unroll 1
+    for (int rr = 0; rr < 2; ++rr) {
+      const int b = warp * 2 + rr;
+      if (b < B) {
+        const size_t bt = (size_t)b * T + t;
+        const float* row = p.g_pre + bt * D3;
+        float v[3 * DV];
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 3 * DV; ++i) {
+          v[i] = __ldcg(row + lane + 32 * i);
+          s += v[i];
+        }
+        const float mean = warp_sum(s) / (float)D3;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < 3 * DV; ++i) {
+          const float dd = v[i] - mean;
+          q = fmaf(dd, dd, q);
+        }
+        const float rstd = 1.f / sqrtf(warp_sum(q) / (float)D3 + p.eps);
+#pragma unroll
+        for (int i = 0; i < DV; ++i) {
+          const int j = lane + 32 * i;
+          const float pr = fmaf((v[i] - mean) * rstd, p.ln_gru_g[j], p.ln_gru_b[j]);
+          const float pc = fmaf((v[i + DV] - mean) * rstd, p.ln_gru_g[D + j], p.ln_gru_b[D + j]);
+          const float pu = fmaf((v[i + 2 * DV] - mean) * rstd, p.ln_gru_g[2 * D + j], p.ln_gru_b[2 * D + j]);
+          const float rg = sigmoidf_(pr);
+          const float cc = tanhf(rg * pc);
+          const float u = sigmoidf_(pu - 1.f);
+          const float hp = __ldcg(p.hprev + bt * D + j);
+          const float hn = u * cc + (1.f - u) * hp;
+          buf[(size_t)b * p.bufw + j] = hn;
+          if (cta == b) p.deter[bt * D + j] = hn;
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---------------- phase D: posterior pre-activations, own columns ----------------
+    if (on > 0) {
+      float* zp = p.z_pre;
+      const float* pe = p.pre_e;
+      gemv16<false>(Wo, on, D, buf, p.bufw, D, nullptr, 0, B, part, [&](int m, int c, float r) {
+        const size_t o = ((size_t)m * T + t) * Hd + o0 + c;
+        zp[o] = r + pe[o];
+      });
+    }
+    grid_barrier(p.bar, G, gen);
+
+    // ---------------- phase E: group g = cta: LN+SiLU(z), logits, unimix draw ----------------
+    if (owns_group) {
+#pragma unroll 1
+      for (int rr = 0; rr < 2; ++rr) {
+        const int b = warp * 2 + rr;
+        if (b < B) {
+          const size_t bt = (size_t)b * T + t;
+          float* zr = buf + (size_t)b * p.bufw;
+          float s = 0.f;
+          for (int i = lane; i < Hd; i += 32) {
+            const float x = __ldcg(p.z_pre + bt * Hd + i);
+            zr[i] = x;
+            s += x;
+          }
+          const float mean = warp_sum(s) / (float)Hd;
+          float q = 0.f;
+          for (int i = lane; i < Hd; i += 32) {
+            const float dd = zr[i] - mean;
+            q = fmaf(dd, dd, q);
+          }
+          const float rstd = 1.f / sqrtf(warp_sum(q) / (float)Hd + p.eps);
+          for (int i = lane; i < Hd; i += 32) {
+            const float y = siluf_(fmaf((zr[i] - mean) * rstd, p.ln_obs_g[i], p.ln_obs_b[i]));
+            zr[i] = y;
+            if (cta == b) p.z[bt * Hd + i] = y;
+          }
+        }
+      }
+      __syncthreads();
+      const float* bos = p.b_os + (size_t)cta * C;
+      gemv16<false>(Ws, C, Hd, buf, p.bufw, Hd, nullptr, 0, B, part,
+                    [&](int m, int c, float r) { lg[m * 32 + c] = r + bos[c]; });
+#pragma unroll 1
+      for (int rr = 0; rr < 2; ++rr) {
+        const int b = warp * 2 + rr;
+        if (b < B) {
+          const size_t bt = (size_t)b * T + t;
+          const bool valid = lane < C;
+          const float l = valid ? lg[b * 32 + lane] : 0.f;
+          const Unimix um = unimix_probs(l, valid, C, p.unimix);
+          const float uu = valid ? p.u_post[(((size_t)t * B + b) * S + cta) * C + lane] : 1.f;
+          const int k = warp_argmax(um.probs / (-logf(uu)), valid, lane);
+          if (valid) {
+            const size_t o = (bt * S + cta) * C + lane;
+            p.post_logit[o] = l;
+            p.post_stoch[o] = (lane == k) ? 1.f : 0.f;
+          }
+          if (lane == 0) p.post_idx[bt * S + cta] = k;
+        }
+      }
+    }
+    grid_barrier(p.bar, G, gen);
+  }
+}
+
+static size_t po_smem_bytes(const PoArgs& a) {
+  const size_t fl = (size_t)a.ncg * (a.Hd + a.D) + (size_t)a.nco * a.D + (size_t)a.C * a.Hd +
+                    (size_t)PO_ROWS * a.bufw + PO_WARPS * PO_NV + PO_ROWS * 32 + 128 +
+                    ((a.S + 3) & ~3) + ((a.A + 3) & ~3) + 16;
+  return fl * 4;
+}
+
+template <int DV>
+static int po_launch(PoArgs& a, int G, size_t smem, cudaStream_t st, bool* used) {
+  auto kern = observe_persistent_fwd_kernel<DV>;
+  DV3_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  DV3_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PO_THREADS, smem));
+  int dev = 0, sms = 0;
+  DV3_CHECK_CUDA(cudaGetDevice(&dev));
+  DV3_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if (per_sm * sms < G) return 0;   // cannot be co-resident: caller falls back to the stepwise path
+  DV3_CHECK_CUDA(cudaMemsetAsync(a.bar, 0, 2 * sizeof(unsigned), st));
+  void* args[] = {&a};
+  DV3_CHECK_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kern), dim3(G), dim3(PO_THREADS),
+                                             args, smem, st));
+  note_launch();
+  *used = true;
+  return 0;
+}
+
+// Runs the T-step recurrence of observe_fwd in one persistent kernel when the shapes allow it.
+// *used == false on return means "not applicable": the caller runs the stepwise launches.
+int observe_fwd_persistent(const dv3_rssm_dims* d, const dv3_rssm_params* p,
+                           const dv3_observe_io* io, const float* WinT, const float* pre_e,
+                           unsigned* bar, cudaStream_t st, bool* used) {
+  *used = false;
+  const char* env = getenv("DV3_OBSERVE_STEPWISE");
+  if (env && env[0] == '1') return 0;
+  const int D = d->deter, Hd = d->hidden, S = d->stoch, C = d->classes;
+  if (io->B > PO_ROWS || D % 32 != 0 || (D / 32 != 2 && D / 32 != 4 && D / 32 != 8 && D / 32 != 16))
+    return 0;
+  if (Hd % 4 != 0 || d->embed % 4 != 0 || C > 32) return 0;
+  int dev = 0, sms = 0, coop = 0;
+  DV3_CHECK_CUDA(cudaGetDevice(&dev));
+  DV3_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  DV3_CHECK_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+  if (!coop) return 0;
+  const int G = sms >= 128 ? 128 : sms;
+  if (S > G || io->B > G) return 0;
+  PoArgs a{};
+  a.B = io->B; a.T = io->T; a.S = S; a.C = C; a.D = D; a.Hd = Hd; a.A = d->actions; a.E = d->embed;
+  a.unimix = d->unimix; a.eps = d->ln_eps;
+  a.w_gru = p->w_gru; a.ln_gru_g = p->ln_gru_g; a.ln_gru_b = p->ln_gru_b; a.w_obs = p->w_obs;
+  a.ln_obs_g = p->ln_obs_g; a.ln_obs_b = p->ln_obs_b; a.w_os = p->w_os; a.b_os = p->b_os;
+  a.ln_in_g = p->ln_in_g; a.ln_in_b = p->ln_in_b;
+  a.WinT = WinT; a.pre_e = pre_e;
+  a.action = io->action; a.first_eff = io->first_eff; a.u_post = io->u_post;
+  a.state_idx = io->state_idx; a.state_deter = io->state_deter;
+  a.init_idx = io->init_idx; a.init_deter = io->init_deter;
+  a.post_stoch = io->post_stoch; a.post_logit = io->post_logit; a.deter = io->deter;
+  a.hprev = io->hprev; a.aprev = io->aprev; a.x_pre = io->x_pre; a.x = io->x; a.g_pre = io->g_pre;
+  a.z_pre = io->z_pre; a.z = io->z; a.post_idx = io->post_idx; a.sprev_idx = io->sprev_idx;
+  a.bar = bar;
+  a.ncg = (3 * D + G - 1) / G;
+  a.nco = (Hd + G - 1) / G;
+  a.bufw = ((D > Hd ? D : Hd) + 3) & ~3;
+  const size_t smem = po_smem_bytes(a);
+  if (smem > 200 * 1024) return 0;
+  switch (D / 32) {
+    case 2: return po_launch<2>(a, G, smem, st, used);
+    case 4: return po_launch<4>(a, G, smem, st, used);
+    case 8: return po_launch<8>(a, G, smem, st, used);
+    default: return po_launch<16>(a, G, smem, st, used);
+  }
+}
+
+}  // namespace dv3

@@ -256,48 +256,6 @@ int gru_gates_bwd(const float* g_pre, int ldg, const float* g, const float* b, f
 //   norm = l' - logsumexp(l'); probs = softmax(norm)        torch Categorical (logits -> probs)
 //   idx = argmax_k probs_k / (-log u_k)                     ATen multinomial n=1
 // ------------------------------------------------------------------------------------------
-struct Unimix {
-  float p;      // softmax(l)
-  float norm;   // normalised log-prob after unimix
-  float probs;  // softmax(norm)
-};
-
-__device__ __forceinline__ Unimix unimix_probs(float l, bool valid, int C, float unimix) {
-  Unimix o;
-  const float NEG = -INFINITY;
-  float m = warp_max(valid ? l : NEG);
-  float e = valid ? expf(l - m) : 0.f;
-  float s = warp_sum(e);
-  o.p = e / s;
-  float lp = l;
-  if (unimix > 0.f) {
-    const float pm = o.p * (1.f - unimix) + unimix / (float)C;
-    lp = logf(pm);
-  }
-  float m2 = warp_max(valid ? lp : NEG);
-  float s2 = warp_sum(valid ? expf(lp - m2) : 0.f);
-  o.norm = lp - (m2 + logf(s2));
-  float m3 = warp_max(valid ? o.norm : NEG);
-  float e3 = valid ? expf(o.norm - m3) : 0.f;
-  float s3 = warp_sum(e3);
-  o.probs = e3 / s3;
-  return o;
-}
-
-// first-index argmax across the warp
-__device__ __forceinline__ int warp_argmax(float v, bool valid, int lane) {
-  float bv = valid ? v : -INFINITY;
-  int bi = valid ? lane : 0x7fffffff;
-  if (valid && v != v) bv = -INFINITY;  // NaN never wins
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float ov = __shfl_xor_sync(FULL, bv, o);
-    const int oi = __shfl_xor_sync(FULL, bi, o);
-    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-  }
-  return bi;
-}
-
 __global__ void __launch_bounds__(256)
 onehot_sample_kernel(const float* __restrict__ logits, int ldl, const float* __restrict__ u,
                      int ldu, int permT, int permB, float unimix, int M, int S, int C,

@@ -42,9 +42,18 @@ from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     for _ in range(2): step()
     torch.cuda.synchronize()
-ev = prof.key_averages()
-rows = sorted([e for e in ev if e.device_time_total > 0 and e.device_type.name == 'CUDA' or getattr(e, 'self_device_time_total', 0) > 0], key=lambda e: -e.self_device_time_total)
-tot = sum(e.self_device_time_total for e in rows)
+import collections
+agg = collections.defaultdict(lambda: [0, 0.0])
+for e in prof.events():
+    if e.device_type.name == 'CUDA':
+        agg[e.name][0] += 1; agg[e.name][1] += e.device_time
+tot = sum(v[1] for v in agg.values())
 print("total GPU kernel time per step (ms):", tot / 2 / 1e3)
-for e in rows[:40]:
-    print(f"{e.self_device_time_total/2/1e3:8.3f} ms  n={e.count//2:5d}  {e.key[:90]}")
+groups = collections.defaultdict(float)
+for k, v in agg.items():
+    gname = ("umma" if "umma" in k else "split" if "split_tf32" in k else "skinny" if "skinny" in k else
+             "dv3 other" if "dv3::" in k else "torch gemm" if ("gemm" in k or "cutlass" in k) else "torch other")
+    groups[gname] += v[1] / 2 / 1e3
+print({k: round(v, 2) for k, v in groups.items()})
+for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:45]:
+    print(f"{v[1]/2/1e3:8.3f} ms  n={v[0]//2:5d} avg={v[1]/v[0]:7.1f}us  {k[:100]}")

@@ -40,8 +40,20 @@ def test_onehot_sample_and_straight_through(pkg, device, C, unimix):
     _assert(res)
 
 
-@pytest.mark.parametrize("config,B,T", [("tiny", 3, 5), ("dmc_proprio", 16, 64), ("dmc_vision", 16, 16)])
-def test_observe_fwd_bwd(pkg, device, config, B, T):
+@pytest.mark.parametrize("stepwise", ["0", "1"])
+@pytest.mark.parametrize("config,B,T", [("tiny", 3, 5), ("dmc_proprio", 16, 64), ("dmc_vision", 16, 16),
+                                        ("dmc_proprio", 7, 9)])
+def test_observe_fwd_bwd(pkg, device, config, B, T, stepwise, monkeypatch):
+    """stepwise=0: persistent cooperative kernel for the forward recurrence (B <= 16);
+    stepwise=1: the launch-per-phase path (what larger shapes use)."""
+    monkeypatch.setenv("DV3_OBSERVE_STEPWISE", stepwise)
+    before = pkg._lib.lib().dv3_launch_count()
+    _assert(pc.observe_case(pkg, device, config=config, B=B, T=T, backward=False))
+    launches = pkg._lib.lib().dv3_launch_count() - before
+    if stepwise == "0":
+        assert launches < 40, launches          # one launch for the whole recurrence
+    else:
+        assert launches > 7 * T
     _assert(pc.observe_case(pkg, device, config=config, B=B, T=T))
 
 

@@ -275,7 +275,8 @@ def run_ours(args):
         "imagined_states_per_s": imag_states,
         "imagine_fwd_ms": imag_ms,
         "roofline": {
-            "kernel": "linear_tiled_kernel (fp32 GEMM of the imagination / bulk rows; dominant by time)",
+            "kernel": "umma_gemm_3xtf32_kernel (tcgen05 3xTF32 GEMM of the imagination steps and all bulk-row "
+                      "contractions; dominant by time) + the fp32 SIMT tiled fallback for K % 4 != 0",
             "bound": "tensor", "achieved": ach, "peak": peaks["tf"], "unit": "TFLOP/s",
             "frac": ach / peaks["tf"], "traffic": None, "peak_source": peaks["src"],
             "launches_per_step": tiled_n / args.steps, "ms_per_step": tiled_ms / args.steps,

@@ -150,6 +150,8 @@ SIGNATURES = {
     "dv3_linear_tc_scratch_bytes": (C.c_size_t, [_i32, _i32, _i32]),
     "dv3_linear_tc_fwd": (C.c_int, [_f, _i32, _i32, _f, _i32, _i32, _f, _f, _i32, _f, _i32, _i32,
                                     _i32, _i32, _v, C.c_size_t, _v]),
+    "dv3_linear_tc2_fwd": (C.c_int, [_f, _i32, _i32, _f, _i32, _i32, _f, _i32, _f, _f, _i32, _f,
+                                     _i32, _i32, _i32, _i32, _v]),
     "dv3_transpose": (C.c_int, [_f, _i32, _i32, _i32, _f, _v]),
     "dv3_ln_silu_fwd": (C.c_int, [_f, _i32, _f, _f, _f32, _i32, _i32, _f, _i32, _v]),
     "dv3_ln_silu_bwd": (C.c_int, [_f, _i32, _f, _f, _f32, _f, _i32, _i32, _i32, _f, _f, _i32, _v]),

@@ -226,6 +226,29 @@ def linear_tc_fwd(a, w, bias=None, addend=None):
     return linear_tc(a, w, bias, addend)
 
 
+def linear_tc2(a1, w, a2=None, bias=None, addend=None, out=None, accumulate=False):
+    """C[M,N] = [a1|a2] w^T (+bias +addend) on the persistent raw-operand tcgen05 kernel
+    (dv3_umma2.cu): a1 [M,K1], a2 [M,K2] | None, w [N,K1+K2]; row-strided 2-D views allowed
+    (innermost stride 1, 16-byte aligned rows)."""
+    M, K1 = a1.shape
+    N = w.shape[0]
+    K2 = a2.shape[1] if a2 is not None else 0
+    if out is None:
+        out = _empty(M, N, like=a1)
+    if M == 0 or N == 0:
+        return out
+    for t in (a1, a2, w):
+        if t is not None and (t.stride(-1) != 1 or t.dtype != torch.float32):
+            raise L.Dv3Error("linear_tc2: fp32 operands with innermost stride 1 required")
+    raw = lambda t: None if t is None else C.cast(C.c_void_p(t.data_ptr()), C.POINTER(C.c_float))
+    L.check(L.lib().dv3_linear_tc2_fwd(raw(a1), a1.stride(0), K1, raw(a2),
+                                       a2.stride(0) if a2 is not None else 0, K2, raw(w),
+                                       w.stride(0), L.fptr(bias), L.fptr(addend), N, raw(out),
+                                       out.stride(0), M, N, int(accumulate), L.stream_ptr()),
+            "linear_tc2_fwd")
+    return out
+
+
 class _DenseLnSilu(torch.autograd.Function):
     """SiLU(LayerNorm(x W^T)) for x [M,K], W [U,K]: the Linear(no bias)+LN(eps 1e-3)+SiLU block of
     the reference MLPs (networks.py:623-632).  All three contractions (y, dx, dW) run on the

@@ -343,6 +343,14 @@ int dv3_linear_tc_fwd(const float* A, int32_t lda, int32_t transA, const float* 
                       int32_t transW, const float* bias, const float* addend, int32_t ldadd,
                       float* C, int32_t ldc, int32_t M, int32_t N, int32_t K, void* scratch,
                       size_t scratch_bytes, void* stream);
+/* Same product straight from fp32 operands, no scratch and no pre-pass: C = [A1|A2] W^T (+bias
+ * +addend, +C when accumulate != 0).  TMA loads each fp32 tile once; the hi/lo split is done
+ * inside the SM by converter warps of the persistent GEMM kernel (dv3_umma2.cu).  A1/A2/W must be
+ * 16-byte aligned with row strides (in floats) that are multiples of 4; A2 may be NULL. */
+int dv3_linear_tc2_fwd(const float* A1, int32_t lda1, int32_t K1, const float* A2, int32_t lda2,
+                       int32_t K2, const float* W, int32_t ldw, const float* bias,
+                       const float* addend, int32_t ldadd, float* C, int32_t ldc, int32_t M,
+                       int32_t N, int32_t accumulate, void* stream);
 /* out[C,R] = in[R,C]^T  (in has row stride ld) */
 int dv3_transpose(const float* in, int32_t ld, int32_t R, int32_t C, float* out, void* stream);
 /* out = SiLU(LayerNorm(pre)) row-wise; networks.py:48-58 (Linear->LN->SiLU blocks) */

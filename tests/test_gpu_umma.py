@@ -34,3 +34,38 @@ def test_linear_tc_transposed_operands(pkg, device, M, N, K):
     assert float((out.double() - ref).abs().max() / ref.abs().max()) < 5e-6
     out = pkg.kernels.linear_tc(at.t().contiguous(), wt, trans_w=True)
     assert float((out.double() - ref).abs().max() / ref.abs().max()) < 5e-6
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (128, 64, 64), (1024, 1536, 1024), (1024, 512, 512),
+                                   (1000, 1032, 500), (24, 48, 48), (257, 130, 100), (15, 32, 4),
+                                   (70, 9, 36), (15360, 512, 1536), (2000, 640, 4096)])
+def test_linear_tc2_matches_fp64(pkg, device, M, N, K):
+    """raw-operand persistent kernel (in-SM hi/lo split) against fp64."""
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    a = torch.randn(M, K, generator=g).to(device)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(device)
+    bias = torch.randn(N, generator=g).to(device)
+    add = torch.randn(M, N, generator=g).to(device)
+    ref = (a.double() @ w.double().t() + bias.double() + add.double())
+    out = pkg.kernels.linear_tc2(a, w, bias=bias, addend=add)
+    torch.cuda.synchronize()
+    err = float((out.double() - ref).abs().max() / ref.abs().max())
+    assert err < 5e-6, err
+    ref2 = a.double() @ w.double().t()
+    out2 = pkg.kernels.linear_tc2(a, w)
+    assert float((out2.double() - ref2).abs().max() / ref2.abs().max()) < 5e-6
+    out3 = pkg.kernels.linear_tc2(a, w, out=out2.clone(), accumulate=True)
+    assert float((out3.double() - 2 * ref2).abs().max() / ref2.abs().max()) < 1e-5
+
+
+@pytest.mark.parametrize("M,N,K1,K2", [(1024, 1536, 512, 512), (300, 200, 100, 60), (64, 64, 32, 4)])
+def test_linear_tc2_two_segments_and_strides(pkg, device, M, N, K1, K2):
+    """[A1|A2] concatenation along K with row-strided views (the GRU's [x|h] product)."""
+    g = torch.Generator().manual_seed(5)
+    big1 = torch.randn(M, K1 + 8, generator=g).to(device)
+    big2 = torch.randn(M, K2 + 12, generator=g).to(device)
+    a1, a2 = big1[:, 4:4 + K1], big2[:, 8:8 + K2]
+    w = (torch.randn(N, K1 + K2, generator=g) / (K1 + K2) ** 0.5).to(device)
+    ref = torch.cat([a1, a2], 1).double() @ w.double().t()
+    out = pkg.kernels.linear_tc2(a1, w, a2=a2)
+    assert float((out.double() - ref).abs().max() / ref.abs().max()) < 5e-6

@@ -110,7 +110,11 @@ class ImagineBwdIO(C.Structure):
         ("workspace", "v"), ("workspace_bytes", "sz")])
 
 
-STRUCTS = {"dv3_rssm_dims": RssmDims, "dv3_rssm_params": RssmParams, "dv3_observe_io": ObserveIO,
+class TcOperand(C.Structure):
+    _fields_ = _fields([("hi", "f"), ("lo", "f"), ("ld", "i32"), ("mn_major", "i32")])
+
+
+STRUCTS = {"dv3_tc_operand": TcOperand, "dv3_rssm_dims": RssmDims, "dv3_rssm_params": RssmParams, "dv3_observe_io": ObserveIO,
            "dv3_observe_bwd_io": ObserveBwdIO, "dv3_actor": Actor, "dv3_imagine_io": ImagineIO,
            "dv3_imagine_bwd_io": ImagineBwdIO}
 
@@ -150,6 +154,9 @@ SIGNATURES = {
     "dv3_linear_tc_scratch_bytes": (C.c_size_t, [_i32, _i32, _i32]),
     "dv3_linear_tc_fwd": (C.c_int, [_f, _i32, _i32, _f, _i32, _i32, _f, _f, _i32, _f, _i32, _i32,
                                     _i32, _i32, _v, C.c_size_t, _v]),
+    "dv3_gemm_tc": (C.c_int, [_P(TcOperand), _i32, _P(TcOperand), _i32, _P(TcOperand), _f, _f, _i32,
+                              _f, _i32, _i32, _i32, _i32, _v]),
+    "dv3_split_tf32": (C.c_int, [_f, _i32, _i32, _i32, _f, _f, _i32, _v]),
     "dv3_linear_tc2_fwd": (C.c_int, [_f, _i32, _i32, _f, _i32, _i32, _f, _i32, _f, _f, _i32, _f,
                                      _i32, _i32, _i32, _i32, _v]),
     "dv3_transpose": (C.c_int, [_f, _i32, _i32, _i32, _f, _v]),

@@ -194,6 +194,18 @@ int tc_split_t(const float* in, int ld, int R, int C, float* hi, float* lo, cuda
 int tc_gemm(const float* Ah, const float* Al, const float* Wh, const float* Wl, const float* bias,
             const float* addend, int ldadd, float* C, int ldc, int M, int N, int K, int accumulate,
             cudaStream_t st);
+// one operand of the persistent tcgen05 GEMM (dv3_umma2.cu): hi/lo planes with a common row
+// stride; mn == false: stored [rows, K] ("K-major"), mn == true: stored [K, rows].
+// lo == nullptr on every operand = raw fp32 operands, split inside the SM (slower, no pre-pass).
+struct TcOperand {
+  const float* hi;
+  const float* lo;
+  int ld;
+  bool mn;
+};
+int tc_gemm_ops(const TcOperand& A1, int K1, const TcOperand* A2, int K2, const TcOperand& B,
+                const float* bias, const float* addend, int ldadd, float* C, int ldc, int M, int N,
+                int accumulate, cudaStream_t st);
 // persistent (single cooperative launch) forward recurrence of observe; *used == false -> not
 // applicable for these shapes, run the stepwise launches instead (dv3_observe_persistent.cu)
 int observe_fwd_persistent(const dv3_rssm_dims* d, const dv3_rssm_params* p,

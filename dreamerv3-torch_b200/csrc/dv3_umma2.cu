@@ -1,15 +1,18 @@
-// fp32-accurate GEMM on the tcgen05 tensor cores, raw-operand version:
-//     C[M,N] = [A1 | A2][M, K1+K2] W[N, K1+K2]^T  (+bias) (+addend) (+C)
-// A1/A2/W are plain fp32 matrices with arbitrary (16-byte aligned) row strides; nothing is
-// pre-processed on the host side of the launch.
+// fp32-accurate GEMM on the tcgen05 tensor cores (persistent, warp-specialised):
+//     C[M,N] = [A1 | A2][M, K1+K2] B[N, K1+K2]^T  (+bias) (+addend) (+C)
 //
 // 3xTF32: x = hi + lo with hi = x & 0xFFFFE000 (exact in tf32) and lo = x - hi (exact in fp32);
-//     A W^T ~= A_hi W_hi^T + A_hi W_lo^T + A_lo W_hi^T      (dropped lo*lo term ~2^-22 relative)
-// The split happens inside the SM: TMA brings each fp32 operand tile from L2 exactly once
-// (128B-swizzled), four converter warps rewrite it in place as hi and write lo beside it, then the
-// MMA warp issues the three kind::tf32 products.  Compared with loading pre-split operands this
-// halves the L2 -> SM traffic, which is what bounds the 128 x BN tile (measured: the pre-split
-// kernel moved 10.5 TB/s through L2 at 60 % tensor-pipe activity).
+//     A B^T ~= A_hi B_hi^T + A_hi B_lo^T + A_lo B_hi^T      (dropped lo*lo term ~2^-22 relative)
+//
+// Two operand modes:
+//   * pre-split (the fast path): every operand is given as its (hi, lo) pair, in either storage
+//     order -- "K-major" [rows, K] or "MN-major" [K, rows] -- selected through the UMMA
+//     descriptors, so y = x W^T, dx = dy W and dW = dy^T x all read the same split arrays with
+//     no transposes.
+//   * raw (RAW=true): plain fp32 operands; TMA brings each tile once and four converter warps
+//     split it in shared memory.  Halves L2 -> SM traffic, but measured 20-35 % slower: the
+//     kernel is bound by shared-memory bandwidth (TMA writes + UMMA operand reads share
+//     128 B/clk/SM: 160 KB per k-block pre-split vs 224 KB with the in-SM split), not by L2.
 //
 // Persistent: grid = min(tiles, SMs); every role loops over tile = blockIdx.x + i * gridDim.x.
 //   warp 0      TMA producer (one lane)
@@ -40,24 +43,52 @@ struct Gemm2Args {
   int ldc, ldadd, M, N, K1;
   int nk1, nk;                           // k-blocks of segment 1 / total
   int tiles_n, tiles;
+  int splitk, nkp, units;                // K partitions, k-blocks per partition, tiles * splitk
   int accumulate;
 };
 
 template <int BN>
 struct G2Cfg {
-  static constexpr int STAGES = (BN == 128) ? 3 : 4;
+  static constexpr int STAGES = (BN == 128) ? 3 : (BN == 64) ? 4 : 5;
   static constexpr uint32_t A_BYTES = G2_BM * G2_BK * 4;            // 16 KB
   static constexpr uint32_t B_BYTES = BN * G2_BK * 4;
   static constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-  static constexpr uint32_t TMEM_COLS = (4 * BN <= 256) ? 256 : 512;
+  static constexpr uint32_t TMEM_COLS = (4 * BN <= 128) ? 128 : (4 * BN <= 256) ? 256 : 512;
+  static constexpr int EPI_WARPS = (BN >= 64) ? 8 : 4;   // a thread drains >= 32 columns
   static constexpr int NBAR = 3 * STAGES + 6;
   static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + NBAR * 8 + 64;
 };
 
-template <int BN, bool MASK_HI>
+// MN-major tf32 operands only exist in the "128B swizzle, 32B atom" layout (layout type 1; TMA
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): rows of 32 MN-floats (128 B) per k, 32-byte chunks XORed
+// with (k % 4), i.e. atoms of 4 k-rows = 512 B.  Canonical form ((8,n),(4,k)):((1,LBO),(8,SBO)) in
+// 16-byte units: SBO = 512 B between k-atoms, LBO = 4096 B between the 32-float-wide MN blocks
+// (one TMA box [32 k x 32 mn] each).
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (256ull << 16) | (32ull << 32) | (1ull << 46) |
+         (1ull << 61);
+}
+
+struct Gemm2Maps {
+  CUtensorMap a1h, a1l, a2h, a2l, bh, bl;   // raw mode uses a1h, a2h, bh only
+};
+
+// one operand tile of `rows` rows for k-block starting at k0: K-major = one box [rows x 32 k],
+// MN-major = rows/32 boxes [32 k x 32 rows], 4 KB apart
+template <bool MN>
+__device__ __forceinline__ void load_tile(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                          int k0, int r0, int rows) {
+  if (!MN) {
+    tma_load_2d(dst, map, bar, k0, r0);
+  } else {
+    for (int j = 0; j < rows / 32; ++j) tma_load_2d(dst + j * 4096, map, bar, r0 + 32 * j, k0);
+  }
+}
+
+template <int BN, bool AMN, bool BMN, bool RAW>
 __global__ void __launch_bounds__(G2_THREADS, 1)
-umma2_gemm_kernel(const __grid_constant__ CUtensorMap mA1, const __grid_constant__ CUtensorMap mA2,
-                  const __grid_constant__ CUtensorMap mW, Gemm2Args g) {
+umma2_gemm_kernel(const __grid_constant__ Gemm2Maps mp, Gemm2Args g) {
+  constexpr bool MASK_HI = true;
   using Cfg = G2Cfg<BN>;
   constexpr int ST = Cfg::STAGES;
   constexpr uint32_t A_BYTES = Cfg::A_BYTES, B_BYTES = Cfg::B_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES;
@@ -70,7 +101,6 @@ umma2_gemm_kernel(const __grid_constant__ CUtensorMap mA1, const __grid_constant
                  tfull0 = empty0 + 8 * ST, tempty0 = tfull0 + 16, lempty0 = tempty0 + 16;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nk = g.nk;
-  const int nchunks = (nk + G2_CH - 1) / G2_CH;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < ST; ++s) {
@@ -80,8 +110,8 @@ umma2_gemm_kernel(const __grid_constant__ CUtensorMap mA1, const __grid_constant
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull0 + 8 * b, 1);
-      mbar_init(tempty0 + 8 * b, 8);     // one arrive per epilogue warp
-      mbar_init(lempty0 + 8 * b, 8);
+      mbar_init(tempty0 + 8 * b, Cfg::EPI_WARPS);     // one arrive per epilogue warp
+      mbar_init(lempty0 + 8 * b, Cfg::EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -100,23 +130,26 @@ umma2_gemm_kernel(const __grid_constant__ CUtensorMap mA1, const __grid_constant
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
       int it = 0;
-      for (int tile = blockIdx.x; tile < g.tiles; tile += gridDim.x) {
+      for (int unit = blockIdx.x; unit < g.units; unit += gridDim.x) {
+        const int tile = unit % g.tiles, kb0 = (unit / g.tiles) * g.nkp;
+        const int kb1 = min(nk, kb0 + g.nkp);
         const int m0 = (tile / g.tiles_n) * G2_BM, n0 = (tile % g.tiles_n) * BN;
-        for (int kb = 0; kb < nk; ++kb, ++it) {
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % ST;
           const uint32_t ph = (it / ST) & 1;
           mbar_wait(empty0 + 8 * s, ph ^ 1);
           const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
-          mbar_expect_tx(full0 + 8 * s, A_BYTES + B_BYTES);
-          int wk;
-          if (kb < g.nk1) {
-            tma_load_2d(base, &mA1, full0 + 8 * s, kb * G2_BK, m0);
-            wk = kb * G2_BK;
-          } else {
-            tma_load_2d(base, &mA2, full0 + 8 * s, (kb - g.nk1) * G2_BK, m0);
-            wk = g.K1 + (kb - g.nk1) * G2_BK;
+          const uint32_t bar = full0 + 8 * s;
+          mbar_expect_tx(bar, RAW ? (A_BYTES + B_BYTES) : STAGE_BYTES);
+          const bool seg1 = kb < g.nk1;
+          const int ak = seg1 ? kb * G2_BK : (kb - g.nk1) * G2_BK;
+          const int wk = seg1 ? ak : g.K1 + ak;
+          load_tile<AMN>(base, seg1 ? &mp.a1h : &mp.a2h, bar, ak, m0, G2_BM);
+          load_tile<BMN>(base + 2 * A_BYTES, &mp.bh, bar, wk, n0, BN);
+          if (!RAW) {
+            load_tile<AMN>(base + A_BYTES, seg1 ? &mp.a1l : &mp.a2l, bar, ak, m0, G2_BM);
+            load_tile<BMN>(base + 2 * A_BYTES + B_BYTES, &mp.bl, bar, wk, n0, BN);
           }
-          tma_load_2d(base + 2 * A_BYTES, &mW, full0 + 8 * s, wk, n0);
         }
       }
     }
@@ -124,40 +157,45 @@ umma2_gemm_kernel(const __grid_constant__ CUtensorMap mA1, const __grid_constant
   } else if (warp == 1) {
     // ------------------------------ MMA issuer --------------------------------
     if (lane == 0) {
-      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+      // c=F32, a=b=TF32; bit 15/16 = A/B MN-major; N>>3 at [17,23), M>>4 at [24,29)
+      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)AMN << 15) |
+                                 ((uint32_t)BMN << 16) | ((uint32_t)(BN >> 3) << 17) |
                                  ((uint32_t)(G2_BM >> 4) << 24);
+      constexpr uint32_t A_KSTEP = AMN ? 1024 : 32, B_KSTEP = BMN ? 1024 : 32;
       int it = 0, cc = 0, tl = 0;
-      for (int tile = blockIdx.x; tile < g.tiles; tile += gridDim.x, ++tl) {
+      for (int unit = blockIdx.x; unit < g.units; unit += gridDim.x, ++tl) {
+        const int kb0 = (unit / g.tiles) * g.nkp, kb1 = min(nk, kb0 + g.nkp);
         const int lb = tl & 1;
         mbar_wait(lempty0 + 8 * lb, ((tl >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t acc_lo = tmem_base + (2 + lb) * BN;
         int buf = 0;
-        for (int kb = 0; kb < nk; ++kb, ++it) {
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % ST;
           const uint32_t ph = (it / ST) & 1;
-          const int kin = kb % G2_CH;
+          const int kin = (kb - kb0) % G2_CH;
           if (kin == 0) {
             buf = cc & 1;
             mbar_wait(tempty0 + 8 * buf, ((cc >> 1) & 1) ^ 1);
             tc_fence_after();
           }
-          mbar_wait(conv0 + 8 * s, ph);
+          mbar_wait((RAW ? conv0 : full0) + 8 * s, ph);
           tc_fence_after();
           const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
           const uint32_t acc_hi = tmem_base + buf * BN;
 #pragma unroll
           for (int k = 0; k < G2_BK / 8; ++k) {
-            const uint64_t ah = umma_desc(base + k * 32);
-            const uint64_t al = umma_desc(base + A_BYTES + k * 32);
-            const uint64_t bh = umma_desc(base + 2 * A_BYTES + k * 32);
-            const uint64_t bl = umma_desc(base + 2 * A_BYTES + B_BYTES + k * 32);
-            umma_tf32(acc_lo, al, bh, idesc, (kb | k) != 0);
+            const uint32_t ao = base + k * A_KSTEP, bo = base + 2 * A_BYTES + k * B_KSTEP;
+            const uint64_t ah = AMN ? umma_desc_mn(ao) : umma_desc(ao);
+            const uint64_t al = AMN ? umma_desc_mn(ao + A_BYTES) : umma_desc(ao + A_BYTES);
+            const uint64_t bh = BMN ? umma_desc_mn(bo) : umma_desc(bo);
+            const uint64_t bl = BMN ? umma_desc_mn(bo + B_BYTES) : umma_desc(bo + B_BYTES);
+            umma_tf32(acc_lo, al, bh, idesc, ((kb - kb0) | k) != 0);
             umma_tf32(acc_lo, ah, bl, idesc, 1);
             umma_tf32(acc_hi, ah, bh, idesc, (kin | k) != 0);
           }
           umma_commit(empty0 + 8 * s);
-          if (kin == G2_CH - 1 || kb == nk - 1) {
+          if (kin == G2_CH - 1 || kb == kb1 - 1) {
             umma_commit(tfull0 + 8 * buf);
             ++cc;
           }
@@ -165,12 +203,13 @@ umma2_gemm_kernel(const __grid_constant__ CUtensorMap mA1, const __grid_constant
       }
     }
     __syncwarp();
-  } else if (warp >= G2_CONV_WARP0) {
+  } else if (RAW && warp >= G2_CONV_WARP0) {
     // ------------------------------ converters --------------------------------
     const int ct = threadIdx.x - G2_CONV_WARP0 * 32;     // 0..127
     int it = 0;
-    for (int tile = blockIdx.x; tile < g.tiles; tile += gridDim.x) {
-      for (int kb = 0; kb < nk; ++kb, ++it) {
+    for (int unit = blockIdx.x; unit < g.units; unit += gridDim.x) {
+      const int kb0 = (unit / g.tiles) * g.nkp, kb1 = min(nk, kb0 + g.nkp);
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
         const int s = it % ST;
         const uint32_t ph = (it / ST) & 1;
         mbar_wait(full0 + 8 * s, ph);
@@ -199,13 +238,15 @@ umma2_gemm_kernel(const __grid_constant__ CUtensorMap mA1, const __grid_constant
         if (lane == 0) mbar_arrive(conv0 + 8 * s);
       }
     }
-  } else if (warp >= G2_EPI_WARP0) {
+  } else if (warp >= G2_EPI_WARP0 && warp < G2_EPI_WARP0 + Cfg::EPI_WARPS) {
     // ------------------------------ epilogue ----------------------------------
-    constexpr int HW = BN / 2;                            // columns per epilogue thread
+    constexpr int HW = BN / (Cfg::EPI_WARPS / 4);         // columns per epilogue thread
     const int q = warp & 3, half = (warp - G2_EPI_WARP0) >> 2;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * HW);
     int cc = 0, tl = 0;
-    for (int tile = blockIdx.x; tile < g.tiles; tile += gridDim.x, ++tl) {
+    for (int unit = blockIdx.x; unit < g.units; unit += gridDim.x, ++tl) {
+      const int tile = unit % g.tiles, ks = unit / g.tiles;
+      const int nchunks = (min(nk, (ks + 1) * g.nkp) - ks * g.nkp + G2_CH - 1) / G2_CH;
       const int m0 = (tile / g.tiles_n) * G2_BM, n0 = (tile % g.tiles_n) * BN + half * HW;
       const int row = m0 + q * 32 + lane;
       const int lb = tl & 1;
@@ -241,7 +282,22 @@ umma2_gemm_kernel(const __grid_constant__ CUtensorMap mA1, const __grid_constant
       __syncwarp();
       if (lane == 0) mbar_arrive(lempty0 + 8 * lb);
 
-      if (row < g.M) {
+      if (row < g.M && g.splitk > 1) {
+        // split-K: partial sums meet in C through fp32 atomics (C zeroed / preloaded by the host
+        // side of the launch); bias and addend ride on partition 0
+        float* crow = g.C + (size_t)row * g.ldc;
+        const float* arow = (g.addend && ks == 0) ? g.addend + (size_t)row * g.ldadd : nullptr;
+#pragma unroll
+        for (int j = 0; j < HW; ++j) {
+          const int col = n0 + j;
+          if (col < g.N) {
+            float r = sum[j];
+            if (g.bias && ks == 0) r += g.bias[col];
+            if (arow) r += arow[col];
+            atomicAdd(crow + col, r);
+          }
+        }
+      } else if (row < g.M) {
         float* crow = g.C + (size_t)row * g.ldc;
         const float* arow = g.addend ? g.addend + (size_t)row * g.ldadd : nullptr;
         const bool vec = ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) &&
@@ -299,19 +355,23 @@ static EncodeTiledFn2 encode_fn2() {
   return fn;
 }
 
-// [rows, K] fp32, row stride ld floats; box = 32 floats (one 128B swizzle row) x box_rows
-static int make_map2(CUtensorMap* m, const float* base, int rows, int K, int ld, int box_rows) {
+// Tensor map of one operand plane.  K-major: memory is [rows, K] (row stride ld), box = 32 k x
+// box_rows rows.  MN-major: memory is [K, rows] (row stride ld), box = 32 rows x 32 k.
+static int make_map2(CUtensorMap* m, const float* base, int rows, int K, int ld, int box_rows,
+                     bool mn) {
   EncodeTiledFn2 fn = encode_fn2();
   DV3_REQUIRE(fn, DV3_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t dims[2] = {(cuuint64_t)(mn ? rows : K), (cuuint64_t)(mn ? K : rows)};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {(cuuint32_t)G2_BK, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)G2_BK, (cuuint32_t)(mn ? G2_BK : box_rows)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides,
-                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  mn ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   DV3_REQUIRE(r == CUDA_SUCCESS, DV3_ERR_CUDA,
-              "cuTensorMapEncodeTiled failed (%d) rows=%d K=%d ld=%d", (int)r, rows, K, ld);
+              "cuTensorMapEncodeTiled failed (%d) rows=%d K=%d ld=%d mn=%d", (int)r, rows, K, ld,
+              (int)mn);
   return 0;
 }
 
@@ -326,78 +386,160 @@ static int sm_count() {
   return sms;
 }
 
-static int g_mask_hi = -1;   // DV3_TC_MASK_HI=0: leave the raw fp32 word as the "hi" operand
-
-template <int BN>
-static int launch_umma2(const CUtensorMap& mA1, const CUtensorMap& mA2, const CUtensorMap& mW,
-                        Gemm2Args g, double flops, cudaStream_t st) {
+template <int BN, bool AMN, bool BMN, bool RAW>
+static int launch_umma2(const Gemm2Maps& mp, Gemm2Args g, double flops, cudaStream_t st) {
   using Cfg = G2Cfg<BN>;
-  if (g_mask_hi < 0) {
-    const char* e = getenv("DV3_TC_MASK_HI");
-    g_mask_hi = (e && e[0] == '0') ? 0 : 1;
-  }
+  auto kern = umma2_gemm_kernel<BN, AMN, BMN, RAW>;
   static bool attr = false;
   if (!attr) {
-    DV3_CHECK_CUDA(cudaFuncSetAttribute(umma2_gemm_kernel<BN, true>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-    DV3_CHECK_CUDA(cudaFuncSetAttribute(umma2_gemm_kernel<BN, false>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    DV3_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)Cfg::SMEM));
     attr = true;
   }
   g.tiles_n = (g.N + BN - 1) / BN;
   g.tiles = g.tiles_n * ((g.M + G2_BM - 1) / G2_BM);
-  const int grid = g.tiles < sm_count() ? g.tiles : sm_count();
+  if (g.splitk < 1) g.splitk = 1;
+  g.nkp = (g.nk + g.splitk - 1) / g.splitk;
+  g.splitk = (g.nk + g.nkp - 1) / g.nkp;           // no empty partition
+  g.units = g.tiles * g.splitk;
+  if (g.splitk > 1 && !g.accumulate)
+    DV3_CHECK_CUDA(cudaMemset2DAsync(g.C, (size_t)g.ldc * 4, 0, (size_t)g.N * 4, g.M, st));
+  const int grid = g.units < sm_count() ? g.units : sm_count();
   const bool prof = prof_on();
   if (prof) prof_begin(st);
-  if (g_mask_hi)
-    umma2_gemm_kernel<BN, true><<<grid, G2_THREADS, Cfg::SMEM, st>>>(mA1, mA2, mW, g);
-  else
-    umma2_gemm_kernel<BN, false><<<grid, G2_THREADS, Cfg::SMEM, st>>>(mA1, mA2, mW, g);
+  kern<<<grid, G2_THREADS, Cfg::SMEM, st>>>(mp, g);
   if (prof) prof_end(st, 1, flops);
   DV3_CHECK_LAUNCH("umma2_gemm_kernel");
   return 0;
+}
+
+template <int BN, bool RAW>
+static int dispatch_major(bool amn, bool bmn, const Gemm2Maps& mp, const Gemm2Args& g, double flops,
+                          cudaStream_t st) {
+  if (RAW || (!amn && !bmn)) return launch_umma2<BN, false, false, RAW>(mp, g, flops, st);
+  if (!amn && bmn) return launch_umma2<BN, false, true, false>(mp, g, flops, st);
+  if (amn && !bmn) return launch_umma2<BN, true, false, false>(mp, g, flops, st);
+  return launch_umma2<BN, true, true, false>(mp, g, flops, st);
 }
 
 static bool tma_ok(const float* p, int ld) {
   return p && (reinterpret_cast<uintptr_t>(p) & 15) == 0 && ld % 4 == 0;
 }
 
-bool tc_gemm_raw_ok(const float* A1, int lda1, const float* A2, int lda2, const float* W, int ldw) {
-  return tma_ok(A1, lda1) && (!A2 || tma_ok(A2, lda2)) && tma_ok(W, ldw);
+// N-tile width (and K partitions, when the caller allows them) by a small cost model:
+// waves x k-blocks x (time per k-block).  The k-block time is set by shared-memory traffic (TMA
+// writes + UMMA operand reads at 128 B/clk: 160 / 120 / 100 KB per k-block for BN = 128 / 64 /
+// 32), measured 1250 / 940 / 780 clk.  Split-K pays a memset and an atomic epilogue.
+static void pick_shape(int M, int N, int nk, bool allow_splitk, int* bn_out, int* splitk_out) {
+  const int tm = (M + G2_BM - 1) / G2_BM, sms = sm_count();
+  const int bns[3] = {128, 64, 32};
+  const long long cost[3] = {1250, 940, 780};
+  long long best_t = -1;
+  *bn_out = 32; *splitk_out = 1;
+  for (int i = 0; i < 3; ++i) {
+    if (bns[i] > 32 && N <= bns[i] / 2) continue;          // mostly padding
+    const int tiles = tm * ((N + bns[i] - 1) / bns[i]);
+    int sk = 1;
+    if (allow_splitk && tiles < sms) {
+      sk = sms / tiles;
+      const int cap = nk / 8;                              // >= 8 k-blocks per partition
+      if (sk > cap) sk = cap;
+      if (sk < 1) sk = 1;
+    }
+    const int nkp = (nk + sk - 1) / sk;
+    long long t = (long long)((tiles * sk + sms - 1) / sms) * nkp * cost[i];
+    if (sk > 1) t += 8000;
+    if (best_t < 0 || t < best_t) { best_t = t; *bn_out = bns[i]; *splitk_out = sk; }
+  }
 }
 
-// C = [A1|A2] W^T (+bias +addend) straight from fp32 operands.  A2 may be NULL (then K2 ignored).
-int tc_gemm_raw(const float* A1, int lda1, int K1, const float* A2, int lda2, int K2,
-                const float* W, int ldw, const float* bias, const float* addend, int ldadd,
-                float* C, int ldc, int M, int N, int accumulate, cudaStream_t st) {
+// C = [A1|A2] B^T (+bias +addend) from pre-split operands.  A2 may be NULL (K2 ignored); it shares
+// A1's storage order.  lo == NULL on all operands selects the raw mode (K-major only).
+// accumulate: bit 0 = add into C; bit 1 = the kernel may partition K over CTAs and combine the
+// partial sums with fp32 atomics (summation order then not fixed: used for parameter gradients).
+int tc_gemm_ops(const TcOperand& A1, int K1, const TcOperand* A2, int K2, const TcOperand& B,
+                const float* bias, const float* addend, int ldadd, float* C, int ldc, int M, int N,
+                int accumulate, cudaStream_t st) {
   if (!A2) K2 = 0;
   DV3_REQUIRE(M > 0 && N > 0 && K1 > 0 && K2 >= 0, DV3_ERR_BAD_SHAPE,
-              "tc_gemm_raw: M=%d N=%d K1=%d K2=%d", M, N, K1, K2);
-  DV3_REQUIRE(tc_gemm_raw_ok(A1, lda1, A2, lda2, W, ldw), DV3_ERR_BAD_SHAPE,
-              "tc_gemm_raw: operands must be 16-byte aligned with row strides %% 4 == 0 "
-              "(lda1=%d lda2=%d ldw=%d)", lda1, lda2, ldw);
+              "tc_gemm: M=%d N=%d K1=%d K2=%d", M, N, K1, K2);
+  const bool raw = !A1.lo;
+  DV3_REQUIRE(tma_ok(A1.hi, A1.ld) && tma_ok(B.hi, B.ld) && (!A2 || tma_ok(A2->hi, A2->ld)),
+              DV3_ERR_BAD_SHAPE,
+              "tc_gemm: operands must be 16-byte aligned with row strides %% 4 == 0 (lda=%d ldb=%d)",
+              A1.ld, B.ld);
+  DV3_REQUIRE(raw ? (!B.lo && (!A2 || !A2->lo) && !A1.mn && !B.mn)
+                  : (tma_ok(A1.lo, A1.ld) && tma_ok(B.lo, B.ld) && (!A2 || tma_ok(A2->lo, A2->ld))),
+              DV3_ERR_BAD_SHAPE, "tc_gemm: mixed raw / pre-split operands");
+  DV3_REQUIRE(!A2 || A2->mn == A1.mn, DV3_ERR_BAD_SHAPE, "tc_gemm: A segments differ in order");
   const int K = K1 + K2;
-  // narrow N tiles when 128-wide ones would leave most of the machine idle
-  const int tiles128 = ((N + 127) / 128) * ((M + G2_BM - 1) / G2_BM);
-  const bool wide = N > 64 && tiles128 >= 96;
-  const int BN = wide ? 128 : 64;
-  CUtensorMap mA1, mA2, mW;
-  DV3_TRY(make_map2(&mA1, A1, M, K1, lda1, G2_BM));
-  if (A2) DV3_TRY(make_map2(&mA2, A2, M, K2, lda2, G2_BM));
-  else mA2 = mA1;
-  DV3_TRY(make_map2(&mW, W, N, K, ldw, BN));
+  const int nk_all = (K1 + G2_BK - 1) / G2_BK + (K2 + G2_BK - 1) / G2_BK;
+  int BN = 32, splitk = 1;
+  pick_shape(M, N, nk_all, (accumulate & 2) != 0, &BN, &splitk);
+  Gemm2Maps mp;
+  DV3_TRY(make_map2(&mp.a1h, A1.hi, M, K1, A1.ld, G2_BM, A1.mn));
+  if (!raw) DV3_TRY(make_map2(&mp.a1l, A1.lo, M, K1, A1.ld, G2_BM, A1.mn));
+  else mp.a1l = mp.a1h;
+  if (A2) {
+    DV3_TRY(make_map2(&mp.a2h, A2->hi, M, K2, A2->ld, G2_BM, A2->mn));
+    if (!raw) DV3_TRY(make_map2(&mp.a2l, A2->lo, M, K2, A2->ld, G2_BM, A2->mn));
+    else mp.a2l = mp.a2h;
+  } else {
+    mp.a2h = mp.a1h; mp.a2l = mp.a1l;
+  }
+  DV3_TRY(make_map2(&mp.bh, B.hi, N, K, B.ld, BN, B.mn));
+  if (!raw) DV3_TRY(make_map2(&mp.bl, B.lo, N, K, B.ld, BN, B.mn));
+  else mp.bl = mp.bh;
   Gemm2Args g{};
   g.C = C; g.bias = bias; g.addend = addend; g.ldc = ldc; g.ldadd = ldadd; g.M = M; g.N = N;
   g.K1 = K1; g.nk1 = (K1 + G2_BK - 1) / G2_BK; g.nk = g.nk1 + (K2 + G2_BK - 1) / G2_BK;
-  g.accumulate = accumulate;
+  g.accumulate = accumulate & 1;
+  g.splitk = splitk;
   const double flops = 2.0 * M * N * K;
-  if (wide) return launch_umma2<128>(mA1, mA2, mW, g, flops, st);
-  return launch_umma2<64>(mA1, mA2, mW, g, flops, st);
+  if (raw) {
+    if (BN == 128) return dispatch_major<128, true>(false, false, mp, g, flops, st);
+    if (BN == 64) return dispatch_major<64, true>(false, false, mp, g, flops, st);
+    return dispatch_major<32, true>(false, false, mp, g, flops, st);
+  }
+  if (BN == 128) return dispatch_major<128, false>(A1.mn, B.mn, mp, g, flops, st);
+  if (BN == 64) return dispatch_major<64, false>(A1.mn, B.mn, mp, g, flops, st);
+  return dispatch_major<32, false>(A1.mn, B.mn, mp, g, flops, st);
 }
 
 }  // namespace dv3
 
-// C ABI: tensor-core Linear straight from fp32 operands (no scratch).
+static dv3::TcOperand to_op(const dv3_tc_operand* o) {
+  dv3::TcOperand r{};
+  if (o) { r.hi = o->hi; r.lo = o->lo; r.ld = o->ld; r.mn = o->mn_major != 0; }
+  return r;
+}
+
+// C ABI (see include/dv3_b200.h)
+extern "C" int dv3_gemm_tc(const dv3_tc_operand* A1, int32_t K1, const dv3_tc_operand* A2,
+                           int32_t K2, const dv3_tc_operand* B, const float* bias,
+                           const float* addend, int32_t ldadd, float* C, int32_t ldc, int32_t M,
+                           int32_t N, int32_t accumulate, void* stream) {
+  using namespace dv3;
+  DV3_REQUIRE(M >= 0 && N >= 0, DV3_ERR_BAD_SHAPE, "gemm_tc: M=%d N=%d", M, N);
+  if (M == 0 || N == 0) return 0;
+  DV3_REQUIRE(A1 && B && C && A1->hi && B->hi, DV3_ERR_NULL, "gemm_tc: null pointer");
+  TcOperand a1 = to_op(A1), a2 = to_op(A2), b = to_op(B);
+  return tc_gemm_ops(a1, K1, (A2 && A2->hi) ? &a2 : nullptr, K2, b, bias, addend, ldadd, C, ldc, M,
+                     N, accumulate, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int dv3_split_tf32(const float* x, int32_t ld, int32_t rows, int32_t cols, float* hi,
+                              float* lo, int32_t ld_out, void* stream) {
+  using namespace dv3;
+  DV3_REQUIRE(rows >= 0 && cols >= 0 && ld_out >= cols, DV3_ERR_BAD_SHAPE,
+              "split_tf32: rows=%d cols=%d ld_out=%d", rows, cols, ld_out);
+  if (rows == 0 || cols == 0) return 0;
+  DV3_REQUIRE(x && hi && lo, DV3_ERR_NULL, "split_tf32: null pointer");
+  return tc_split(x, ld, cols, nullptr, 0, 0, rows, hi, lo, static_cast<cudaStream_t>(stream),
+                  ld_out);
+}
+
+// raw-operand convenience entry (no scratch, in-SM split)
 extern "C" int dv3_linear_tc2_fwd(const float* A1, int32_t lda1, int32_t K1, const float* A2,
                                   int32_t lda2, int32_t K2, const float* W, int32_t ldw,
                                   const float* bias, const float* addend, int32_t ldadd, float* C,
@@ -407,6 +549,7 @@ extern "C" int dv3_linear_tc2_fwd(const float* A1, int32_t lda1, int32_t K1, con
   DV3_REQUIRE(M >= 0 && N >= 0, DV3_ERR_BAD_SHAPE, "linear_tc2_fwd: M=%d N=%d", M, N);
   if (M == 0 || N == 0) return 0;
   DV3_REQUIRE(A1 && W && C, DV3_ERR_NULL, "linear_tc2_fwd: null pointer");
-  return tc_gemm_raw(A1, lda1, K1, A2, lda2, K2, W, ldw, bias, addend, ldadd, C, ldc, M, N,
+  TcOperand a1{A1, nullptr, lda1, false}, a2{A2, nullptr, lda2, false}, b{W, nullptr, ldw, false};
+  return tc_gemm_ops(a1, K1, A2 ? &a2 : nullptr, K2, b, bias, addend, ldadd, C, ldc, M, N,
                      accumulate, static_cast<cudaStream_t>(stream));
 }

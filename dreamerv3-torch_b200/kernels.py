@@ -204,22 +204,110 @@ def linear_fwd(a1, w1, a2=None, w2=None, bias=None, addend=None):
     return out
 
 
-def linear_tc(a, w, bias=None, addend=None, trans_a=False, trans_w=False):
-    """C[M,N] = op(a) op(w)^T (+bias +addend) on the tcgen05 tensor cores (3xTF32 split,
-    fp32-accurate).  op(a) is [M,K] (a stored [K,M] when trans_a); op(w) is [N,K] (w stored [K,N]
-    when trans_w).  a / w must be contiguous 2-D."""
-    M, Kd = (a.shape[1], a.shape[0]) if trans_a else a.shape
-    N = w.shape[1] if trans_w else w.shape[0]
-    out = _empty(M, N, like=a)
+class Split:
+    """tf32 hi/lo planes of a 2-D fp32 tensor [rows, cols]: hi = x with the 13 low mantissa bits
+    cleared, lo = x - hi (so hi + lo == x exactly).  Both planes are [rows, ld] with ld = cols
+    rounded up to 4 (zero pad) so that every row is 16-byte aligned for TMA.  One Split serves
+    every product the tensor takes part in: as [rows, K] ("K-major") or, read transposed, as
+    [K, rows] ("MN-major") -- selected by descriptor bits in the kernel, never by copying."""
+    __slots__ = ("hi", "lo", "rows", "cols")
+
+    def __init__(self, hi, lo, rows, cols):
+        self.hi, self.lo, self.rows, self.cols = hi, lo, rows, cols
+
+    @property
+    def ld(self):
+        return self.hi.shape[1]
+
+    def operand(self, transposed):
+        o = L.TcOperand()
+        o.hi, o.lo, o.ld, o.mn_major = _raw(self.hi), _raw(self.lo), self.ld, int(transposed)
+        return o
+
+
+def _raw(t):
+    return None if t is None else C.cast(C.c_void_p(t.data_ptr()), C.POINTER(C.c_float))
+
+
+def split(x):
+    """x: 2-D fp32 CUDA tensor (row-strided views allowed) -> Split."""
+    if isinstance(x, Split):
+        return x
+    if x.dim() != 2 or x.dtype != torch.float32 or x.stride(1) != 1:
+        x = x.reshape(-1, x.shape[-1]).to(torch.float32).contiguous()
+    rows, cols = x.shape
+    ld = (cols + 3) & ~3
+    hi = torch.empty(rows, ld, dtype=torch.float32, device=x.device)
+    lo = torch.empty(rows, ld, dtype=torch.float32, device=x.device)
+    if rows and cols:
+        L.check(L.lib().dv3_split_tf32(_raw(x), x.stride(0), rows, cols, _raw(hi), _raw(lo), ld,
+                                       L.stream_ptr()), "split_tf32")
+    return Split(hi, lo, rows, cols)
+
+
+_WEIGHT_EPOCH = [0]
+
+
+def invalidate_weight_splits():
+    """Called by whatever rewrites parameters in place without going through autograd's version
+    counter (the fused Adam step, the slow-critic EMA)."""
+    _WEIGHT_EPOCH[0] += 1
+
+
+def split_param(w):
+    """Split of a weight.  For an nn.Parameter the planes are cached on the parameter object
+    itself and reused until the parameter changes: tools.Optimizer bumps a global epoch after
+    every step (torch's fused Adam does not move the autograd version counter), and the version
+    counter / storage pointer catch load_state_dict and re-assignment."""
+    if not isinstance(w, torch.nn.Parameter):
+        return split(w.detach())
+    tag = (_WEIGHT_EPOCH[0], w._version, w.data_ptr(), tuple(w.shape))
+    hit = getattr(w, "_dv3_split", None)
+    if hit is not None and hit[0] == tag:
+        return hit[1]
+    sp = split(w.detach())
+    w._dv3_split = (tag, sp)
+    return sp
+
+
+def gemm_tc(A, B, a_t=False, b_t=False, A2=None, bias=None, addend=None, out=None,
+            accumulate=False, split_k=False):
+    """C[M,N] = [op(A) | op(A2)] op(B)^T (+bias +addend, +out when accumulate) on the persistent
+    tcgen05 3xTF32 kernel.  A, A2, B are Splits (tensors are split on the fly).  op(X) = X when
+    the flag is False (X stored [rows, K]) and X^T when True (X stored [K, rows]).  So:
+    y = x W^T -> gemm_tc(x, W);  dx = dy W -> gemm_tc(dy, W, b_t=True);
+    dW = dy^T x -> gemm_tc(dy, x, a_t=True, b_t=True)."""
+    A, B = split(A), split(B)
+    M, K1 = (A.cols, A.rows) if a_t else (A.rows, A.cols)
+    N, K = (B.cols, B.rows) if b_t else (B.rows, B.cols)
+    K2 = 0
+    a2 = None
+    if A2 is not None:
+        A2 = split(A2)
+        K2 = A2.rows if a_t else A2.cols
+        a2 = A2.operand(a_t)
+    if K1 + K2 != K:
+        raise L.Dv3Error(f"gemm_tc: contraction mismatch {K1}+{K2} vs {K}")
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float32, device=A.hi.device)
     if M == 0 or N == 0:
         return out
-    nbytes = L.lib().dv3_linear_tc_scratch_bytes(M, N, Kd)
-    ws = _ws(nbytes, a.device)
-    L.check(L.lib().dv3_linear_tc_fwd(L.fptr(a), a.shape[1], int(trans_a), L.fptr(w), w.shape[1],
-                                      int(trans_w), L.fptr(bias), L.fptr(addend), N, L.fptr(out),
-                                      N, M, N, Kd, C.c_void_p(ws.data_ptr()), ws.numel(),
-                                      L.stream_ptr()), "linear_tc_fwd")
+    if K == 0:
+        if not accumulate:
+            out.zero_()
+        return out
+    a1, b = A.operand(a_t), B.operand(b_t)
+    L.check(L.lib().dv3_gemm_tc(C.byref(a1), K1, C.byref(a2) if a2 is not None else None, K2,
+                                C.byref(b), L.fptr(bias), L.fptr(addend), N, _raw(out),
+                                out.stride(0), M, N, int(accumulate) | (2 if split_k else 0),
+                                L.stream_ptr()), "gemm_tc")
     return out
+
+
+def linear_tc(a, w, bias=None, addend=None, trans_a=False, trans_w=False):
+    """C[M,N] = op(a) op(w)^T (+bias +addend), fp32-accurate on the tensor cores.  op(a) is
+    [M,K] (a stored [K,M] when trans_a); op(w) is [N,K] (w stored [K,N] when trans_w)."""
+    return gemm_tc(a, w, a_t=trans_a, b_t=trans_w, bias=bias, addend=addend)
 
 
 def linear_tc_fwd(a, w, bias=None, addend=None):
@@ -252,25 +340,30 @@ def linear_tc2(a1, w, a2=None, bias=None, addend=None, out=None, accumulate=Fals
 class _DenseLnSilu(torch.autograd.Function):
     """SiLU(LayerNorm(x W^T)) for x [M,K], W [U,K]: the Linear(no bias)+LN(eps 1e-3)+SiLU block of
     the reference MLPs (networks.py:623-632).  All three contractions (y, dx, dW) run on the
-    tensor-core GEMM, LN/SiLU forward and backward on the row kernels."""
+    tensor-core GEMM from one split each of x, W and dy; LN/SiLU forward and backward on the row
+    kernels."""
 
     @staticmethod
     def forward(ctx, x, W, g, b):
-        x, Wc = _f32(x), _c(W.detach())
-        pre = linear_tc(x, Wc)
+        xs, Ws = split(_f32(x)), split_param(W)
+        pre = gemm_tc(xs, Ws)
         out = ln_silu_fwd(pre, _c(g.detach()), _c(b.detach()))
-        ctx.save_for_backward(x, Wc, g.detach(), b.detach(), pre)
+        ctx.save_for_backward(g.detach(), b.detach(), pre, xs.hi, xs.lo, Ws.hi, Ws.lo)
+        ctx.shapes = (xs.rows, xs.cols, Ws.rows, Ws.cols)
         return out
 
     @staticmethod
     def backward(ctx, d_out):
-        x, W, g, b, pre = ctx.saved_tensors
+        g, b, pre, xh, xl, Wh, Wl = ctx.saved_tensors
+        M, Kd, U, _ = ctx.shapes
+        xs, Ws = Split(xh, xl, M, Kd), Split(Wh, Wl, U, Kd)
         d_pre, d_ln = ln_silu_bwd(pre, _c(g), _c(b), _f32(d_out))
         dx = dW = dg = db = None
+        ds = split(d_pre)
         if ctx.needs_input_grad[0]:
-            dx = linear_tc(d_pre, W, trans_w=True)                   # dy W
+            dx = gemm_tc(ds, Ws, b_t=True)                    # dy W
         if ctx.needs_input_grad[1]:
-            dW = linear_tc(d_pre, x, trans_a=True, trans_w=True)     # dy^T x
+            dW = gemm_tc(ds, xs, a_t=True, b_t=True, split_k=True)   # dy^T x
         if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
             dg, db = _ln_grads(pre, d_ln)
         return dx, dW, dg, db
@@ -281,19 +374,23 @@ class _LinearBias(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, W, bias):
-        x, Wc = _f32(x), _c(W.detach())
-        ctx.save_for_backward(x, Wc)
-        return linear_tc(x, Wc, None if bias is None else _c(bias.detach()))
+        xs, Ws = split(_f32(x)), split_param(W)
+        ctx.save_for_backward(xs.hi, xs.lo, Ws.hi, Ws.lo)
+        ctx.shapes = (xs.rows, xs.cols, Ws.rows, Ws.cols)
+        return gemm_tc(xs, Ws, bias=None if bias is None else _c(bias.detach()))
 
     @staticmethod
     def backward(ctx, d_out):
-        x, W = ctx.saved_tensors
+        xh, xl, Wh, Wl = ctx.saved_tensors
+        M, Kd, N, _ = ctx.shapes
+        xs, Ws = Split(xh, xl, M, Kd), Split(Wh, Wl, N, Kd)
         d_out = _f32(d_out)
+        ds = split(d_out)
         dx = dW = db = None
         if ctx.needs_input_grad[0]:
-            dx = linear_tc(d_out, W, trans_w=True)
+            dx = gemm_tc(ds, Ws, b_t=True)
         if ctx.needs_input_grad[1]:
-            dW = linear_tc(d_out, x, trans_a=True, trans_w=True)
+            dW = gemm_tc(ds, xs, a_t=True, b_t=True, split_k=True)
         if ctx.needs_input_grad[2]:
             db = d_out.sum(0)
         return dx, dW, db
@@ -434,19 +531,31 @@ class _Observe(torch.autograd.Function):
         if any(need.values()):
             r2 = lambda t: t.reshape(B * T, -1)
             hot = F.one_hot(sprev_idx.reshape(B * T, S).long(), Cc).reshape(B * T, SC).float()
-            dx, dg, dy, dz = r2(o["d_x_pre"]), r2(o["d_g_pre"]), r2(o["d_y_pre"]), r2(o["d_z_pre"])
+            dx, dg, dy, dz = (split(r2(o[k])) for k in ("d_x_pre", "d_g_pre", "d_y_pre", "d_z_pre"))
             dpo, dpr = r2(o["d_post_logit"]), r2(o["d_prior_logit"])
-            G["w_in"] = torch.cat([dx.t() @ hot, dx.t() @ r2(aprev)], 1)
+            dpos, dprs = split(dpo), split(dpr)
+            deters = split(r2(deter))
+            # dW = delta^T @ input over all B*T rows: transposed-operand tcgen05 products with the
+            # rows (K = B*T) partitioned over the SMs; column blocks of one weight are written
+            # through strided output views
+            dw = lambda d, inp, out=None: gemm_tc(d, inp, a_t=True, b_t=True, out=out, split_k=True)
+            G["w_in"] = torch.empty(Hd, SC + A, dtype=torch.float32, device=dev)
+            dw(dx, hot, G["w_in"][:, :SC])
+            dw(dx, r2(aprev), G["w_in"][:, SC:])
             G["ln_in_g"], G["ln_in_b"] = _ln_grads(r2(x_pre), r2(o["d_x_ln"]))
-            G["w_gru"] = torch.cat([dg.t() @ r2(x), dg.t() @ r2(hprev)], 1)
+            G["w_gru"] = torch.empty(3 * D, Hd + D, dtype=torch.float32, device=dev)
+            dw(dg, r2(x), G["w_gru"][:, :Hd])
+            dw(dg, r2(hprev), G["w_gru"][:, Hd:])
             G["ln_gru_g"], G["ln_gru_b"] = _ln_grads(r2(g_pre), r2(o["d_g_ln"]))
-            G["w_out"] = dy.t() @ r2(deter)
+            G["w_out"] = dw(dy, deters)
             G["ln_out_g"], G["ln_out_b"] = _ln_grads(r2(y_pre), r2(o["d_y_ln"]))
-            G["w_ims"] = dpr.t() @ r2(y)
+            G["w_ims"] = dw(dprs, r2(y))
             G["b_ims"] = dpr.sum(0)
-            G["w_obs"] = torch.cat([dz.t() @ r2(deter), dz.t() @ r2(embed)], 1)
+            G["w_obs"] = torch.empty(Hd, D + E, dtype=torch.float32, device=dev)
+            dw(dz, deters, G["w_obs"][:, :D])
+            dw(dz, r2(embed), G["w_obs"][:, D:])
             G["ln_obs_g"], G["ln_obs_b"] = _ln_grads(r2(z_pre), r2(o["d_z_ln"]))
-            G["w_os"] = dpo.t() @ r2(z)
+            G["w_os"] = dw(dpos, r2(z))
             G["b_os"] = dpo.sum(0)
             # RSSM.initial (networks.py:99-125): tanh(W) -> prior head -> mode (straight-through
             # on the normalised log-probs).  One row; differentiated with autograd.
@@ -609,21 +718,24 @@ class _Imagine(torch.autograd.Function):
         dm = o["d_mean_raw"].reshape(HN, A)
         top = a_act[Lr - 1].reshape(HN, U)
         ga = [None] * len(actor_params)
-        ga[3 * Lr], ga[3 * Lr + 1] = dm.t() @ top, dm.sum(0)
+        dw = lambda d, inp: gemm_tc(d, inp, a_t=True, b_t=True, split_k=True)
+        tops = split(top)
+        ga[3 * Lr], ga[3 * Lr + 1] = dw(dm, tops), dm.sum(0)
         d_act = dm @ actor_params[3 * Lr]
         if spec.dist == "normal":
             ds = o["d_std_raw"].reshape(HN, A)
-            ga[3 * Lr + 2], ga[3 * Lr + 3] = ds.t() @ top, ds.sum(0)
+            ga[3 * Lr + 2], ga[3 * Lr + 3] = dw(ds, tops), ds.sum(0)
             d_act = d_act + ds @ actor_params[3 * Lr + 2]
         for i in range(Lr - 1, -1, -1):
             pre = a_pre[i].reshape(HN, U)
             d_pre, d_ln = ln_silu_bwd(pre, actor_params[3 * i + 1], actor_params[3 * i + 2],
                                       _c(d_act))
+            dps = split(d_pre)
             inp = feat.reshape(HN, -1) if i == 0 else a_act[i - 1].reshape(HN, U)
-            ga[3 * i] = d_pre.t() @ inp
+            ga[3 * i] = dw(dps, inp)
             ga[3 * i + 1], ga[3 * i + 2] = _ln_grads(pre, d_ln)
             if i > 0:
-                d_act = d_pre @ actor_params[3 * i]
+                d_act = gemm_tc(dps, split(actor_params[3 * i]), b_t=True)
         need = ctx.needs_input_grad[9 + 17:]
         ga = [g if n else None for g, n in zip(ga, need)]
         return (None, None, None, None, None, None, None, None, None, *([None] * 17), *ga)

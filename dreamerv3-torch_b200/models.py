@@ -316,4 +316,5 @@ class ImagBehavior(nn.Module):
                     dst = list(self._slow_value.parameters())
                     torch._foreach_mul_(dst, 1 - mix)
                     torch._foreach_add_(dst, src, alpha=mix)
+                K.invalidate_weight_splits()
             self._updates += 1

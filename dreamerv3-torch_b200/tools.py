@@ -366,6 +366,7 @@ class Optimizer:
                 for p in params:
                     p.mul_(1 - self._wd)
         self._opt.step()
+        K.invalidate_weight_splits()
         self._opt.zero_grad(set_to_none=True)
         metrics[f"{self._name}_grad_norm"] = norm.detach()
         return metrics

@@ -343,6 +343,29 @@ int dv3_linear_tc_fwd(const float* A, int32_t lda, int32_t transA, const float* 
                       int32_t transW, const float* bias, const float* addend, int32_t ldadd,
                       float* C, int32_t ldc, int32_t M, int32_t N, int32_t K, void* scratch,
                       size_t scratch_bytes, void* stream);
+/* The tcgen05 GEMM proper: C[M,N] = [A1|A2] B^T (+bias +addend, +C when accumulate != 0) from
+ * operands already split into tf32 hi/lo planes (dv3_split_tf32, or emitted by the row kernels).
+ * mn_major == 0: the operand is stored [rows, K] (row stride ld); mn_major != 0: stored
+ * [K, rows] -- so y = x W^T, dx = dy W and dW = dy^T x read the same planes, no transposes.
+ * Planes are 16-byte aligned, ld % 4 == 0.  lo == NULL on all operands: raw fp32, split in the SM.
+ * accumulate: bit 0 = add into C; bit 1 = allow split-K (deep contractions with few output tiles
+ * -- the dW products -- are partitioned along K and combined with fp32 atomics; the summation
+ * order is then not fixed, so callers that need run-to-run bit-identical results leave it 0).
+ * Persistent kernel (grid = min(tiles, SMs)), 128 x {128,64,32} tiles, TMA 128B-swizzled stages,
+ * fp32 accumulation in TMEM promoted to registers every 128 k. */
+typedef struct dv3_tc_operand {
+  const float* hi;
+  const float* lo;
+  int32_t ld;
+  int32_t mn_major;
+} dv3_tc_operand;
+int dv3_gemm_tc(const dv3_tc_operand* A1, int32_t K1, const dv3_tc_operand* A2, int32_t K2,
+                const dv3_tc_operand* B, const float* bias, const float* addend, int32_t ldadd,
+                float* C, int32_t ldc, int32_t M, int32_t N, int32_t accumulate, void* stream);
+/* hi = x with the 13 low mantissa bits cleared, lo = x - hi; x is [rows, cols] with row stride
+ * ld, the planes have row stride ld_out >= cols (pad columns are zeroed). */
+int dv3_split_tf32(const float* x, int32_t ld, int32_t rows, int32_t cols, float* hi, float* lo,
+                   int32_t ld_out, void* stream);
 /* Same product straight from fp32 operands, no scratch and no pre-pass: C = [A1|A2] W^T (+bias
  * +addend, +C when accumulate != 0).  TMA loads each fp32 tile once; the hi/lo split is done
  * inside the SM by converter warps of the persistent GEMM kernel (dv3_umma2.cu).  A1/A2/W must be

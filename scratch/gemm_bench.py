@@ -18,8 +18,9 @@ def timeit(fn, n=10):
 for (M, N, Kd) in shapes:
     a = torch.randn(M, Kd, device=dev); w = torch.randn(N, Kd, device=dev) / Kd ** 0.5
     ref = a.double() @ w.double().t()
-    o1 = K.linear_tc(a, w); o2 = K.linear_tc2(a, w)
+    As, Ws = K.split(a), K.split(w)
+    o1 = K.gemm_tc(As, Ws); o2 = K.linear_tc2(a, w)
     e1 = float((o1.double() - ref).abs().max() / ref.abs().max())
     e2 = float((o2.double() - ref).abs().max() / ref.abs().max())
-    t1 = timeit(lambda: K.linear_tc(a, w)); t2 = timeit(lambda: K.linear_tc2(a, w))
-    print(f"{M:6d} {N:6d} {Kd:6d}  v1 {t1[0]:8.1f} us {t1[1]:7.1f} TF/s err {e1:.1e} | v2 {t2[0]:8.1f} us {t2[1]:7.1f} TF/s err {e2:.1e}", flush=True)
+    t1 = timeit(lambda: K.gemm_tc(As, Ws)); t2 = timeit(lambda: K.linear_tc2(a, w))
+    print(f"{M:6d} {N:6d} {Kd:6d}  presplit {t1[0]:8.1f} us {t1[1]:7.1f} TF/s err {e1:.1e} | raw {t2[0]:8.1f} us {t2[1]:7.1f} TF/s err {e2:.1e}", flush=True)

@@ -69,3 +69,56 @@ def test_linear_tc2_two_segments_and_strides(pkg, device, M, N, K1, K2):
     ref = torch.cat([a1, a2], 1).double() @ w.double().t()
     out = pkg.kernels.linear_tc2(a1, w, a2=a2)
     assert float((out.double() - ref).abs().max() / ref.abs().max()) < 5e-6
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (1024, 512, 512), (1000, 1032, 500), (257, 130, 100),
+                                   (70, 9, 36), (15360, 512, 1536), (512, 1536, 15360), (40, 24, 2000)])
+@pytest.mark.parametrize("a_t,b_t", [(False, False), (False, True), (True, False), (True, True)])
+def test_gemm_tc_all_storage_orders(pkg, device, M, N, K, a_t, b_t):
+    """pre-split operands read K-major or MN-major (transposed) through the UMMA descriptors:
+    y = x W^T, dx = dy W, dW = dy^T x from the same planes."""
+    g = torch.Generator().manual_seed(M + 3 * N + 7 * K)
+    a = torch.randn(M, K, generator=g).to(device)
+    b = (torch.randn(N, K, generator=g) / K ** 0.5).to(device)
+    ref = a.double() @ b.double().t()
+    As = pkg.kernels.split(a.t().contiguous() if a_t else a)
+    Bs = pkg.kernels.split(b.t().contiguous() if b_t else b)
+    out = pkg.kernels.gemm_tc(As, Bs, a_t=a_t, b_t=b_t)
+    err = float((out.double() - ref).abs().max() / ref.abs().max())
+    assert err < 5e-6, err
+
+
+def test_gemm_tc_segments_bias_accumulate(pkg, device):
+    g = torch.Generator().manual_seed(9)
+    M, N, K1, K2 = 1024, 1536, 512, 512
+    a1 = torch.randn(M, K1, generator=g).to(device)
+    a2 = torch.randn(M, K2, generator=g).to(device)
+    w = (torch.randn(N, K1 + K2, generator=g) / 32).to(device)
+    bias = torch.randn(N, generator=g).to(device)
+    add = torch.randn(M, N, generator=g).to(device)
+    ref = torch.cat([a1, a2], 1).double() @ w.double().t() + bias.double() + add.double()
+    out = pkg.kernels.gemm_tc(a1, w, A2=a2, bias=bias, addend=add)
+    assert float((out.double() - ref).abs().max() / ref.abs().max()) < 5e-6
+    out2 = pkg.kernels.gemm_tc(a1, w, A2=a2, out=out.clone(), accumulate=True)
+    ref2 = ref + torch.cat([a1, a2], 1).double() @ w.double().t()
+    assert float((out2.double() - ref2).abs().max() / ref2.abs().max()) < 5e-6
+    # hi + lo reproduces the input exactly
+    sp = pkg.kernels.split(a1)
+    assert torch.equal(sp.hi[:, :K1] + sp.lo[:, :K1], a1)
+
+
+@pytest.mark.parametrize("M,N,K", [(512, 512, 15360), (1536, 1024, 1024), (512, 6, 1024), (200, 1030, 5000)])
+def test_gemm_tc_split_k(pkg, device, M, N, K):
+    """dW-shaped products (deep K, few output tiles): K partitioned over CTAs, fp32 atomics."""
+    g = torch.Generator().manual_seed(M + N + K)
+    dy = torch.randn(K, M, generator=g).to(device)          # [rows, out]
+    x = (torch.randn(K, N, generator=g) / K ** 0.5).to(device)
+    ref = dy.double().t() @ x.double()
+    out = pkg.kernels.gemm_tc(dy, x, a_t=True, b_t=True, split_k=True)
+    assert float((out.double() - ref).abs().max() / ref.abs().max()) < 5e-6
+    # strided output view + accumulate
+    big = torch.zeros(M, N + 8, device=device)
+    pkg.kernels.gemm_tc(dy, x, a_t=True, b_t=True, split_k=True, out=big[:, 4:4 + N])
+    pkg.kernels.gemm_tc(dy, x, a_t=True, b_t=True, split_k=True, out=big[:, 4:4 + N], accumulate=True)
+    assert float((big[:, 4:4 + N].double() - 2 * ref).abs().max() / ref.abs().max()) < 1e-5
+    assert float(big[:, :4].abs().max()) == 0.0 and float(big[:, 4 + N:].abs().max()) == 0.0

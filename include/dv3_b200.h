@@ -353,7 +353,7 @@ int dv3_linear_tc_fwd(const float* A, int32_t lda, int32_t transA, const float* 
  * order is then not fixed, so callers that need run-to-run bit-identical results leave it 0).
  * Persistent kernel (grid = min(tiles, SMs)), 128 x {128,64,32} tiles, TMA 128B-swizzled stages,
  * fp32 accumulation in TMEM promoted to registers every 128 k. */
-typedef struct dv3_tc_operand {
+typedef struct {
   const float* hi;
   const float* lo;
   int32_t ld;

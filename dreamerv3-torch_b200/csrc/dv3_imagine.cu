@@ -50,6 +50,64 @@ __global__ void actor_normal_sample_bwd_kernel(const float* __restrict__ mean_ra
   d_std_raw[i] = dout * eps[i] * (max_std - min_std) * sg * (1.f - sg);
 }
 
+// Actor output heads fused with the draw: one warp per row computes the A (normal: 2A) dot
+// products of the top activation with the head weights held in shared memory, then
+//   normal: a = clip(tanh(mean) + std * eps)      (networks.py:693-700, tools.py:575-601)
+//   onehot: only the logits are written; the unimix categorical draw follows in onehot_sample.
+// Replaces two [N x U] x [U x A] SIMT GEMM launches (8 CTAs each) plus the sample kernel.
+constexpr int AH_THREADS = 256;
+
+__global__ void __launch_bounds__(AH_THREADS)
+actor_head_kernel(const float* __restrict__ top, int ldt, const float* __restrict__ w_mean,
+                  const float* __restrict__ b_mean, const float* __restrict__ w_std,
+                  const float* __restrict__ b_std, const float* __restrict__ eps, float min_std,
+                  float max_std, int N, int U, int A, float* __restrict__ mean_raw,
+                  float* __restrict__ std_raw, float* __restrict__ action) {
+  extern __shared__ __align__(16) float ah_smem[];
+  const int nh = w_std ? 2 : 1;
+  float* ws = ah_smem;                         // [nh*A][U]
+  for (int i = threadIdx.x * 4; i < A * U; i += AH_THREADS * 4) {
+    *reinterpret_cast<float4*>(ws + i) = __ldg(reinterpret_cast<const float4*>(w_mean + i));
+    if (w_std)
+      *reinterpret_cast<float4*>(ws + A * U + i) = __ldg(reinterpret_cast<const float4*>(w_std + i));
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = AH_THREADS / 32;
+  for (int r = blockIdx.x * nw + warp; r < N; r += gridDim.x * nw) {
+    const float* x = top + (size_t)r * ldt;
+    float mine = 0.f;                          // lane j < nh*A ends up holding head value j
+    for (int j = 0; j < nh * A; ++j) {
+      const float* w = ws + (size_t)j * U;
+      float acc = 0.f;
+      for (int k = lane * 4; k < U; k += 128) {
+        const float4 xv = *reinterpret_cast<const float4*>(x + k);
+        const float4 wv = *reinterpret_cast<const float4*>(w + k);
+        acc = fmaf(xv.x, wv.x, acc); acc = fmaf(xv.y, wv.y, acc);
+        acc = fmaf(xv.z, wv.z, acc); acc = fmaf(xv.w, wv.w, acc);
+      }
+      acc = warp_sum(acc);
+      if (lane == j) mine = acc;
+    }
+    const size_t o = (size_t)r * A;
+    if (lane < A) {
+      mine += b_mean[lane];
+      mean_raw[o + lane] = mine;
+    } else if (lane < nh * A) {
+      mine += b_std[lane - A];
+      std_raw[o + lane - A] = mine;
+    }
+    if (w_std) {
+      const float sraw = __shfl_sync(FULL, mine, (lane + A) & 31);
+      if (lane < A) {
+        const float mean = tanhf(mine);
+        const float std = (max_std - min_std) * sigmoidf_(sraw + 2.f) + min_std;
+        const float out = mean + std * eps[o + lane];
+        action[o + lane] = out * (1.f / fmaxf(fabsf(out), 1.f));
+      }
+    }
+  }
+}
+
 struct ImgFwdWs {
   float* WinT;   // [(SC+A), Hd]
   float* Wa0T;   // [F, U]
@@ -180,18 +238,37 @@ extern "C" int dv3_imagine_fwd(const dv3_rssm_dims* d, const dv3_rssm_params* p,
       }
       const float* top = io->a_act + (L - 1) * lstride + (size_t)k * N * U;
       float* mraw = io->a_mean_raw + (size_t)k * N * A;
-      DV3_TRY(linear1(top, U, a->w_mean, U, U, a->b_mean, mraw, A, N, A, 0, st));
-      if (a->dist == 0) {
-        float* sraw = io->a_std_raw + (size_t)k * N * A;
-        DV3_TRY(linear1(top, U, a->w_std, U, U, a->b_std, sraw, A, N, A, 0, st));
-        const long long tot = (long long)N * A;
-        actor_normal_sample_kernel<<<(int)((tot + 255) / 256), 256, 0, st>>>(
-            mraw, sraw, io->act_noise + (size_t)k * N * A, a->min_std, a->max_std, tot, actk);
-        DV3_CHECK_LAUNCH("actor_normal_sample_kernel");
+      float* sraw = a->dist == 0 ? io->a_std_raw + (size_t)k * N * A : nullptr;
+      const int nh = a->dist == 0 ? 2 : 1;
+      const size_t ah_smem = (size_t)nh * A * U * sizeof(float);
+      if (nh * A <= 32 && ah_smem <= 160 * 1024) {
+        static bool attr = false;
+        if (!attr) {
+          DV3_CHECK_CUDA(cudaFuncSetAttribute(actor_head_kernel,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              160 * 1024));
+          attr = true;
+        }
+        const int nw = AH_THREADS / 32;
+        int grid = (N + nw - 1) / nw;
+        if (grid > 148) grid = 148;
+        actor_head_kernel<<<grid, AH_THREADS, ah_smem, st>>>(
+            top, U, a->w_mean, a->b_mean, a->dist == 0 ? a->w_std : nullptr, a->b_std,
+            io->act_noise + (size_t)k * N * A, a->min_std, a->max_std, N, U, A, mraw, sraw, actk);
+        DV3_CHECK_LAUNCH("actor_head_kernel");
       } else {
+        DV3_TRY(linear1(top, U, a->w_mean, U, U, a->b_mean, mraw, A, N, A, 0, st));
+        if (a->dist == 0) {
+          DV3_TRY(linear1(top, U, a->w_std, U, U, a->b_std, sraw, A, N, A, 0, st));
+          const long long tot = (long long)N * A;
+          actor_normal_sample_kernel<<<(int)((tot + 255) / 256), 256, 0, st>>>(
+              mraw, sraw, io->act_noise + (size_t)k * N * A, a->min_std, a->max_std, tot, actk);
+          DV3_CHECK_LAUNCH("actor_normal_sample_kernel");
+        }
+      }
+      if (a->dist != 0)
         DV3_TRY(onehot_sample(mraw, A, io->act_noise + (size_t)k * N * A, A, 0, 0, a->unimix, N, 1,
                               A, nullptr, 0, actk, A, st));
-      }
     } else if (k < H - 1) {
       DV3_TRY(copy_rows(io->given_action + (size_t)k * N * A, A, N, A, actk, A, st));
     } else {

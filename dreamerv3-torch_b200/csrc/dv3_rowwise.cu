@@ -411,6 +411,106 @@ int fill_zero(void* p, size_t bytes, cudaStream_t st) {
 using namespace dv3;
 #define ST(s) static_cast<cudaStream_t>(s)
 
+// ------------------------------------------------------------------------------------------
+// LayerNorm parameter gradients over all rows:  dg[j] = sum_r d_ln[r,j] * xhat[r,j],
+// db[j] = sum_r d_ln[r,j]   (xhat recomputed from the saved pre-LN rows, two-pass statistics).
+// One warp per row, a lane owns columns lane + 32 i and keeps their partial sums in registers
+// over all the rows its warp visits; the warps of a CTA fold through shared memory and the CTA
+// issues one atomicAdd per column.  dg/db must be zeroed by the caller.
+// ------------------------------------------------------------------------------------------
+namespace dv3 {
+
+constexpr int LG_THREADS = 256;
+
+template <int NPL>   // columns per lane
+__global__ void __launch_bounds__(LG_THREADS)
+ln_param_grads_kernel(const float* __restrict__ pre, int ld, const float* __restrict__ d_ln,
+                      int ldl, float eps, int M, int n, float* __restrict__ dg,
+                      float* __restrict__ db) {
+  extern __shared__ float lg_sm[];               // [2][n]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = LG_THREADS / 32;
+  float ag[NPL], ab[NPL];
+#pragma unroll
+  for (int i = 0; i < NPL; ++i) ag[i] = ab[i] = 0.f;
+  for (int r = blockIdx.x * nw + warp; r < M; r += gridDim.x * nw) {
+    const float* row = pre + (size_t)r * ld;
+    const float* dr = d_ln + (size_t)r * ldl;
+    float v[NPL];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) {
+      const int j = lane + 32 * i;
+      v[i] = j < n ? row[j] : 0.f;
+      s += v[i];
+    }
+    const float mean = warp_sum(s) / (float)n;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) {
+      const int j = lane + 32 * i;
+      const float d = j < n ? v[i] - mean : 0.f;
+      q = fmaf(d, d, q);
+    }
+    const float rstd = 1.f / sqrtf(warp_sum(q) / (float)n + eps);
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) {
+      const int j = lane + 32 * i;
+      if (j < n) {
+        const float d = dr[j];
+        ag[i] = fmaf(d, (v[i] - mean) * rstd, ag[i]);
+        ab[i] += d;
+      }
+    }
+  }
+  for (int i = threadIdx.x; i < 2 * n; i += LG_THREADS) lg_sm[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NPL; ++i) {
+    const int j = lane + 32 * i;
+    if (j < n) {
+      atomicAdd(&lg_sm[j], ag[i]);
+      atomicAdd(&lg_sm[n + j], ab[i]);
+    }
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < n; j += LG_THREADS) {
+    atomicAdd(dg + j, lg_sm[j]);
+    atomicAdd(db + j, lg_sm[n + j]);
+  }
+}
+
+template <int NPL>
+static int launch_ln_param_grads(const float* pre, int ld, const float* d_ln, int ldl, float eps,
+                                 int M, int n, float* dg, float* db, cudaStream_t st) {
+  const int nw = LG_THREADS / 32;
+  int grid = (M + nw - 1) / nw;
+  if (grid > 2 * 148) grid = 2 * 148;
+  ln_param_grads_kernel<NPL><<<grid, LG_THREADS, (size_t)2 * n * 4, st>>>(pre, ld, d_ln, ldl, eps,
+                                                                           M, n, dg, db);
+  DV3_CHECK_LAUNCH("ln_param_grads_kernel");
+  return 0;
+}
+
+}  // namespace dv3
+
+extern "C" int dv3_ln_param_grads(const float* pre, int32_t ld, const float* d_ln, int32_t ldl,
+                                  float eps, int32_t M, int32_t n, float* dg, float* db,
+                                  void* stream) {
+  using namespace dv3;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DV3_REQUIRE(M >= 0 && n > 0 && n <= 2048, DV3_ERR_BAD_SHAPE, "ln_param_grads: M=%d n=%d", M, n);
+  DV3_REQUIRE(pre && d_ln && dg && db, DV3_ERR_NULL, "ln_param_grads: null pointer");
+  DV3_CHECK_CUDA(cudaMemsetAsync(dg, 0, (size_t)n * 4, st));
+  DV3_CHECK_CUDA(cudaMemsetAsync(db, 0, (size_t)n * 4, st));
+  if (M == 0) return 0;
+  const int npl = (n + 31) / 32;
+  if (npl <= 4) return launch_ln_param_grads<4>(pre, ld, d_ln, ldl, eps, M, n, dg, db, st);
+  if (npl <= 16) return launch_ln_param_grads<16>(pre, ld, d_ln, ldl, eps, M, n, dg, db, st);
+  if (npl <= 32) return launch_ln_param_grads<32>(pre, ld, d_ln, ldl, eps, M, n, dg, db, st);
+  if (npl <= 48) return launch_ln_param_grads<48>(pre, ld, d_ln, ldl, eps, M, n, dg, db, st);
+  return launch_ln_param_grads<64>(pre, ld, d_ln, ldl, eps, M, n, dg, db, st);
+}
+
 extern "C" int dv3_ln_silu_fwd(const float* pre, int32_t ld, const float* g, const float* b,
                                float eps, int32_t M, int32_t n, float* out, int32_t ldo,
                                void* stream) {

@@ -431,7 +431,16 @@ def _xhat(pre):
 
 
 def _ln_grads(pre2d, d_ln2d):
-    return (d_ln2d * _xhat(pre2d)).sum(0), d_ln2d.sum(0)
+    """LayerNorm weight / bias gradients from the saved pre-LN rows and d(LN output)."""
+    M, n = pre2d.shape
+    if n > 2048 or pre2d.stride(1) != 1 or d_ln2d.stride(1) != 1:
+        return (d_ln2d * _xhat(pre2d)).sum(0), d_ln2d.sum(0)
+    dg = torch.empty(n, dtype=torch.float32, device=pre2d.device)
+    db = torch.empty(n, dtype=torch.float32, device=pre2d.device)
+    L.check(L.lib().dv3_ln_param_grads(_raw(pre2d), pre2d.stride(0), _raw(d_ln2d), d_ln2d.stride(0),
+                                       LN_EPS, M, n, L.fptr(dg), L.fptr(db), L.stream_ptr()),
+            "ln_param_grads")
+    return dg, db
 
 
 # --------------------------------------------------------------------------------------

@@ -382,6 +382,10 @@ int dv3_ln_silu_fwd(const float* pre, int32_t ld, const float* g, const float* b
 int dv3_ln_silu_bwd(const float* pre, int32_t ld, const float* g, const float* b, float eps,
                     const float* d_out, int32_t ldd, int32_t M, int32_t n, float* d_pre,
                     float* d_ln, int32_t ldp, void* stream);
+/* LayerNorm affine-parameter gradients over all M rows: dg[j] = sum_r d_ln[r,j]*xhat[r,j],
+ * db[j] = sum_r d_ln[r,j]; xhat is recomputed from the saved pre-LN rows.  n <= 2048. */
+int dv3_ln_param_grads(const float* pre, int32_t ld, const float* d_ln, int32_t ldl, float eps,
+                       int32_t M, int32_t n, float* dg, float* db, void* stream);
 /* LayerNorm-GRU gate block (networks.py:760-768): parts = LN_3D(g_pre); r = sig(p0);
  * c = tanh(r*p1); u = sig(p2 - 1); h_new = u*c + (1-u)*h.  bwd also returns d_g_ln (gradient
  * w.r.t. the LayerNorm affine output) and d_h = the direct (1-u) path only. */

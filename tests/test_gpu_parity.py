@@ -131,3 +131,18 @@ def test_train_api_runs_and_updates(pkg, device):
               "EMA_095", "value_mean", "target_std", "imag_reward_min", "imag_action_max", "normed_target_mean"):
         assert k in m2, k
     assert all(np.isfinite(np.asarray(v)).all() for v in m2.values())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,n", [(1024, 512), (15360, 512), (1024, 1536), (37, 40), (5, 2000)])
+def test_ln_param_grads(pkg, device, M, n):
+    """LN weight/bias gradient kernel against the torch expression it replaces."""
+    import torch
+    g = torch.Generator().manual_seed(M + n)
+    pre = torch.randn(M, n, generator=g).to(device) * 2 + 0.3
+    d_ln = torch.randn(M, n, generator=g).to(device)
+    dg, db = pkg.kernels._ln_grads(pre, d_ln)
+    xh = torch.nn.functional.layer_norm(pre.double(), (n,), None, None, 1e-3)
+    rg, rb = (d_ln.double() * xh).sum(0), d_ln.double().sum(0)
+    assert float((dg.double() - rg).abs().max() / rg.abs().max()) < 1e-5
+    assert float((db.double() - rb).abs().max() / rb.abs().max()) < 1e-5

@@ -43,24 +43,31 @@ struct PoArgs {
   int32_t *post_idx, *sprev_idx;
   unsigned* bar;
   int ncg, nco, bufw;
+  unsigned long long* timing;   // debug: [T][8] %globaltimer stamps of CTA 0 (NULL = off)
 };
 
+__device__ __forceinline__ void po_stamp(const PoArgs& p, int t, int slot) {
+  if (p.timing && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long v;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+    p.timing[t * 8 + slot] = v;
+  }
+}
+
+// Grid barrier on a monotonically increasing arrival counter: barrier number n is passed once
+// the counter reaches n * nblocks.  One release-atomic per CTA and an acquire spin on the same
+// word -- no reset / flag second hop.
 __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned nblocks, unsigned& gen) {
   __syncthreads();
-  const unsigned next = gen + 1;
+  const unsigned target = (gen + 1) * nblocks;
   if (threadIdx.x == 0) {
-    __threadfence();
-    if (atomicAdd(&bar[0], 1u) == nblocks - 1) {
-      bar[0] = 0;
-      __threadfence();
-      atomicExch(&bar[1], next);
-    } else {
-      while (*reinterpret_cast<volatile unsigned*>(&bar[1]) != next) {
-      }
-    }
-    __threadfence();
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+    unsigned v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+    } while (v < target);
   }
-  gen = next;
+  gen += 1;
   __syncthreads();
 }
 
@@ -77,6 +84,17 @@ __device__ __forceinline__ void gemv16(const float* Ws, int ncols, int K, const 
                                        int K1, const float* in2, int ld2, int B, float* part,
                                        Epi epi) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool once = (K >> 2) <= PO_THREADS;      // one k-quad per thread: load the inputs once
+  float4 a[PO_ROWS];
+  if (once) {
+    const int k = tid << 2;
+    const bool live = k < K;
+    const float* src = live ? ((k < K1) ? in1 + k : in2 + (k - K1)) : in1;
+    const int ld = (k < K1) ? ld1 : ld2;
+#pragma unroll
+    for (int m = 0; m < PO_ROWS; ++m)
+      a[m] = (live && m < B) ? load4<GLOBAL_IN>(src + (size_t)m * ld) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   for (int cb = 0; cb < ncols; cb += PO_CP) {
     float acc[PO_NV];
 #pragma unroll
@@ -84,13 +102,14 @@ __device__ __forceinline__ void gemv16(const float* Ws, int ncols, int K, const 
 #pragma unroll 1
     for (int q = tid; q < (K >> 2); q += PO_THREADS) {
       const int k = q << 2;
-      const float* src;
-      int ld;
-      if (k < K1) { src = in1 + k; ld = ld1; } else { src = in2 + (k - K1); ld = ld2; }
-      float4 a[PO_ROWS];
+      if (!once) {
+        const float* src;
+        int ld;
+        if (k < K1) { src = in1 + k; ld = ld1; } else { src = in2 + (k - K1); ld = ld2; }
 #pragma unroll
-      for (int m = 0; m < PO_ROWS; ++m)
-        a[m] = (m < B) ? load4<GLOBAL_IN>(src + (size_t)m * ld) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int m = 0; m < PO_ROWS; ++m)
+          a[m] = (m < B) ? load4<GLOBAL_IN>(src + (size_t)m * ld) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
 #pragma unroll
       for (int c = 0; c < PO_CP; ++c) {
         const float4 w = (cb + c < ncols)
@@ -141,13 +160,17 @@ __global__ void __launch_bounds__(PO_THREADS, 1) observe_persistent_fwd_kernel(P
   const int SC = S * C, Kg = Hd + D, D3 = 3 * D;
   float* Wg = smf;
   float* Wo = Wg + (size_t)p.ncg * Kg;
-  float* Ws = Wo + (size_t)p.nco * D;
-  float* buf = Ws + (size_t)C * Hd;
-  float* part = buf + (size_t)PO_ROWS * p.bufw;
-  float* lg = part + PO_WARPS * PO_NV;
-  float* red = lg + PO_ROWS * 32;
+  float* Ws = Wo + (size_t)p.nco * D;                     // [C][Hd + 4]
+  float* zs = Ws + (size_t)C * (Hd + 4);                  // [16][Hd]  (phase A reuses row 0)
+  float* lng = zs + (size_t)PO_ROWS * Hd;                 // GRU LN gamma [3D], beta [3D]
+  float* lnb = lng + D3;
+  float* lzg = lnb + D3;                                  // obs LN gamma [Hd], beta [Hd]
+  float* lzb = lzg + Hd;
+  float* part = lzb + Hd;
+  float* red = part + PO_WARPS * PO_NV;
   int* sidx = reinterpret_cast<int*>(red + 128);
   float* sact = reinterpret_cast<float*>(sidx + ((S + 3) & ~3));
+  float* buf = zs;
 
   const int g0 = min(cta * p.ncg, D3), gn = min(p.ncg, D3 - g0);
   const int o0 = min(cta * p.nco, Hd), on = min(p.nco, Hd - o0);
@@ -163,14 +186,19 @@ __global__ void __launch_bounds__(PO_THREADS, 1) observe_persistent_fwd_kernel(P
         __ldg(reinterpret_cast<const float4*>(p.w_obs + (size_t)(o0 + r) * (D + E) + k));
   }
   if (owns_group)
-    for (int i = tid * 4; i < C * Hd; i += PO_THREADS * 4)
-      *reinterpret_cast<float4*>(Ws + i) =
+    for (int i = tid * 4; i < C * Hd; i += PO_THREADS * 4) {
+      const int r = i / Hd, k = i % Hd;
+      *reinterpret_cast<float4*>(Ws + (size_t)r * (Hd + 4) + k) =
           __ldg(reinterpret_cast<const float4*>(p.w_os + (size_t)cta * C * Hd + i));
+    }
+  for (int i = tid; i < D3; i += PO_THREADS) { lng[i] = p.ln_gru_g[i]; lnb[i] = p.ln_gru_b[i]; }
+  for (int i = tid; i < Hd; i += PO_THREADS) { lzg[i] = p.ln_obs_g[i]; lzb[i] = p.ln_obs_b[i]; }
   __syncthreads();
 
   unsigned gen = 0;
   for (int t = 0; t < T; ++t) {
     // ---------------- phase A: row b = cta ----------------
+    po_stamp(p, t, 0);
     if (cta < B) {
       const int b = cta;
       const size_t bt = (size_t)b * T + t;
@@ -213,7 +241,9 @@ __global__ void __launch_bounds__(PO_THREADS, 1) observe_persistent_fwd_kernel(P
       for (int i = tid; i < Hd; i += PO_THREADS)
         p.x[bt * Hd + i] = siluf_(fmaf((buf[i] - mean) * rstd, p.ln_in_g[i], p.ln_in_b[i]));
     }
+    po_stamp(p, t, 1);
     grid_barrier(p.bar, G, gen);
+    po_stamp(p, t, 2);
 
     // ---------------- phase B: GRU pre-activations, own columns ----------------
     if (gn > 0) {
@@ -223,22 +253,26 @@ __global__ void __launch_bounds__(PO_THREADS, 1) observe_persistent_fwd_kernel(P
                      gp[((size_t)m * T + t) * D3 + g0 + c] = r;
                    });
     }
+    po_stamp(p, t, 3);
     grid_barrier(p.bar, G, gen);
+    po_stamp(p, t, 4);
 
-    // ---------------- phase C: LN_3D + gates for every row (redundant), h' -> smem ----------------
+    // ------- phase C+D, one warp per row pair: LN_3D + gates from registers, then the row's
+    // posterior pre-activations for this CTA's W_obs columns straight from the h' registers -------
 #pragma unroll 1
     for (int rr = 0; rr < 2; ++rr) {
       const int b = warp * 2 + rr;
       if (b < B) {
         const size_t bt = (size_t)b * T + t;
         const float* row = p.g_pre + bt * D3;
-        float v[3 * DV];
+        float v[3 * DV], hp[DV];
         float s = 0.f;
 #pragma unroll
-        for (int i = 0; i < 3 * DV; ++i) {
-          v[i] = __ldcg(row + lane + 32 * i);
-          s += v[i];
-        }
+        for (int i = 0; i < 3 * DV; ++i) v[i] = __ldcg(row + lane + 32 * i);
+#pragma unroll
+        for (int i = 0; i < DV; ++i) hp[i] = __ldcg(p.hprev + bt * D + lane + 32 * i);
+#pragma unroll
+        for (int i = 0; i < 3 * DV; ++i) s += v[i];
         const float mean = warp_sum(s) / (float)D3;
         float q = 0.f;
 #pragma unroll
@@ -247,74 +281,102 @@ __global__ void __launch_bounds__(PO_THREADS, 1) observe_persistent_fwd_kernel(P
           q = fmaf(dd, dd, q);
         }
         const float rstd = 1.f / sqrtf(warp_sum(q) / (float)D3 + p.eps);
+        float hn[DV];
 #pragma unroll
         for (int i = 0; i < DV; ++i) {
           const int j = lane + 32 * i;
-          const float pr = fmaf((v[i] - mean) * rstd, p.ln_gru_g[j], p.ln_gru_b[j]);
-          const float pc = fmaf((v[i + DV] - mean) * rstd, p.ln_gru_g[D + j], p.ln_gru_b[D + j]);
-          const float pu = fmaf((v[i + 2 * DV] - mean) * rstd, p.ln_gru_g[2 * D + j], p.ln_gru_b[2 * D + j]);
+          const float pr = fmaf((v[i] - mean) * rstd, lng[j], lnb[j]);
+          const float pc = fmaf((v[i + DV] - mean) * rstd, lng[D + j], lnb[D + j]);
+          const float pu = fmaf((v[i + 2 * DV] - mean) * rstd, lng[2 * D + j], lnb[2 * D + j]);
           const float rg = sigmoidf_(pr);
           const float cc = tanhf(rg * pc);
           const float u = sigmoidf_(pu - 1.f);
-          const float hp = __ldcg(p.hprev + bt * D + j);
-          const float hn = u * cc + (1.f - u) * hp;
-          buf[(size_t)b * p.bufw + j] = hn;
-          if (cta == b) p.deter[bt * D + j] = hn;
+          hn[i] = u * cc + (1.f - u) * hp[i];
+        }
+        if (cta == b) {
+#pragma unroll
+          for (int i = 0; i < DV; ++i) p.deter[bt * D + lane + 32 * i] = hn[i];
+        }
+        for (int c = 0; c < on; ++c) {
+          const float* w = Wo + (size_t)c * D + lane;
+          float acc = 0.f;
+#pragma unroll
+          for (int i = 0; i < DV; ++i) acc = fmaf(hn[i], w[32 * i], acc);
+          acc = warp_sum(acc);
+          if (lane == 0) {
+            const size_t o = bt * Hd + o0 + c;
+            p.z_pre[o] = acc + p.pre_e[o];
+          }
         }
       }
     }
-    __syncthreads();
-
-    // ---------------- phase D: posterior pre-activations, own columns ----------------
-    if (on > 0) {
-      float* zp = p.z_pre;
-      const float* pe = p.pre_e;
-      gemv16<false>(Wo, on, D, buf, p.bufw, D, nullptr, 0, B, part, [&](int m, int c, float r) {
-        const size_t o = ((size_t)m * T + t) * Hd + o0 + c;
-        zp[o] = r + pe[o];
-      });
-    }
+    po_stamp(p, t, 5);
     grid_barrier(p.bar, G, gen);
+    po_stamp(p, t, 6);
 
-    // ---------------- phase E: group g = cta: LN+SiLU(z), logits, unimix draw ----------------
+    // ------- phase E, CTA g < S owns categorical group g; one warp per row pair, lane = class:
+    // LN+SiLU(z) from registers -> smem, logits by a serial dot per lane, unimix draw -------
     if (owns_group) {
+      float* z0 = zs + (size_t)(warp * 2) * Hd;
+      float lgt[2];
 #pragma unroll 1
       for (int rr = 0; rr < 2; ++rr) {
         const int b = warp * 2 + rr;
         if (b < B) {
           const size_t bt = (size_t)b * T + t;
-          float* zr = buf + (size_t)b * p.bufw;
+          float zv[32];
           float s = 0.f;
-          for (int i = lane; i < Hd; i += 32) {
-            const float x = __ldcg(p.z_pre + bt * Hd + i);
-            zr[i] = x;
-            s += x;
-          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            zv[i] = (lane + 32 * i < Hd) ? __ldcg(p.z_pre + bt * Hd + lane + 32 * i) : 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) s += zv[i];
           const float mean = warp_sum(s) / (float)Hd;
           float q = 0.f;
-          for (int i = lane; i < Hd; i += 32) {
-            const float dd = zr[i] - mean;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float dd = (lane + 32 * i < Hd) ? zv[i] - mean : 0.f;
             q = fmaf(dd, dd, q);
           }
           const float rstd = 1.f / sqrtf(warp_sum(q) / (float)Hd + p.eps);
-          for (int i = lane; i < Hd; i += 32) {
-            const float y = siluf_(fmaf((zr[i] - mean) * rstd, p.ln_obs_g[i], p.ln_obs_b[i]));
-            zr[i] = y;
-            if (cta == b) p.z[bt * Hd + i] = y;
+          float* zr = z0 + (size_t)rr * Hd;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int j = lane + 32 * i;
+            if (j < Hd) {
+              const float y = siluf_(fmaf((zv[i] - mean) * rstd, lzg[j], lzb[j]));
+              zr[j] = y;
+              if (cta == b) p.z[bt * Hd + j] = y;
+            }
           }
         }
       }
-      __syncthreads();
-      const float* bos = p.b_os + (size_t)cta * C;
-      gemv16<false>(Ws, C, Hd, buf, p.bufw, Hd, nullptr, 0, B, part,
-                    [&](int m, int c, float r) { lg[m * 32 + c] = r + bos[c]; });
-#pragma unroll 1
+      __syncwarp();
+      {
+        // logits of rows 2w, 2w+1 for class `lane`: Ws rows are padded by 4 floats so that the 32
+        // lanes' float4 reads hit distinct banks; the z rows are broadcast reads
+        const float* wrow = Ws + (size_t)min(lane, C - 1) * (Hd + 4);
+        float a0 = 0.f, a1 = 0.f;
+        for (int k = 0; k < Hd; k += 4) {
+          const float4 w = *reinterpret_cast<const float4*>(wrow + k);
+          const float4 x0 = *reinterpret_cast<const float4*>(z0 + k);
+          const float4 x1 = *reinterpret_cast<const float4*>(z0 + Hd + k);
+          a0 = fmaf(x0.x, w.x, a0); a0 = fmaf(x0.y, w.y, a0);
+          a0 = fmaf(x0.z, w.z, a0); a0 = fmaf(x0.w, w.w, a0);
+          a1 = fmaf(x1.x, w.x, a1); a1 = fmaf(x1.y, w.y, a1);
+          a1 = fmaf(x1.z, w.z, a1); a1 = fmaf(x1.w, w.w, a1);
+        }
+        const float bb = lane < C ? p.b_os[(size_t)cta * C + lane] : 0.f;
+        lgt[0] = a0 + bb;
+        lgt[1] = a1 + bb;
+      }
+#pragma unroll
       for (int rr = 0; rr < 2; ++rr) {
         const int b = warp * 2 + rr;
         if (b < B) {
           const size_t bt = (size_t)b * T + t;
           const bool valid = lane < C;
-          const float l = valid ? lg[b * 32 + lane] : 0.f;
+          const float l = valid ? lgt[rr] : 0.f;
           const Unimix um = unimix_probs(l, valid, C, p.unimix);
           const float uu = valid ? p.u_post[(((size_t)t * B + b) * S + cta) * C + lane] : 1.f;
           const int k = warp_argmax(um.probs / (-logf(uu)), valid, lane);
@@ -327,14 +389,17 @@ __global__ void __launch_bounds__(PO_THREADS, 1) observe_persistent_fwd_kernel(P
         }
       }
     }
+    po_stamp(p, t, 7);
     grid_barrier(p.bar, G, gen);
   }
 }
 
+static unsigned long long* g_po_timing = nullptr;
+
 static size_t po_smem_bytes(const PoArgs& a) {
-  const size_t fl = (size_t)a.ncg * (a.Hd + a.D) + (size_t)a.nco * a.D + (size_t)a.C * a.Hd +
-                    (size_t)PO_ROWS * a.bufw + PO_WARPS * PO_NV + PO_ROWS * 32 + 128 +
-                    ((a.S + 3) & ~3) + ((a.A + 3) & ~3) + 16;
+  const size_t fl = (size_t)a.ncg * (a.Hd + a.D) + (size_t)a.nco * a.D + (size_t)a.C * (a.Hd + 4) +
+                    (size_t)PO_ROWS * a.Hd + 6 * (size_t)a.D + 2 * (size_t)a.Hd + PO_WARPS * PO_NV +
+                    128 + ((a.S + 3) & ~3) + ((a.A + 3) & ~3) + 16;
   return fl * 4;
 }
 
@@ -368,7 +433,7 @@ int observe_fwd_persistent(const dv3_rssm_dims* d, const dv3_rssm_params* p,
   const int D = d->deter, Hd = d->hidden, S = d->stoch, C = d->classes;
   if (io->B > PO_ROWS || D % 32 != 0 || (D / 32 != 2 && D / 32 != 4 && D / 32 != 8 && D / 32 != 16))
     return 0;
-  if (Hd % 4 != 0 || d->embed % 4 != 0 || C > 32) return 0;
+  if (Hd % 4 != 0 || Hd > 1024 || d->embed % 4 != 0 || C > 32) return 0;
   int dev = 0, sms = 0, coop = 0;
   DV3_CHECK_CUDA(cudaGetDevice(&dev));
   DV3_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -390,6 +455,13 @@ int observe_fwd_persistent(const dv3_rssm_dims* d, const dv3_rssm_params* p,
   a.hprev = io->hprev; a.aprev = io->aprev; a.x_pre = io->x_pre; a.x = io->x; a.g_pre = io->g_pre;
   a.z_pre = io->z_pre; a.z = io->z; a.post_idx = io->post_idx; a.sprev_idx = io->sprev_idx;
   a.bar = bar;
+  a.timing = nullptr;
+  if (const char* te = getenv("DV3_OBSERVE_TIMING")) {
+    if (te[0] == '1') {
+      if (!g_po_timing) DV3_CHECK_CUDA(cudaMalloc(&g_po_timing, 4096 * 8 * sizeof(unsigned long long)));
+      if (io->T <= 4096) a.timing = g_po_timing;
+    }
+  }
   a.ncg = (3 * D + G - 1) / G;
   a.nco = (Hd + G - 1) / G;
   a.bufw = ((D > Hd ? D : Hd) + 3) & ~3;
@@ -404,3 +476,12 @@ int observe_fwd_persistent(const dv3_rssm_dims* d, const dv3_rssm_params* p,
 }
 
 }  // namespace dv3
+
+// debug: copies the [T][8] phase stamps of the last timed persistent observe launch (ns)
+extern "C" int dv3_debug_observe_timing(unsigned long long* host, int32_t T) {
+  DV3_REQUIRE(dv3::g_po_timing && host && T > 0 && T <= 4096, DV3_ERR_NULL,
+              "debug_observe_timing: no timing buffer (set DV3_OBSERVE_TIMING=1)");
+  DV3_CHECK_CUDA(cudaMemcpy(host, dv3::g_po_timing, (size_t)T * 8 * sizeof(unsigned long long),
+                            cudaMemcpyDeviceToHost));
+  return 0;
+}

@@ -414,6 +414,10 @@ int dv3_onehot_st_bwd(const float* logits, const float* g_sample, const float* e
 int dv3_idx_to_onehot(const int32_t* idx, int32_t M, int32_t S, int32_t C, float* out, int32_t ld,
                       void* stream);
 
+/* Debug aid: with DV3_OBSERVE_TIMING=1 in the environment the persistent observe kernel stamps
+ * %globaltimer (ns) at its 8 phase boundaries per step on CTA 0; this copies [T][8] stamps out. */
+int dv3_debug_observe_timing(unsigned long long* host, int32_t T);
+
 #ifdef __cplusplus
 }
 #endif

@@ -42,7 +42,9 @@ struct PoArgs {
   float *post_stoch, *post_logit, *deter, *hprev, *aprev, *x_pre, *x, *g_pre, *z_pre, *z;
   int32_t *post_idx, *sprev_idx;
   unsigned* bar;
-  int ncg, nco, bufw;
+  int ncg, bufw;
+  int nrbC, rpbC, cpb;          // phase C/D: row blocks, rows per block, W_obs columns per CTA
+  int nrbE, rpbE;               // phase E: row blocks per categorical group, rows per block
   unsigned long long* timing;   // debug: [T][8] %globaltimer stamps of CTA 0 (NULL = off)
 };
 
@@ -159,10 +161,11 @@ __global__ void __launch_bounds__(PO_THREADS, 1) observe_persistent_fwd_kernel(P
   const int B = p.B, T = p.T, S = p.S, C = p.C, D = p.D, Hd = p.Hd, A = p.A, E = p.E;
   const int SC = S * C, Kg = Hd + D, D3 = 3 * D;
   float* Wg = smf;
-  float* Wo = Wg + (size_t)p.ncg * Kg;
-  float* Ws = Wo + (size_t)p.nco * D;                     // [C][Hd + 4]
-  float* zs = Ws + (size_t)C * (Hd + 4);                  // [16][Hd]  (phase A reuses row 0)
-  float* lng = zs + (size_t)PO_ROWS * Hd;                 // GRU LN gamma [3D], beta [3D]
+  float* Wo = Wg + (size_t)p.ncg * Kg;                    // [cpb][D + 4]
+  float* Ws = Wo + (size_t)p.cpb * (D + 4);               // [C][Hd + 4]
+  float* zs = Ws + (size_t)C * (Hd + 4);                  // [8 warps][Hd]  (phase A reuses row 0)
+  float* hs = zs + (size_t)PO_WARPS * Hd;                 // [4 rows][D]    h' of this CTA's rows
+  float* lng = hs + (size_t)4 * D;                        // GRU LN gamma [3D], beta [3D]
   float* lnb = lng + D3;
   float* lzg = lnb + D3;                                  // obs LN gamma [Hd], beta [Hd]
   float* lzb = lzg + Hd;
@@ -171,10 +174,16 @@ __global__ void __launch_bounds__(PO_THREADS, 1) observe_persistent_fwd_kernel(P
   int* sidx = reinterpret_cast<int*>(red + 128);
   float* sact = reinterpret_cast<float*>(sidx + ((S + 3) & ~3));
   float* buf = zs;
+  float* xch = part;                                      // [4][32] warp-pair exchange
 
   const int g0 = min(cta * p.ncg, D3), gn = min(p.ncg, D3 - g0);
-  const int o0 = min(cta * p.nco, Hd), on = min(p.nco, Hd - o0);
-  const bool owns_group = cta < S;
+  // phase C/D: CTA = (row block rbC, column block cbC) -> rows rC0.., W_obs columns o0..o0+on
+  const int rbC = cta % p.nrbC, cbC = cta / p.nrbC;
+  const int rC0 = rbC * p.rpbC, rCn = max(0, min(p.rpbC, B - rC0));
+  const int o0 = min(cbC * p.cpb, Hd), on = min(p.cpb, Hd - o0);
+  // phase E: CTA = (group gE, row block rbE)
+  const int gE = cta % S, rbE = cta / S;
+  const int rE0 = rbE * p.rpbE, rEn = (rbE < p.nrbE) ? max(0, min(p.rpbE, B - rE0)) : 0;
 
   // resident weight slices
   for (int i = tid * 4; i < gn * Kg; i += PO_THREADS * 4)
@@ -182,14 +191,14 @@ __global__ void __launch_bounds__(PO_THREADS, 1) observe_persistent_fwd_kernel(P
         __ldg(reinterpret_cast<const float4*>(p.w_gru + (size_t)g0 * Kg + i));
   for (int i = tid * 4; i < on * D; i += PO_THREADS * 4) {
     const int r = i / D, k = i % D;
-    *reinterpret_cast<float4*>(Wo + i) =
+    *reinterpret_cast<float4*>(Wo + (size_t)r * (D + 4) + k) =
         __ldg(reinterpret_cast<const float4*>(p.w_obs + (size_t)(o0 + r) * (D + E) + k));
   }
-  if (owns_group)
+  if (rEn > 0)
     for (int i = tid * 4; i < C * Hd; i += PO_THREADS * 4) {
       const int r = i / Hd, k = i % Hd;
       *reinterpret_cast<float4*>(Ws + (size_t)r * (Hd + 4) + k) =
-          __ldg(reinterpret_cast<const float4*>(p.w_os + (size_t)cta * C * Hd + i));
+          __ldg(reinterpret_cast<const float4*>(p.w_os + (size_t)gE * C * Hd + i));
     }
   for (int i = tid; i < D3; i += PO_THREADS) { lng[i] = p.ln_gru_g[i]; lnb[i] = p.ln_gru_b[i]; }
   for (int i = tid; i < Hd; i += PO_THREADS) { lzg[i] = p.ln_obs_g[i]; lzb[i] = p.ln_obs_b[i]; }
@@ -257,20 +266,23 @@ __global__ void __launch_bounds__(PO_THREADS, 1) observe_persistent_fwd_kernel(P
     grid_barrier(p.bar, G, gen);
     po_stamp(p, t, 4);
 
-    // ------- phase C+D, one warp per row pair: LN_3D + gates from registers, then the row's
-    // posterior pre-activations for this CTA's W_obs columns straight from the h' registers -------
-#pragma unroll 1
-    for (int rr = 0; rr < 2; ++rr) {
-      const int b = warp * 2 + rr;
-      if (b < B) {
-        const size_t bt = (size_t)b * T + t;
+    // ------- phase C+D.  CTA (row block, column block): two warps per row.  Each warp takes the
+    // LN_3D statistics of the whole row but evaluates the gates for its half of D only; h' goes to
+    // smem, then lane = (W_obs column, quarter of D) does a serial dot over its quarter -------
+    {
+      const int rl = warp & 3, half = warp >> 2;
+      const bool act = rl < rCn && on > 0;
+      const int b = rC0 + rl;
+      const size_t bt = (size_t)b * T + t;
+      if (act) {
         const float* row = p.g_pre + bt * D3;
-        float v[3 * DV], hp[DV];
-        float s = 0.f;
+        float v[3 * DV], hp[DV / 2];
+        const int jb = half * (D >> 1);
 #pragma unroll
         for (int i = 0; i < 3 * DV; ++i) v[i] = __ldcg(row + lane + 32 * i);
 #pragma unroll
-        for (int i = 0; i < DV; ++i) hp[i] = __ldcg(p.hprev + bt * D + lane + 32 * i);
+        for (int i = 0; i < DV / 2; ++i) hp[i] = __ldcg(p.hprev + bt * D + jb + lane + 32 * i);
+        float s = 0.f;
 #pragma unroll
         for (int i = 0; i < 3 * DV; ++i) s += v[i];
         const float mean = warp_sum(s) / (float)D3;
@@ -281,112 +293,113 @@ __global__ void __launch_bounds__(PO_THREADS, 1) observe_persistent_fwd_kernel(P
           q = fmaf(dd, dd, q);
         }
         const float rstd = 1.f / sqrtf(warp_sum(q) / (float)D3 + p.eps);
-        float hn[DV];
 #pragma unroll
-        for (int i = 0; i < DV; ++i) {
-          const int j = lane + 32 * i;
-          const float pr = fmaf((v[i] - mean) * rstd, lng[j], lnb[j]);
-          const float pc = fmaf((v[i + DV] - mean) * rstd, lng[D + j], lnb[D + j]);
-          const float pu = fmaf((v[i + 2 * DV] - mean) * rstd, lng[2 * D + j], lnb[2 * D + j]);
+        for (int i = 0; i < DV / 2; ++i) {
+          // this warp's half of each part (selects, so that v[] keeps static register indices)
+          const float vr = half ? v[DV / 2 + i] : v[i];
+          const float vc = half ? v[DV + DV / 2 + i] : v[DV + i];
+          const float vu = half ? v[2 * DV + DV / 2 + i] : v[2 * DV + i];
+          const int j = jb + lane + 32 * i;
+          const float pr = fmaf((vr - mean) * rstd, lng[j], lnb[j]);
+          const float pc = fmaf((vc - mean) * rstd, lng[D + j], lnb[D + j]);
+          const float pu = fmaf((vu - mean) * rstd, lng[2 * D + j], lnb[2 * D + j]);
           const float rg = sigmoidf_(pr);
           const float cc = tanhf(rg * pc);
           const float u = sigmoidf_(pu - 1.f);
-          hn[i] = u * cc + (1.f - u) * hp[i];
+          const float hn = u * cc + (1.f - u) * hp[i];
+          hs[(size_t)rl * D + j] = hn;
+          if (cbC == 0) p.deter[bt * D + j] = hn;
         }
-        if (cta == b) {
-#pragma unroll
-          for (int i = 0; i < DV; ++i) p.deter[bt * D + lane + 32 * i] = hn[i];
+      }
+      __syncthreads();
+      float acc = 0.f;
+      const int cl = lane & 15, jq = half * 2 + (lane >> 4);
+      if (act && cl < on) {
+        const int j0 = jq * (D >> 2);
+        const float* w = Wo + (size_t)cl * (D + 4) + j0;
+        const float* h = hs + (size_t)rl * D + j0;
+        float a0 = 0.f, a1 = 0.f;
+        for (int k = 0; k < (D >> 2); k += 4) {
+          const float4 wv = *reinterpret_cast<const float4*>(w + k);
+          const float4 hv = *reinterpret_cast<const float4*>(h + k);
+          a0 = fmaf(hv.x, wv.x, a0); a1 = fmaf(hv.y, wv.y, a1);
+          a0 = fmaf(hv.z, wv.z, a0); a1 = fmaf(hv.w, wv.w, a1);
         }
-        for (int c = 0; c < on; ++c) {
-          const float* w = Wo + (size_t)c * D + lane;
-          float acc = 0.f;
-#pragma unroll
-          for (int i = 0; i < DV; ++i) acc = fmaf(hn[i], w[32 * i], acc);
-          acc = warp_sum(acc);
-          if (lane == 0) {
-            const size_t o = bt * Hd + o0 + c;
-            p.z_pre[o] = acc + p.pre_e[o];
-          }
-        }
+        acc = a0 + a1;
+      }
+      acc += __shfl_xor_sync(FULL, acc, 16);
+      if (half == 1 && lane < 16) xch[rl * 32 + lane] = acc;
+      __syncthreads();
+      if (half == 0 && act && lane < on) {
+        const size_t o = bt * Hd + o0 + lane;
+        p.z_pre[o] = acc + xch[rl * 32 + lane] + p.pre_e[o];
       }
     }
     po_stamp(p, t, 5);
     grid_barrier(p.bar, G, gen);
     po_stamp(p, t, 6);
 
-    // ------- phase E, CTA g < S owns categorical group g; one warp per row pair, lane = class:
-    // LN+SiLU(z) from registers -> smem, logits by a serial dot per lane, unimix draw -------
-    if (owns_group) {
-      float* z0 = zs + (size_t)(warp * 2) * Hd;
-      float lgt[2];
-#pragma unroll 1
-      for (int rr = 0; rr < 2; ++rr) {
-        const int b = warp * 2 + rr;
-        if (b < B) {
-          const size_t bt = (size_t)b * T + t;
-          float zv[32];
-          float s = 0.f;
+    // ------- phase E.  CTA (group, row block): two warps per row, lane = class.  Each warp
+    // normalises the whole z row into its own smem row and dots its half of Hd; the pair meets
+    // in smem, then the unimix draw -------
+    {
+      const int rl = warp & 3, half = warp >> 2;
+      const bool act = rl < rEn;
+      const int b = rE0 + rl;
+      const size_t bt = (size_t)b * T + t;
+      const bool valid = lane < C;
+      float uu = 1.f, a0 = 0.f, a1 = 0.f;
+      if (act) {
+        if (half == 0 && valid) uu = __ldcs(p.u_post + (((size_t)t * B + b) * S + gE) * C + lane);
+        float zv[32];
+        float s = 0.f;
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            zv[i] = (lane + 32 * i < Hd) ? __ldcg(p.z_pre + bt * Hd + lane + 32 * i) : 0.f;
+        for (int i = 0; i < 32; ++i)
+          zv[i] = (lane + 32 * i < Hd) ? __ldcg(p.z_pre + bt * Hd + lane + 32 * i) : 0.f;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) s += zv[i];
-          const float mean = warp_sum(s) / (float)Hd;
-          float q = 0.f;
+        for (int i = 0; i < 32; ++i) s += zv[i];
+        const float mean = warp_sum(s) / (float)Hd;
+        float q = 0.f;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float dd = (lane + 32 * i < Hd) ? zv[i] - mean : 0.f;
-            q = fmaf(dd, dd, q);
-          }
-          const float rstd = 1.f / sqrtf(warp_sum(q) / (float)Hd + p.eps);
-          float* zr = z0 + (size_t)rr * Hd;
+        for (int i = 0; i < 32; ++i) {
+          const float dd = (lane + 32 * i < Hd) ? zv[i] - mean : 0.f;
+          q = fmaf(dd, dd, q);
+        }
+        const float rstd = 1.f / sqrtf(warp_sum(q) / (float)Hd + p.eps);
+        float* zr = zs + (size_t)warp * Hd;
+        const bool wr = gE == 0 && half == 0;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int j = lane + 32 * i;
-            if (j < Hd) {
-              const float y = siluf_(fmaf((zv[i] - mean) * rstd, lzg[j], lzb[j]));
-              zr[j] = y;
-              if (cta == b) p.z[bt * Hd + j] = y;
-            }
+        for (int i = 0; i < 32; ++i) {
+          const int j = lane + 32 * i;
+          if (j < Hd) {
+            const float y = siluf_(fmaf((zv[i] - mean) * rstd, lzg[j], lzb[j]));
+            zr[j] = y;
+            if (wr) p.z[bt * Hd + j] = y;
           }
         }
-      }
-      __syncwarp();
-      {
-        // logits of rows 2w, 2w+1 for class `lane`: Ws rows are padded by 4 floats so that the 32
-        // lanes' float4 reads hit distinct banks; the z rows are broadcast reads
-        const float* wrow = Ws + (size_t)min(lane, C - 1) * (Hd + 4);
-        float a0 = 0.f, a1 = 0.f;
-        for (int k = 0; k < Hd; k += 4) {
+        __syncwarp();
+        const int k0 = half * (Hd >> 1);
+        const float* wrow = Ws + (size_t)min(lane, C - 1) * (Hd + 4) + k0;
+        const float* x = zr + k0;
+        for (int k = 0; k < (Hd >> 1); k += 4) {
           const float4 w = *reinterpret_cast<const float4*>(wrow + k);
-          const float4 x0 = *reinterpret_cast<const float4*>(z0 + k);
-          const float4 x1 = *reinterpret_cast<const float4*>(z0 + Hd + k);
-          a0 = fmaf(x0.x, w.x, a0); a0 = fmaf(x0.y, w.y, a0);
-          a0 = fmaf(x0.z, w.z, a0); a0 = fmaf(x0.w, w.w, a0);
-          a1 = fmaf(x1.x, w.x, a1); a1 = fmaf(x1.y, w.y, a1);
-          a1 = fmaf(x1.z, w.z, a1); a1 = fmaf(x1.w, w.w, a1);
+          const float4 xv = *reinterpret_cast<const float4*>(x + k);
+          a0 = fmaf(xv.x, w.x, a0); a1 = fmaf(xv.y, w.y, a1);
+          a0 = fmaf(xv.z, w.z, a0); a1 = fmaf(xv.w, w.w, a1);
         }
-        const float bb = lane < C ? p.b_os[(size_t)cta * C + lane] : 0.f;
-        lgt[0] = a0 + bb;
-        lgt[1] = a1 + bb;
+        if (half == 1) xch[rl * 32 + lane] = a0 + a1;
       }
-#pragma unroll
-      for (int rr = 0; rr < 2; ++rr) {
-        const int b = warp * 2 + rr;
-        if (b < B) {
-          const size_t bt = (size_t)b * T + t;
-          const bool valid = lane < C;
-          const float l = valid ? lgt[rr] : 0.f;
-          const Unimix um = unimix_probs(l, valid, C, p.unimix);
-          const float uu = valid ? p.u_post[(((size_t)t * B + b) * S + cta) * C + lane] : 1.f;
-          const int k = warp_argmax(um.probs / (-logf(uu)), valid, lane);
-          if (valid) {
-            const size_t o = (bt * S + cta) * C + lane;
-            p.post_logit[o] = l;
-            p.post_stoch[o] = (lane == k) ? 1.f : 0.f;
-          }
-          if (lane == 0) p.post_idx[bt * S + cta] = k;
+      __syncthreads();
+      if (act && half == 0) {
+        const float l = valid ? (a0 + a1) + xch[rl * 32 + lane] + p.b_os[(size_t)gE * C + lane] : 0.f;
+        const Unimix um = unimix_probs(l, valid, C, p.unimix);
+        const int k = warp_argmax(um.probs / (-logf(uu)), valid, lane);
+        if (valid) {
+          const size_t o = (bt * S + gE) * C + lane;
+          p.post_logit[o] = l;
+          p.post_stoch[o] = (lane == k) ? 1.f : 0.f;
         }
+        if (lane == 0) p.post_idx[bt * S + gE] = k;
       }
     }
     po_stamp(p, t, 7);
@@ -397,9 +410,10 @@ __global__ void __launch_bounds__(PO_THREADS, 1) observe_persistent_fwd_kernel(P
 static unsigned long long* g_po_timing = nullptr;
 
 static size_t po_smem_bytes(const PoArgs& a) {
-  const size_t fl = (size_t)a.ncg * (a.Hd + a.D) + (size_t)a.nco * a.D + (size_t)a.C * (a.Hd + 4) +
-                    (size_t)PO_ROWS * a.Hd + 6 * (size_t)a.D + 2 * (size_t)a.Hd + PO_WARPS * PO_NV +
-                    128 + ((a.S + 3) & ~3) + ((a.A + 3) & ~3) + 16;
+  const size_t fl = (size_t)a.ncg * (a.Hd + a.D) + (size_t)a.cpb * (a.D + 4) +
+                    (size_t)a.C * (a.Hd + 4) + (size_t)PO_WARPS * a.Hd + 4 * (size_t)a.D +
+                    6 * (size_t)a.D + 2 * (size_t)a.Hd + PO_WARPS * PO_NV + 128 +
+                    ((a.S + 3) & ~3) + ((a.A + 3) & ~3) + 16;
   return fl * 4;
 }
 
@@ -463,10 +477,19 @@ int observe_fwd_persistent(const dv3_rssm_dims* d, const dv3_rssm_params* p,
     }
   }
   a.ncg = (3 * D + G - 1) / G;
-  a.nco = (Hd + G - 1) / G;
   a.bufw = ((D > Hd ? D : Hd) + 3) & ~3;
+  // phase C/D: up to 4 rows per CTA (two warps per row); the W_obs columns go over the rest
+  a.nrbC = (io->B + 3) / 4;
+  a.rpbC = (io->B + a.nrbC - 1) / a.nrbC;
+  const int ncb = G / a.nrbC;
+  a.cpb = (Hd + ncb - 1) / ncb;
+  // phase E: G / S row blocks per categorical group
+  a.nrbE = G / S;
+  if (a.nrbE > io->B) a.nrbE = io->B;
+  a.rpbE = (io->B + a.nrbE - 1) / a.nrbE;
+  if (ncb < 1 || a.cpb > 16 || a.rpbC > 4 || a.rpbE > 4 || Hd % 8 != 0) return 0;
   const size_t smem = po_smem_bytes(a);
-  if (smem > 200 * 1024) return 0;
+  if (smem > 220 * 1024) return 0;
   switch (D / 32) {
     case 2: return po_launch<2>(a, G, smem, st, used);
     case 4: return po_launch<4>(a, G, smem, st, used);

@@ -4,7 +4,8 @@ H=15 imagination from all 1024 posteriors) on N B200s, one process per GPU.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--suite S]
 
-``--impl ours``       the product: dreamerv3-torch_b200 (CUDA kernels through the C ABI).
+``--impl ours``       the product: dreamerv3-torch_b200 (CUDA kernels through the C ABI), one
+                      whole train step per call of graphs.TrainStepGraph (a captured CUDA graph).
 ``--impl reference``  the reference's algorithm on the box's host cores: the CPU oracle port
                       (oracle/train_step.py), all host threads, same workload / metric / unit.
 
@@ -82,23 +83,30 @@ def _oracle_modules():
     return dv3_oracle, synth, train_step
 
 
-def cpu_oracle_rate(suite, steps, warmup, seed=0):
-    """Reference algorithm on the host cores: steps/s of oracle Agent.train_step."""
+def cpu_oracle_rate(suite, steps, warmup, seed=0, device="cpu"):
+    """Reference algorithm on the host cores (or, device='cuda:N', the same port run eagerly by
+    PyTorch on the GPU): steps/s of oracle Agent.train_step."""
     import torch
     O, synth, TS = _oracle_modules()
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     d = synth.dims_of(suite)
     c = synth.CONFIGS[suite]
+    mv = lambda D: {k: v.to(device) for k, v in D.items()}
     P, Pa, Pv = synth.agent_params(suite, seed)
     cfg = TS.make_cfg(actor_layers=c["actor_layers"], actor_dist=c["actor_dist"], units=c["units"])
-    agent = TS.Agent(P, Pa, Pv, cfg, d)
-    data = synth.replay_batch(d, 16, 64, seed)
+    agent = TS.Agent(mv(P), mv(Pa), mv(Pv), cfg, d)
+    data = {k: torch.as_tensor(v).to(device) for k, v in synth.replay_batch(d, 16, 64, seed).items()}
+    gpu = str(device).startswith("cuda")
     times = []
     for i in range(warmup + steps):
-        noise = synth.train_noise(d, 16, 64, cfg.imag_horizon, seed + i, c["actor_dist"])
+        noise = mv(synth.train_noise(d, 16, 64, cfg.imag_horizon, seed + i, c["actor_dist"]))
+        if gpu:
+            torch.cuda.synchronize()
         t0 = time.perf_counter()
         agent.train_step(data, noise)
+        if gpu:
+            torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
@@ -187,29 +195,29 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # The public API for a whole step is graphs.TrainStepGraph (the body of Dreamer._train,
+    # dreamer.py:194-200): its first calls run eagerly, then the step is captured into one CUDA
+    # graph; every call is exactly one WM + AC update.
+    graph = pkg.graphs.TrainStepGraph(wm, beh, reward_fn, warmup=2, device_metrics=True)
     W = max(args.warmup, 3)
-    for _ in range(W):
-        step(resident)
+    for _ in range(W + 3):                    # 2 eager + capture + >= W replays
+        graph(resident)
     barrier()
+    assert graph.captured
 
     # ---- timed region 1: inputs resident in HBM -----------------------------------------
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    lib.dv3_prof_enable(1)
-    launches0 = lib.dv3_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
     for _ in range(args.steps):
-        step(resident)
+        graph(resident)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    launches = lib.dv3_launch_count() - launches0
-    lib.dv3_prof_enable(0)
-    pm, pf, pl = (ctypes.c_double * 2)(), (ctypes.c_double * 2)(), (ctypes.c_longlong * 2)()
-    lib.dv3_prof_read(pm, pf, pl)
+    launches = graph.library_launches_per_step * args.steps
     if sampler:
         sampler.stop_flag = True
         sampler.join(timeout=3)
@@ -220,22 +228,41 @@ def run_ours(args):
     value = world * args.steps / (ms / 1e3)
 
     # ---- timed region 2: end to end through the public API with host buffers ------------
-    cfg.device_metrics = False               # _train returns numpy metrics: one D2H per call
+    graph.device_metrics = False             # numpy metrics: one stacked D2H per call
     d2h = 0
+    for _ in range(2):
+        graph(pinned)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        m1, m2 = step(pinned)
+        out = graph(pinned)
         if not d2h:
-            d2h = sum(np.asarray(v).nbytes for v in list(m1.values()) + list(m2.values())
-                      if isinstance(v, np.ndarray))
+            d2h = sum(np.asarray(v).nbytes for v in list(out["wm_metrics"].values()) +
+                      list(out["beh_metrics"].values()) if isinstance(v, np.ndarray))
     barrier()
     e2e_s = time.perf_counter() - t0
     t_e = torch.tensor([e2e_s], device=device)
     if world > 1:
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
     e2e = world * args.steps / float(t_e.item())
-    cfg.device_metrics = True
+    graph.device_metrics = True
+
+    # ---- roofline pass: the same step, eagerly, with CUDA events around every GEMM launch
+    # (events cannot be recorded per kernel while a graph replays) ------------------------
+    psteps = min(args.steps, 5)
+    step(resident)
+    barrier()
+    lib.dv3_prof_enable(1)
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for _ in range(psteps):
+        step(resident)
+    p1.record()
+    barrier()
+    eager_ms = p0.elapsed_time(p1) / psteps
+    lib.dv3_prof_enable(0)
+    pm, pf, pl = (ctypes.c_double * 2)(), (ctypes.c_double * 2)(), (ctypes.c_longlong * 2)()
+    lib.dv3_prof_read(pm, pf, pl)
 
     # ---- imagined states/s: _imagine forward alone ----------------------------------------
     post, _, _ = wm._train(resident)
@@ -256,8 +283,8 @@ def run_ours(args):
             dist.destroy_process_group()
         return
     peaks = _peaks()
-    tiled_ms, tiled_fl, tiled_n = pm[1], pf[1], pl[1]
-    skinny_ms, skinny_fl, skinny_n = pm[0], pf[0], pl[0]
+    tiled_ms, tiled_fl, tiled_n = pm[1] / psteps, pf[1] / psteps, pl[1] / psteps
+    skinny_ms, skinny_fl, skinny_n = pm[0] / psteps, pf[0] / psteps, pl[0] / psteps
     ach = (tiled_fl / (tiled_ms / 1e3) / 1e12) if tiled_ms > 0 else 0.0
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
@@ -275,13 +302,17 @@ def run_ours(args):
         "imagined_states_per_s": imag_states,
         "imagine_fwd_ms": imag_ms,
         "roofline": {
-            "kernel": "umma_gemm_3xtf32_kernel (tcgen05 3xTF32 GEMM of the imagination steps and all bulk-row "
-                      "contractions; dominant by time) + the fp32 SIMT tiled fallback for K % 4 != 0",
+            "kernel": "umma2_gemm_kernel (persistent tcgen05 3xTF32 GEMM: every imagination-step and bulk-row "
+                      "contraction, y / dx / dW; dominant by time)",
             "bound": "tensor", "achieved": ach, "peak": peaks["tf"], "unit": "TFLOP/s",
             "frac": ach / peaks["tf"], "traffic": None, "peak_source": peaks["src"],
-            "launches_per_step": tiled_n / args.steps, "ms_per_step": tiled_ms / args.steps,
-            "share_of_step": (tiled_ms / ms) if ms > 0 else None,
-            "skinny_gemv": {"launches_per_step": skinny_n / args.steps, "ms_per_step": skinny_ms / args.steps,
+            "flops": "algorithmic 2*M*N*K per launch (fp32 result); the kernel issues 3 tf32 MMAs per product, "
+                     "so the tensor pipe does 3x this against a tf32 peak of half the bf16 figure",
+            "timed_in": f"separate eager pass of {psteps} identical steps ({eager_ms:.2f} ms/step), CUDA events "
+                        "around every GEMM launch on the launching stream",
+            "launches_per_step": tiled_n, "ms_per_step": tiled_ms,
+            "share_of_step": (tiled_ms / eager_ms) if eager_ms > 0 else None,
+            "skinny_gemv": {"launches_per_step": skinny_n, "ms_per_step": skinny_ms,
                             "achieved_gflops": (skinny_fl / (skinny_ms / 1e3) / 1e9) if skinny_ms > 0 else 0.0},
         },
     }
@@ -290,6 +321,14 @@ def run_ours(args):
         line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                                 "sample": "3 full train steps (WM+AC, 16x64, H=15) after 1 warm-up, "
                                           "oracle/train_step.py on all host threads"}
+        try:
+            g = cpu_oracle_rate(args.suite, steps=10, warmup=3, device=device)
+            line["cpu_baseline"]["same_algorithm_eager_torch_on_this_gpu"] = {
+                "value": g["value"], "unit": UNIT, "ms_per_step": g["ms_per_step"],
+                "note": "the oracle port run op by op by PyTorch on cuda:0 (the north star's 'same-box "
+                        "PyTorch-CUDA' comparator; the port issues fewer ops than the reference's own code)"}
+        except Exception as e:          # informational only
+            line["cpu_baseline"]["same_algorithm_eager_torch_on_this_gpu"] = {"error": str(e)[:120]}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

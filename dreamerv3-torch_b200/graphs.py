@@ -1,0 +1,112 @@
+"""Whole-train-step CUDA graph: the reference's ``Dreamer._train`` body (dreamer.py:194-200 --
+``WorldModel._train`` followed by ``ImagBehavior._train`` on the detached posteriors) captured
+once and replayed, so that the ~1400 kernel launches of a step cost one ``cudaGraphLaunch``.
+
+Every call is exactly one training step.  The first ``warmup`` calls run eagerly (lazy CUDA
+initialisation, allocator warm-up), the next call captures -- recording only -- and replays.
+Inputs are copied into static device tensors before each replay (asynchronously from pinned
+host memory); sampling noise is drawn inside the graph from torch's graph-safe generator, or
+supplied per call (``noise=dict(u_prior, u_post, act_noise, u_state)``, staged like the batch);
+metrics come back as device scalars, or as numpy after one stacked device->host copy.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import kernels as K
+from . import tools
+
+
+class TrainStepGraph:
+    def __init__(self, world_model, behavior, objective=None, warmup=3, device_metrics=False):
+        self.wm, self.beh = world_model, behavior
+        if objective is None:
+            objective = lambda f, s, a: world_model.heads["reward"](
+                world_model.dynamics.get_feat(s)).mode()
+        self.objective = objective
+        self.warmup = int(warmup)
+        self.device_metrics = device_metrics
+        self._calls = 0
+        self._graph = None
+        self._static = None
+        self._out = None
+        self.library_launches_per_step = 0   # libdv3_b200 kernel nodes recorded in the graph
+        # warm-up steps and the capture share one side stream: autograd's gradient accumulators
+        # remember the stream they were created on, and the legacy default stream must not be
+        # made to wait on a capturing stream
+        self._stream = torch.cuda.Stream(device=world_model._config.device)
+        cfg = world_model._config
+        if cfg.critic["slow_target"] and cfg.critic["slow_target_update"] != 1:
+            raise NotImplementedError("graph capture bakes in the slow-critic update of every "
+                                      "step (slow_target_update must be 1)")
+
+    # -- staging -------------------------------------------------------------------------
+    def _stage(self, data, noise=None):
+        dev = self.wm._config.device
+        data = dict(data)
+        if noise is not None:
+            data.update({"__noise_" + k: v for k, v in noise.items()})
+        if self._static is None:
+            self._static = {}
+            for k, v in data.items():
+                t = v if torch.is_tensor(v) else torch.as_tensor(v)
+                self._static[k] = torch.empty(t.shape, dtype=t.dtype, device=dev)
+        if set(data) != set(self._static):
+            raise K.L.Dv3Error("TrainStepGraph: the set of batch / noise entries changed")
+        for k, buf in self._static.items():
+            v = data[k]
+            t = v if torch.is_tensor(v) else torch.as_tensor(v)
+            if t.shape != buf.shape or t.dtype != buf.dtype:
+                raise K.L.Dv3Error(f"TrainStepGraph: batch entry {k!r} changed shape/dtype "
+                                   f"({tuple(t.shape)} {t.dtype} vs {tuple(buf.shape)} {buf.dtype})")
+            buf.copy_(t, non_blocking=True)
+        return self._static
+
+    def _run(self, staged):
+        cfg = self.wm._config
+        keep = getattr(cfg, "device_metrics", False)
+        cfg.device_metrics = True
+        batch = {k: v for k, v in staged.items() if not k.startswith("__noise_")}
+        n1 = n2 = None
+        if "__noise_u_prior" in staged:
+            n1 = (staged["__noise_u_prior"], staged["__noise_u_post"])
+            n2 = (staged["__noise_act_noise"], staged["__noise_u_state"])
+        try:
+            post, context, m1 = self.wm._train(batch, noise=n1)
+            feat, state, action, weights, m2 = self.beh._train(post, self.objective, noise=n2)
+        finally:
+            cfg.device_metrics = keep
+        return dict(post=post, context=context, wm_metrics=m1, imag_feat=feat, imag_state=state,
+                    imag_action=action, weights=weights, beh_metrics=m2)
+
+    # -- one training step ---------------------------------------------------------------
+    def __call__(self, data, noise=None):
+        batch = self._stage(data, noise)
+        if self._graph is None and self._calls < self.warmup:
+            cur = torch.cuda.current_stream()
+            self._stream.wait_stream(cur)
+            with torch.cuda.stream(self._stream):
+                out = self._run(batch)
+            cur.wait_stream(self._stream)
+        else:
+            if self._graph is None:
+                torch.cuda.synchronize()
+                self._graph = torch.cuda.CUDAGraph()
+                n0 = K.L.lib().dv3_launch_count()
+                with torch.cuda.graph(self._graph, stream=self._stream):
+                    self._out = self._run(batch)
+                self.library_launches_per_step = int(K.L.lib().dv3_launch_count() - n0)
+                K.invalidate_weight_splits()     # planes cached during capture live in the pool
+            self._graph.replay()
+            out = self._out
+        self._calls += 1
+        if self.device_metrics:
+            return out
+        out = dict(out)
+        out["wm_metrics"] = tools.to_host(out["wm_metrics"])
+        out["beh_metrics"] = tools.to_host(out["beh_metrics"])
+        return out
+
+    @property
+    def captured(self):
+        return self._graph is not None

@@ -539,7 +539,9 @@ class _Observe(torch.autograd.Function):
         G = {k: None for k in L.RSSM_PARAM_FIELDS}
         if any(need.values()):
             r2 = lambda t: t.reshape(B * T, -1)
-            hot = F.one_hot(sprev_idx.reshape(B * T, S).long(), Cc).reshape(B * T, SC).float()
+            hot = torch.empty(B * T, SC, dtype=torch.float32, device=dev)
+            L.check(L.lib().dv3_idx_to_onehot(L.iptr(sprev_idx.reshape(B * T, S)), B * T, S, Cc,
+                                              L.fptr(hot), SC, L.stream_ptr()), "idx_to_onehot")
             dx, dg, dy, dz = (split(r2(o[k])) for k in ("d_x_pre", "d_g_pre", "d_y_pre", "d_z_pre"))
             dpo, dpr = r2(o["d_post_logit"]), r2(o["d_prior_logit"])
             dpos, dprs = split(dpo), split(dpr)

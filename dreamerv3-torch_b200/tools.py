@@ -339,7 +339,9 @@ class Optimizer:
         self._clip = clip
         self._wd = wd
         fused = bool(self._params) and self._params[0].is_cuda
-        self._opt = torch.optim.Adam(self._params, lr=lr, eps=eps, fused=fused)
+        # capturable: the step counter lives on the device, so that a whole train step can be
+        # recorded into a CUDA graph (graphs.TrainStepGraph)
+        self._opt = torch.optim.Adam(self._params, lr=lr, eps=eps, fused=fused, capturable=fused)
         self._sync = grad_sync
 
     def set_grad_sync(self, sync):

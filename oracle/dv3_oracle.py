@@ -163,7 +163,7 @@ def rssm_initial(p: Params, batch: int, d: RSSMDims) -> Dict[str, Tensor]:
     deter = torch.tanh(p["W"]).repeat(batch, 1)
     stoch = onehot_mode(prior_head(p, deter, d), d.unimix)
     return {"stoch": stoch, "deter": deter,
-            "logit": torch.zeros(batch, d.stoch, d.classes, dtype=deter.dtype)}
+            "logit": torch.zeros(batch, d.stoch, d.classes, dtype=deter.dtype, device=deter.device)}
 
 
 def img_step(p: Params, state: Dict[str, Tensor], action: Tensor, u: Optional[Tensor],
@@ -190,7 +190,7 @@ def obs_step(p: Params, prev: Optional[Dict[str, Tensor]], action: Tensor, embed
     n = is_first.shape[0]
     if prev is None or bool(is_first.sum() == n):
         prev = rssm_initial(p, n, d)
-        action = torch.zeros(n, d.actions, dtype=embed.dtype)
+        action = torch.zeros(n, d.actions, dtype=embed.dtype, device=embed.device)
     elif bool(is_first.sum() > 0):
         m = is_first[:, None]
         action = action * (1.0 - m)
@@ -284,19 +284,20 @@ def lambda_return(reward: Tensor, value: Tensor, pcont: Tensor, bootstrap: Tenso
 # --------------------------------------------------------------------------------------
 # symlog two-hot discrete regression head                              tools.py:463-517
 # --------------------------------------------------------------------------------------
-def buckets(dtype=torch.float32) -> Tensor:
-    return torch.linspace(-20.0, 20.0, steps=255).to(dtype)
+def buckets(dtype=torch.float32, device=None) -> Tensor:
+    # built on the CPU like the reference's config-time linspace, then moved (same bits everywhere)
+    return torch.linspace(-20.0, 20.0, steps=255).to(dtype).to(device)
 
 
 def twohot_mean(logits: Tensor) -> Tensor:
     """DiscDist.mean / mode: symexp(sum softmax(l) * buckets).  tools.py:481-487."""
-    b = buckets(logits.dtype)
+    b = buckets(logits.dtype, logits.device)
     return symexp(torch.sum(torch.softmax(logits, -1) * b, dim=-1, keepdim=True))
 
 
 def twohot_logprob(logits: Tensor, x: Tensor) -> Tensor:
     """DiscDist.log_prob.  tools.py:490-513.  logits [...,255], x [...,1] -> [...]."""
-    b = buckets(logits.dtype)
+    b = buckets(logits.dtype, logits.device)
     x = symlog(x)
     below = torch.sum((b <= x[..., None]).to(torch.int32), dim=-1) - 1
     above = len(b) - torch.sum((b > x[..., None]).to(torch.int32), dim=-1)

@@ -113,7 +113,7 @@ def behavior_losses(P_wm, P_actor, P_value, P_slow, ema_vals, start, noise, cfg,
     weights = torch.cumprod(torch.cat([torch.ones_like(discount[:1]), discount[:-1]], 0), 0).detach()
     base = value[:-1]
     if cfg.reward_EMA:                                                # models.py:19-26, 654-659
-        q = torch.quantile(target.detach().flatten(), torch.tensor([0.05, 0.95]))
+        q = torch.quantile(target.detach().flatten(), torch.tensor([0.05, 0.95], device=target.device))
         ema_vals = 0.01 * q + 0.99 * ema_vals
         scale = torch.clip(ema_vals[1] - ema_vals[0], min=1.0)
         offset = ema_vals[0]
@@ -181,7 +181,7 @@ class Agent:
         self.P_wm, self.P_actor, self.P_value = leaf(P_wm), leaf(P_actor), leaf(P_value)
         self.P_slow = {k: v.detach().clone() for k, v in self.P_value.items()}
         self.cfg, self.d = cfg, d
-        self.ema_vals = torch.zeros(2)
+        self.ema_vals = torch.zeros(2, device=next(iter(self.P_wm.values())).device)
         self.updates = 0
         self.opt_wm = Adam(self.P_wm, cfg.model_lr, cfg.model_eps, cfg.model_clip)
         self.opt_actor = Adam(self.P_actor, cfg.actor_lr, cfg.actor_eps, cfg.actor_clip)

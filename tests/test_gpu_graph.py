@@ -1,0 +1,65 @@
+"""-m gpu: the whole-train-step CUDA graph replays the same training as the eager calls."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _agent(pkg, device, seed=0):
+    cfgs = pkg.configs
+    torch.manual_seed(seed)
+    cfg = cfgs.make_config("dmc_proprio", device=device, dyn_stoch=8, dyn_discrete=8, dyn_deter=64,
+                           dyn_hidden=64, units=64, imag_horizon=5,
+                           encoder=dict(mlp_units=64, mlp_layers=2), decoder=dict(mlp_units=64, mlp_layers=2))
+    wm = pkg.models.WorldModel(cfgs.ObsSpace(cfgs.PROPRIO_SHAPES), None, 0, cfg)
+    beh = pkg.models.ImagBehavior(cfg, wm)
+    return cfg, wm, beh
+
+
+def _batch(rs, B, T, A):
+    host = {k: rs.randn(B, T, n).astype(np.float32) for k, n in (("orientations", 14), ("height", 1), ("velocity", 9))}
+    host["action"] = rs.uniform(-1, 1, size=(B, T, A)).astype(np.float32)
+    host["reward"] = rs.randn(B, T).astype(np.float32)
+    host["discount"] = np.ones((B, T), np.float32)
+    host["is_terminal"] = np.zeros((B, T), np.float32)
+    host["is_first"] = np.zeros((B, T), np.float32)
+    host["is_first"][:, 0] = 1
+    host["is_first"][1, T // 2] = 1
+    return host
+
+
+def test_graph_step_matches_eager(pkg, device):
+    B, T = 6, 10
+    cfg, wm_a, beh_a = _agent(pkg, device)
+    _, wm_b, beh_b = _agent(pkg, device)
+    wm_b.load_state_dict(wm_a.state_dict())
+    beh_b.load_state_dict(beh_a.state_dict())
+    A, S, C, H = cfg.num_actions, cfg.dyn_stoch, cfg.dyn_discrete, cfg.imag_horizon
+    N = B * T
+    graph = pkg.graphs.TrainStepGraph(wm_b, beh_b, warmup=2)
+    reward = lambda f, s, a: wm_a.heads["reward"](wm_a.dynamics.get_feat(s)).mode()
+    rs = np.random.RandomState(3)
+    gen = torch.Generator().manual_seed(5)
+    for step in range(5):
+        data = _batch(rs, B, T, A)
+        noise = dict(u_prior=torch.rand(T, B, S, C, generator=gen).clamp_(1e-30, 1.0),
+                     u_post=torch.rand(T, B, S, C, generator=gen).clamp_(1e-30, 1.0),
+                     act_noise=torch.randn(H, N, A, generator=gen),
+                     u_state=torch.rand(H, N, S, C, generator=gen).clamp_(1e-30, 1.0))
+        nd = {k: v.to(device) for k, v in noise.items()}
+        post, _, m1 = wm_a._train(data, noise=(nd["u_prior"], nd["u_post"]))
+        _, _, _, _, m2 = beh_a._train(post, reward, noise=(nd["act_noise"], nd["u_state"]))
+        out = graph(data, noise=noise)
+        assert graph.captured == (step >= 2)
+        assert torch.equal(out["post"]["stoch"], post["stoch"]), step
+        for k in ("model_loss", "model_grad_norm", "kl"):
+            assert abs(float(out["wm_metrics"][k]) - float(m1[k])) <= 2e-5 * abs(float(m1[k])) + 1e-7, (step, k)
+        for k in ("actor_loss", "value_loss", "actor_grad_norm", "value_grad_norm"):
+            assert abs(float(out["beh_metrics"][k]) - float(m2[k])) <= 2e-5 * abs(float(m2[k])) + 1e-7, (step, k)
+    for (k, a), b in zip(wm_a.state_dict().items(), wm_b.state_dict().values()):
+        assert float((a - b).abs().max()) <= 2e-6, k
+    for (k, a), b in zip(beh_a.state_dict().items(), beh_b.state_dict().values()):
+        assert float((a.float() - b.float()).abs().max()) <= 2e-6, k

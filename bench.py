@@ -198,12 +198,19 @@ def run_ours(args):
     # The public API for a whole step is graphs.TrainStepGraph (the body of Dreamer._train,
     # dreamer.py:194-200): its first calls run eagerly, then the step is captured into one CUDA
     # graph; every call is exactly one WM + AC update.
-    graph = pkg.graphs.TrainStepGraph(wm, beh, reward_fn, warmup=2, device_metrics=True)
+    def stage(msg):
+        if os.environ.get("DV3_BENCH_TRACE"):
+            print(f"[bench rank {rank}] {msg}", file=sys.stderr, flush=True)
+
+    never = 1 << 30 if args.no_graph else 2
+    graph = pkg.graphs.TrainStepGraph(wm, beh, reward_fn, warmup=never, device_metrics=True)
     W = max(args.warmup, 3)
-    for _ in range(W + 3):                    # 2 eager + capture + >= W replays
+    stage("warm-up / capture")
+    for i in range(W + 3):                    # 2 eager + capture + >= W replays
         graph(resident)
+        stage(f"call {i} done (captured={graph.captured})")
     barrier()
-    assert graph.captured
+    assert graph.captured or args.no_graph
 
     # ---- timed region 1: inputs resident in HBM -----------------------------------------
     sampler = ClockSampler(local) if rank == 0 else None
@@ -211,13 +218,16 @@ def run_ours(args):
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    launches0 = lib.dv3_launch_count()
     e0.record()
     for _ in range(args.steps):
         graph(resident)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    launches = graph.library_launches_per_step * args.steps
+    launches = (graph.library_launches_per_step * args.steps if graph.captured
+                else lib.dv3_launch_count() - launches0)
+    stage("timed region 1 done")
     if sampler:
         sampler.stop_flag = True
         sampler.join(timeout=3)
@@ -232,6 +242,7 @@ def run_ours(args):
     d2h = 0
     for _ in range(2):
         graph(pinned)
+    stage("e2e warm calls done")
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -246,11 +257,13 @@ def run_ours(args):
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
     e2e = world * args.steps / float(t_e.item())
     graph.device_metrics = True
+    stage("timed region 2 done")
 
     # ---- roofline pass: the same step, eagerly, with CUDA events around every GEMM launch
     # (events cannot be recorded per kernel while a graph replays) ------------------------
     psteps = min(args.steps, 5)
     step(resident)
+    stage("first eager step after graph done")
     barrier()
     lib.dv3_prof_enable(1)
     p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -263,6 +276,7 @@ def run_ours(args):
     lib.dv3_prof_enable(0)
     pm, pf, pl = (ctypes.c_double * 2)(), (ctypes.c_double * 2)(), (ctypes.c_longlong * 2)()
     lib.dv3_prof_read(pm, pf, pl)
+    stage("roofline pass done")
 
     # ---- imagined states/s: _imagine forward alone ----------------------------------------
     post, _, _ = wm._train(resident)
@@ -278,9 +292,21 @@ def run_ours(args):
     imag_ms = a0.elapsed_time(a1) / 5
     imag_states = world * B * T * cfg.imag_horizon / (imag_ms / 1e3)
 
-    if rank != 0:
+    stage("imagine timing done")
+    barrier()
+
+    def leave():
+        # The NCCL communicator is referenced by the captured graph; tearing the process group
+        # down while the graph is alive blocks (measured: destroy_process_group never returns
+        # after a capture that contains the allreduce).  All collective work is finished here,
+        # so every rank just flushes and exits.
+        sys.stdout.flush()
+        sys.stderr.flush()
         if world > 1:
-            dist.destroy_process_group()
+            os._exit(0)
+
+    if rank != 0:
+        leave()
         return
     peaks = _peaks()
     tiled_ms, tiled_fl, tiled_n = pm[1] / psteps, pf[1] / psteps, pl[1] / psteps
@@ -330,8 +356,7 @@ def run_ours(args):
         except Exception as e:          # informational only
             line["cpu_baseline"]["same_algorithm_eager_torch_on_this_gpu"] = {"error": str(e)[:120]}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    leave()
 
 
 def main():
@@ -342,6 +367,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--suite", default="dmc_proprio", choices=["dmc_proprio", "dmc_vision", "atari100k"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="run every step eagerly (debugging)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

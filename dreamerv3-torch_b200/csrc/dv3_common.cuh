@@ -153,32 +153,40 @@ int linear1(const float* A, int lda, const float* W, int ldw, int K, const float
             int ldc, int M, int N, int accumulate, cudaStream_t st);
 int launch_transpose(const float* in, int ld, int R, int C, float* out, cudaStream_t st);
 
+// optional tf32 hi/lo planes [M, ld] written by a producer kernel beside its fp32 output
+struct SplitOut {
+  float* hi = nullptr;
+  float* lo = nullptr;
+  int ld = 0;
+};
+
 // Row-wise kernels.  Every matrix argument is (pointer, row stride) so that batch-major
 // [B,T,w] tensors can be addressed per time step as (base + t*w, T*w).
 int ln_silu_fwd(const float* pre, int ld, const float* g, const float* b, float eps, int M, int n,
-                float* out, int ldo, cudaStream_t st);
+                float* out, int ldo, cudaStream_t st, SplitOut so = SplitOut());
 int ln_silu_bwd(const float* pre, int ld, const float* g, const float* b, float eps,
                 const float* d_out, int ldd, int M, int n, float* d_pre, int ldp, float* d_ln,
-                int ldl, cudaStream_t st);
+                int ldl, cudaStream_t st, SplitOut so = SplitOut());
 // x_pre = addend + sum_g WT[g*C+idx[g]] + sum_a act[a]*WT[S*C+a];  x = SiLU(LN(x_pre))
 int gather_ln_silu(const int32_t* idx, int ldi, int S, int C, const float* act, int lda, int A,
                    const float* WT, const float* addend, int ldadd, const float* g, const float* b,
                    float eps, int M, int n, float* pre, int ldp, float* out, int ldo,
-                   cudaStream_t st);
+                   cudaStream_t st, SplitOut so = SplitOut());
 int gru_gates_fwd(const float* g_pre, int ldg, const float* g, const float* b, float eps,
-                  const float* h, int ldh, int M, int D, float* h_new, int ldn, cudaStream_t st);
+                  const float* h, int ldh, int M, int D, float* h_new, int ldn, cudaStream_t st,
+                  SplitOut so = SplitOut());
 // dh_in: up to 4 addends (NULL = skip), each with its own row stride
 int gru_gates_bwd(const float* g_pre, int ldg, const float* g, const float* b, float eps,
                   const float* h, int ldh, const float* const dh_in[4], const int ld_in[4], int M,
                   int D, float* d_g_pre, int ldp, float* d_g_ln, int ldl, float* dh_direct,
-                  int ldd, cudaStream_t st);
+                  int ldd, cudaStream_t st, SplitOut so = SplitOut());
 // u row r is read at row perm(r) = (r % permT) * permB + r / permT when permT > 0
 int onehot_sample(const float* logits, int ldl, const float* u, int ldu, int permT, int permB,
                   float unimix, int M, int S, int C, int32_t* idx, int ldi, float* onehot, int ldo,
                   cudaStream_t st);
 int onehot_st_bwd(const float* logits, int ldl, const float* g1, int ldg1, const float* g2,
                   int ldg2, const float* ext, int lde, float unimix, int M, int S, int C,
-                  float* d_logits, int ldd, cudaStream_t st);
+                  float* d_logits, int ldd, cudaStream_t st, SplitOut so = SplitOut());
 int idx_to_onehot(const int32_t* idx, int ldi, int M, int S, int C, float* out, int ld,
                   cudaStream_t st);
 int copy_rows(const float* in, int ldi, int M, int n, float* out, int ldo, cudaStream_t st);
@@ -244,6 +252,13 @@ struct LinW {
     W = w; ldw = ld;
     if (tc) return tc_split(w, ld, K, nullptr, 0, 0, N, hi, lo, st);
     return 0;
+  }
+  // C = [A1|A2] W^T from A planes a producer kernel already wrote (tensor-core path only)
+  int apply_split(const SplitOut& a1, int K1, const SplitOut* a2, int K2, const float* bias,
+                  const float* addend, int ldadd, float* C, int ldc, int M, cudaStream_t st) const {
+    TcOperand o1{a1.hi, a1.lo, a1.ld, false}, o2{nullptr, nullptr, 0, false}, b{hi, lo, K, false};
+    if (a2) { o2.hi = a2->hi; o2.lo = a2->lo; o2.ld = a2->ld; }
+    return tc_gemm_ops(o1, K1, a2 ? &o2 : nullptr, K2, b, bias, addend, ldadd, C, ldc, M, N, 0, st);
   }
   // ascr: 2*M*K floats of scratch (only used on the tensor-core path)
   int apply(const float* A1, int lda1, int K1, const float* A2, int lda2, int K2, const float* bias,

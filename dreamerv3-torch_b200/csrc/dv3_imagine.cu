@@ -112,9 +112,24 @@ struct ImgFwdWs {
   float* WinT;   // [(SC+A), Hd]
   float* Wa0T;   // [F, U]
   float* a_add;  // [N, U]
-  float* ascr;   // split scratch for the tensor-core path: 2 * N * max K
+  // tensor-core path: tf32 hi/lo planes of every GEMM input, written by the kernel that produces
+  // the activation (no split passes inside the time loop)
+  SplitOut dsp[2];   // deter of state k / k+1   [N, D]
+  SplitOut xsp;      // x                        [N, Hd]
+  SplitOut ysp;      // y                        [N, Hd]
+  SplitOut asp[2];   // actor activations        [N, U]
   LinW gru, out, ims, a0d, al[16];
 };
+
+static SplitOut take_split(Arena& a, bool on, size_t rows, int cols) {
+  SplitOut s;
+  if (on) {
+    s.hi = a.take<float>(rows * cols);
+    s.lo = a.take<float>(rows * cols);
+    s.ld = cols;
+  }
+  return s;
+}
 
 static void carve_img_fwd(Arena& a, const dv3_rssm_dims* d, const dv3_actor* act, int N,
                           ImgFwdWs& w) {
@@ -124,18 +139,21 @@ static void carve_img_fwd(Arena& a, const dv3_rssm_dims* d, const dv3_actor* act
   w.gru.reserve(a, tc, 3 * D, Hd + D);
   w.out.reserve(a, tc, Hd, D);
   w.ims.reserve(a, tc, SC, Hd);
-  int maxk = Hd + D;
+  w.dsp[0] = take_split(a, tc, N, D);
+  w.dsp[1] = take_split(a, tc, N, D);
+  w.xsp = take_split(a, tc, N, Hd);
+  w.ysp = take_split(a, tc, N, Hd);
   if (act) {
     const int U = act->units;
     w.Wa0T = a.take<float>((size_t)(SC + D) * U);
     w.a_add = a.take<float>((size_t)N * U);
     w.a0d.reserve(a, tc, U, D);
     for (int i = 1; i < act->layers; ++i) w.al[i].reserve(a, tc, U, U);
-    if (U > maxk) maxk = U;
+    w.asp[0] = take_split(a, tc, N, U);
+    w.asp[1] = take_split(a, tc, N, U);
   } else {
     w.Wa0T = w.a_add = nullptr;
   }
-  w.ascr = tc ? a.take<float>((size_t)2 * N * maxk) : nullptr;
 }
 
 static int check_actor(const dv3_rssm_dims* d, const dv3_actor* a, const char* who) {
@@ -214,27 +232,38 @@ extern "C" int dv3_imagine_fwd(const dv3_rssm_dims* d, const dv3_rssm_params* p,
   DV3_TRY(copy_rows_i32(io->start_idx, S, N, S, io->idx, S, st));
   DV3_TRY(idx_to_onehot(io->start_idx, S, N, S, C, io->feat, F, st));
   DV3_TRY(copy_rows(io->start_deter, D, N, D, io->feat + SC, F, st));
+  const bool tc = w.gru.tc;
+  if (tc) DV3_TRY(tc_split(io->start_deter, D, D, nullptr, 0, 0, N, w.dsp[0].hi, w.dsp[0].lo, st));
+  // C = [A1|A2] W^T: from the producers' hi/lo planes on the tensor-core path, from the fp32
+  // activations on the CUDA-core path (N < 64 rows)
+  auto lin = [&](const LinW& W, const float* A1, int lda1, int K1, const SplitOut& s1,
+                 const float* A2, int lda2, int K2, const SplitOut* s2, const float* bias, float* Cc,
+                 int ldc) -> int {
+    if (W.tc) return W.apply_split(s1, K1, A2 ? s2 : nullptr, K2, bias, nullptr, 0, Cc, ldc, N, st);
+    return W.apply(A1, lda1, K1, A2, lda2, K2, bias, nullptr, 0, Cc, ldc, N, nullptr, st);
+  };
 
   for (int k = 0; k < H; ++k) {
     float* featk = io->feat + (size_t)k * N * F;
     const int32_t* idxk = io->idx + (size_t)k * N * S;
     float* actk = io->action + (size_t)k * N * A;
+    const SplitOut& dcur = w.dsp[k & 1];
+    const SplitOut& dnxt = w.dsp[(k + 1) & 1];
     if (a) {
       const size_t lstride = (size_t)H * N * U;
       float* pre0 = io->a_pre + (size_t)k * N * U;
       float* act0 = io->a_act + (size_t)k * N * U;
       // layer 0: deter columns dense, stoch columns gathered
-      DV3_TRY(w.a0d.apply(featk + SC, F, D, nullptr, 0, 0, nullptr, nullptr, 0, w.a_add, U, N,
-                          w.ascr, st));
+      DV3_TRY(lin(w.a0d, featk + SC, F, D, dcur, nullptr, 0, 0, nullptr, nullptr, w.a_add, U));
       DV3_TRY(gather_ln_silu(idxk, S, S, C, nullptr, 0, 0, w.Wa0T, w.a_add, U, a->ln_g[0],
-                             a->ln_b[0], d->ln_eps, N, U, pre0, U, act0, U, st));
+                             a->ln_b[0], d->ln_eps, N, U, pre0, U, act0, U, st, w.asp[0]));
       for (int i = 1; i < L; ++i) {
         float* prei = io->a_pre + i * lstride + (size_t)k * N * U;
         float* acti = io->a_act + i * lstride + (size_t)k * N * U;
         const float* prev = io->a_act + (i - 1) * lstride + (size_t)k * N * U;
-        DV3_TRY(w.al[i].apply(prev, U, U, nullptr, 0, 0, nullptr, nullptr, 0, prei, U, N, w.ascr,
-                              st));
-        DV3_TRY(ln_silu_fwd(prei, U, a->ln_g[i], a->ln_b[i], d->ln_eps, N, U, acti, U, st));
+        DV3_TRY(lin(w.al[i], prev, U, U, w.asp[(i - 1) & 1], nullptr, 0, 0, nullptr, nullptr, prei, U));
+        DV3_TRY(ln_silu_fwd(prei, U, a->ln_g[i], a->ln_b[i], d->ln_eps, N, U, acti, U, st,
+                            i + 1 < L ? w.asp[i & 1] : SplitOut()));
       }
       const float* top = io->a_act + (L - 1) * lstride + (size_t)k * N * U;
       float* mraw = io->a_mean_raw + (size_t)k * N * A;
@@ -284,15 +313,13 @@ extern "C" int dv3_imagine_fwd(const dv3_rssm_dims* d, const dv3_rssm_params* p,
     float* yk = io->y + (size_t)k * N * Hd;
     float* logn = io->logit + (size_t)(k + 1) * N * SC;
     DV3_TRY(gather_ln_silu(idxk, S, S, C, actk, A, A, w.WinT, nullptr, 0, p->ln_in_g, p->ln_in_b,
-                           d->ln_eps, N, Hd, xpre, Hd, xk, Hd, st));
-    DV3_TRY(w.gru.apply(xk, Hd, Hd, featk + SC, F, D, nullptr, nullptr, 0, gpre, 3 * D, N, w.ascr,
-                        st));
+                           d->ln_eps, N, Hd, xpre, Hd, xk, Hd, st, w.xsp));
+    DV3_TRY(lin(w.gru, xk, Hd, Hd, w.xsp, featk + SC, F, D, &dcur, nullptr, gpre, 3 * D));
     DV3_TRY(gru_gates_fwd(gpre, 3 * D, p->ln_gru_g, p->ln_gru_b, d->ln_eps, featk + SC, F, N, D,
-                          featn + SC, F, st));
-    DV3_TRY(w.out.apply(featn + SC, F, D, nullptr, 0, 0, nullptr, nullptr, 0, ypre, Hd, N, w.ascr,
-                        st));
-    DV3_TRY(ln_silu_fwd(ypre, Hd, p->ln_out_g, p->ln_out_b, d->ln_eps, N, Hd, yk, Hd, st));
-    DV3_TRY(w.ims.apply(yk, Hd, Hd, nullptr, 0, 0, p->b_ims, nullptr, 0, logn, SC, N, w.ascr, st));
+                          featn + SC, F, st, dnxt));
+    DV3_TRY(lin(w.out, featn + SC, F, D, dnxt, nullptr, 0, 0, nullptr, nullptr, ypre, Hd));
+    DV3_TRY(ln_silu_fwd(ypre, Hd, p->ln_out_g, p->ln_out_b, d->ln_eps, N, Hd, yk, Hd, st, w.ysp));
+    DV3_TRY(lin(w.ims, yk, Hd, Hd, w.ysp, nullptr, 0, 0, nullptr, p->b_ims, logn, SC));
     DV3_TRY(onehot_sample(logn, SC, io->u_state + (size_t)k * N * SC, SC, 0, 0, d->unimix, N, S, C,
                           io->idx + (size_t)(k + 1) * N * S, S, featn, F, st));
   }
@@ -306,7 +333,8 @@ namespace dv3 {
 
 struct ImgBwdWs {
   float *WimsT, *WoutT, *WgruT, *WinT;
-  float *d_y, *dh_y, *dxh, *dxh_add, *dsa, *ascr;
+  float *d_y, *dh_y, *dxh, *dxh_add, *dsa;
+  SplitOut dlsp, dysp, dgsp, dxsp;   // hi/lo planes of d_logit, d_y_pre, d_g_pre, d_x_pre
   LinW ims, out, gru, in;   // over the transposed weights
 };
 
@@ -327,9 +355,10 @@ static void carve_img_bwd(Arena& a, const dv3_rssm_dims* d, int N, ImgBwdWs& w) 
   w.out.reserve(a, tc, (int)D, (int)Hd);            // dh_y  = d_y_pre @ W_out      (K = Hd)
   w.gru.reserve(a, tc, (int)(Hd + D), (int)(3 * D)); // dxh  = d_g_pre @ W_gru      (K = 3D)
   w.in.reserve(a, tc, (int)(SC + A), (int)Hd);      // dsa   = d_x_pre @ W_in       (K = Hd)
-  size_t maxk = SC > 3 * D ? SC : 3 * D;
-  if (Hd > maxk) maxk = Hd;
-  w.ascr = tc ? a.take<float>((size_t)2 * N * maxk) : nullptr;
+  w.dlsp = take_split(a, tc, N, (int)SC);
+  w.dysp = take_split(a, tc, N, (int)Hd);
+  w.dgsp = take_split(a, tc, N, (int)(3 * D));
+  w.dxsp = take_split(a, tc, N, (int)Hd);
 }
 
 __global__ void add2_rows_kernel(const float* __restrict__ a, int lda, const float* __restrict__ b,
@@ -390,6 +419,13 @@ extern "C" int dv3_imagine_bwd(const dv3_rssm_dims* d, const dv3_rssm_params* p,
   DV3_TRY(w.in.prepare(w.WinT, Hd, st));
   DV3_TRY(fill_zero(w.dxh_add, (size_t)N * (Hd + D) * 4, st));
 
+  // C = A W^T with A = a delta the producing kernel also wrote as hi/lo planes
+  auto blin = [&](const LinW& W, const float* A1, int lda, int K, const SplitOut& sp,
+                  const float* addend, int ldadd, float* Cc, int ldc) -> int {
+    if (W.tc) return W.apply_split(sp, K, nullptr, 0, nullptr, addend, ldadd, Cc, ldc, N, st);
+    return W.apply(A1, lda, K, nullptr, 0, 0, nullptr, addend, ldadd, Cc, ldc, N, nullptr, st);
+  };
+
   auto actor_bwd = [&](int k, const float* d_a, int ld, int col) -> int {
     if (!a) return 0;
     const size_t o = (size_t)k * N * A;
@@ -417,26 +453,24 @@ extern "C" int dv3_imagine_bwd(const dv3_rssm_dims* d, const dv3_rssm_params* p,
     const float* gl = io->g_logit ? io->g_logit + on * SC : nullptr;
     float* dlog = io->d_logit + on * SC;
     DV3_TRY(onehot_st_bwd(io->logit + on * SC, SC, gs, SC, ds_rec, SC + A, gl, SC, d->unimix, N, S,
-                          C, dlog, SC, st));
-    DV3_TRY(w.ims.apply(dlog, SC, SC, nullptr, 0, 0, nullptr, nullptr, 0, w.d_y, Hd, N, w.ascr, st));
+                          C, dlog, SC, st, w.dlsp));
+    DV3_TRY(blin(w.ims, dlog, SC, SC, w.dlsp, nullptr, 0, w.d_y, Hd));
     const size_t ok = (size_t)k * N;
     DV3_TRY(ln_silu_bwd(io->y_pre + ok * Hd, Hd, p->ln_out_g, p->ln_out_b, d->ln_eps, w.d_y, Hd, N,
-                        Hd, io->d_y_pre + ok * Hd, Hd, io->d_y_ln + ok * Hd, Hd, st));
-    DV3_TRY(w.out.apply(io->d_y_pre + ok * Hd, Hd, Hd, nullptr, 0, 0, nullptr, nullptr, 0, w.dh_y, D,
-                        N, w.ascr, st));
+                        Hd, io->d_y_pre + ok * Hd, Hd, io->d_y_ln + ok * Hd, Hd, st, w.dysp));
+    DV3_TRY(blin(w.out, io->d_y_pre + ok * Hd, Hd, Hd, w.dysp, nullptr, 0, w.dh_y, D));
     const float* dh_in[4] = {w.dh_y, io->g_deter ? io->g_deter + on * D : nullptr, dh_rec, nullptr};
     const int ld_in[4] = {D, D, Hd + D, 0};
     DV3_TRY(gru_gates_bwd(io->g_pre + ok * 3 * D, 3 * D, p->ln_gru_g, p->ln_gru_b, d->ln_eps,
                           io->feat + ok * F + SC, F, dh_in, ld_in, N, D, io->d_g_pre + ok * 3 * D,
-                          3 * D, io->d_g_ln + ok * 3 * D, 3 * D, w.dxh_add + Hd, Hd + D, st));
-    DV3_TRY(w.gru.apply(io->d_g_pre + ok * 3 * D, 3 * D, 3 * D, nullptr, 0, 0, nullptr, w.dxh_add,
-                        Hd + D, w.dxh, Hd + D, N, w.ascr, st));
+                          3 * D, io->d_g_ln + ok * 3 * D, 3 * D, w.dxh_add + Hd, Hd + D, st, w.dgsp));
+    DV3_TRY(blin(w.gru, io->d_g_pre + ok * 3 * D, 3 * D, 3 * D, w.dgsp, w.dxh_add, Hd + D, w.dxh,
+                 Hd + D));
     dh_rec = w.dxh + Hd;
     DV3_TRY(ln_silu_bwd(io->x_pre + ok * Hd, Hd, p->ln_in_g, p->ln_in_b, d->ln_eps, w.dxh, Hd + D,
-                        N, Hd, io->d_x_pre + ok * Hd, Hd, io->d_x_ln + ok * Hd, Hd, st));
+                        N, Hd, io->d_x_pre + ok * Hd, Hd, io->d_x_ln + ok * Hd, Hd, st, w.dxsp));
     // [d stoch_k | d action_k] = d_x_pre @ W_in
-    DV3_TRY(w.in.apply(io->d_x_pre + ok * Hd, Hd, Hd, nullptr, 0, 0, nullptr, nullptr, 0, w.dsa,
-                       SC + A, N, w.ascr, st));
+    DV3_TRY(blin(w.in, io->d_x_pre + ok * Hd, Hd, Hd, w.dxsp, nullptr, 0, w.dsa, SC + A));
     ds_rec = w.dsa;
     DV3_TRY(actor_bwd(k, w.dsa, SC + A, SC));
   }

@@ -13,6 +13,17 @@ namespace dv3 {
 
 constexpr int ROW_THREADS = 256;
 
+// optional tf32 hi/lo planes of a kernel's output (the A operand of the next tensor-core GEMM):
+// hi = x with the 13 low mantissa bits cleared, lo = x - hi.  Written next to the fp32 output so
+// no separate split pass (and its extra read of the tensor) is needed.
+__device__ __forceinline__ void put_split(const SplitOut& so, size_t row, int col, float x) {
+  if (so.hi) {
+    const float h = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+    so.hi[row * so.ld + col] = h;
+    so.lo[row * so.ld + col] = x - h;
+  }
+}
+
 // mean and 1/sqrt(var+eps) of a row (two-pass, biased variance, like ATen's layer_norm)
 __device__ __forceinline__ void row_stats(const float* __restrict__ row, int n, float eps,
                                           float* red, float& mean, float& rstd) {
@@ -35,20 +46,23 @@ __device__ __forceinline__ void row_stats(const float* __restrict__ row, int n, 
 __global__ void __launch_bounds__(ROW_THREADS)
 ln_silu_fwd_kernel(const float* __restrict__ pre, int ld, const float* __restrict__ g,
                    const float* __restrict__ b, float eps, int n, float* __restrict__ out,
-                   int ldo) {
+                   int ldo, SplitOut so) {
   __shared__ float red[4 * 32];
   const float* row = pre + (size_t)blockIdx.x * ld;
   float mean, rstd;
   row_stats(row, n, eps, red, mean, rstd);
   float* o = out + (size_t)blockIdx.x * ldo;
-  for (int i = threadIdx.x; i < n; i += blockDim.x)
-    o[i] = siluf_(fmaf((row[i] - mean) * rstd, g[i], b[i]));
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float y = siluf_(fmaf((row[i] - mean) * rstd, g[i], b[i]));
+    o[i] = y;
+    put_split(so, blockIdx.x, i, y);
+  }
 }
 
 int ln_silu_fwd(const float* pre, int ld, const float* g, const float* b, float eps, int M, int n,
-                float* out, int ldo, cudaStream_t st) {
+                float* out, int ldo, cudaStream_t st, SplitOut so) {
   if (M <= 0) return 0;
-  ln_silu_fwd_kernel<<<M, ROW_THREADS, 0, st>>>(pre, ld, g, b, eps, n, out, ldo);
+  ln_silu_fwd_kernel<<<M, ROW_THREADS, 0, st>>>(pre, ld, g, b, eps, n, out, ldo, so);
   DV3_CHECK_LAUNCH("ln_silu_fwd_kernel");
   return 0;
 }
@@ -59,7 +73,7 @@ __global__ void __launch_bounds__(ROW_THREADS)
 ln_silu_bwd_kernel(const float* __restrict__ pre, int ld, const float* __restrict__ g,
                    const float* __restrict__ b, float eps, const float* __restrict__ d_out,
                    int ldd, int n, float* __restrict__ d_pre, int ldp, float* __restrict__ d_ln,
-                   int ldl) {
+                   int ldl, SplitOut so) {
   __shared__ float red[4 * 32];
   const float* row = pre + (size_t)blockIdx.x * ld;
   const float* dor = d_out + (size_t)blockIdx.x * ldd;
@@ -81,16 +95,18 @@ ln_silu_bwd_kernel(const float* __restrict__ pre, int ld, const float* __restric
     const float xh = (row[i] - mean) * rstd;
     const float v = fmaf(xh, g[i], b[i]);
     const float dx = dor[i] * silu_grad(v) * g[i];
-    d_pre[(size_t)blockIdx.x * ldp + i] = rstd * (dx - m1 - xh * m2);
+    const float dp = rstd * (dx - m1 - xh * m2);
+    d_pre[(size_t)blockIdx.x * ldp + i] = dp;
+    put_split(so, blockIdx.x, i, dp);
   }
 }
 
 int ln_silu_bwd(const float* pre, int ld, const float* g, const float* b, float eps,
                 const float* d_out, int ldd, int M, int n, float* d_pre, int ldp, float* d_ln,
-                int ldl, cudaStream_t st) {
+                int ldl, cudaStream_t st, SplitOut so) {
   if (M <= 0) return 0;
   ln_silu_bwd_kernel<<<M, ROW_THREADS, 0, st>>>(pre, ld, g, b, eps, d_out, ldd, n, d_pre, ldp,
-                                                d_ln, ldl);
+                                                d_ln, ldl, so);
   DV3_CHECK_LAUNCH("ln_silu_bwd_kernel");
   return 0;
 }
@@ -104,7 +120,7 @@ gather_ln_silu_kernel(const int32_t* __restrict__ idx, int ldi, int S, int C,
                       const float* __restrict__ act, int lda, int A, const float* __restrict__ WT,
                       const float* __restrict__ addend, int ldadd, const float* __restrict__ g,
                       const float* __restrict__ b, float eps, int n, float* __restrict__ pre,
-                      int ldp, float* __restrict__ out, int ldo) {
+                      int ldp, float* __restrict__ out, int ldo, SplitOut so) {
   extern __shared__ float sm[];
   float* rowbuf = sm;                                   // n
   float* red = sm + n;                                  // 128
@@ -125,19 +141,22 @@ gather_ln_silu_kernel(const int32_t* __restrict__ idx, int ldi, int S, int C,
   __syncthreads();
   float mean, rstd;
   row_stats(rowbuf, n, eps, red, mean, rstd);
-  for (int i = threadIdx.x; i < n; i += blockDim.x)
-    out[(size_t)r * ldo + i] = siluf_(fmaf((rowbuf[i] - mean) * rstd, g[i], b[i]));
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float y = siluf_(fmaf((rowbuf[i] - mean) * rstd, g[i], b[i]));
+    out[(size_t)r * ldo + i] = y;
+    put_split(so, r, i, y);
+  }
 }
 
 int gather_ln_silu(const int32_t* idx, int ldi, int S, int C, const float* act, int lda, int A,
                    const float* WT, const float* addend, int ldadd, const float* g, const float* b,
                    float eps, int M, int n, float* pre, int ldp, float* out, int ldo,
-                   cudaStream_t st) {
+                   cudaStream_t st, SplitOut so) {
   if (M <= 0) return 0;
   const size_t smem = (size_t)(n + 4 * 32 + S + A) * 4;
   DV3_REQUIRE(smem <= 48 * 1024, DV3_ERR_BAD_SHAPE, "gather_ln_silu: row of %d too wide", n);
   gather_ln_silu_kernel<<<M, ROW_THREADS, smem, st>>>(idx, ldi, S, C, act, lda, A, WT, addend,
-                                                      ldadd, g, b, eps, n, pre, ldp, out, ldo);
+                                                      ldadd, g, b, eps, n, pre, ldp, out, ldo, so);
   DV3_CHECK_LAUNCH("gather_ln_silu_kernel");
   return 0;
 }
@@ -149,7 +168,7 @@ int gather_ln_silu(const int32_t* idx, int ldi, int S, int C, const float* act, 
 __global__ void __launch_bounds__(ROW_THREADS)
 gru_gates_fwd_kernel(const float* __restrict__ g_pre, int ldg, const float* __restrict__ g,
                      const float* __restrict__ b, float eps, const float* __restrict__ h, int ldh,
-                     int D, float* __restrict__ h_new, int ldn) {
+                     int D, float* __restrict__ h_new, int ldn, SplitOut so) {
   __shared__ float red[4 * 32];
   const float* row = g_pre + (size_t)blockIdx.x * ldg;
   float mean, rstd;
@@ -162,14 +181,18 @@ gru_gates_fwd_kernel(const float* __restrict__ g_pre, int ldg, const float* __re
     const float c = tanhf(r * pc);
     const float u = sigmoidf_(pu - 1.f);
     const float hp = h[(size_t)blockIdx.x * ldh + j];
-    h_new[(size_t)blockIdx.x * ldn + j] = u * c + (1.f - u) * hp;
+    const float hn = u * c + (1.f - u) * hp;
+    h_new[(size_t)blockIdx.x * ldn + j] = hn;
+    put_split(so, blockIdx.x, j, hn);
   }
 }
 
 int gru_gates_fwd(const float* g_pre, int ldg, const float* g, const float* b, float eps,
-                  const float* h, int ldh, int M, int D, float* h_new, int ldn, cudaStream_t st) {
+                  const float* h, int ldh, int M, int D, float* h_new, int ldn, cudaStream_t st,
+                  SplitOut so) {
   if (M <= 0) return 0;
-  gru_gates_fwd_kernel<<<M, ROW_THREADS, 0, st>>>(g_pre, ldg, g, b, eps, h, ldh, D, h_new, ldn);
+  gru_gates_fwd_kernel<<<M, ROW_THREADS, 0, st>>>(g_pre, ldg, g, b, eps, h, ldh, D, h_new, ldn,
+                                                  so);
   DV3_CHECK_LAUNCH("gru_gates_fwd_kernel");
   return 0;
 }
@@ -183,7 +206,8 @@ __global__ void __launch_bounds__(ROW_THREADS)
 gru_gates_bwd_kernel(const float* __restrict__ g_pre, int ldg, const float* __restrict__ g,
                      const float* __restrict__ b, float eps, const float* __restrict__ h, int ldh,
                      DhIn dh, int D, float* __restrict__ d_g_pre, int ldp,
-                     float* __restrict__ d_g_ln, int ldl, float* __restrict__ dh_direct, int ldd) {
+                     float* __restrict__ d_g_ln, int ldl, float* __restrict__ dh_direct, int ldd,
+                     SplitOut so) {
   extern __shared__ float sm[];
   float* dparts = sm;             // 3D: gradient w.r.t. the LN affine output
   float* red = sm + 3 * D;        // 128
@@ -224,14 +248,16 @@ gru_gates_bwd_kernel(const float* __restrict__ g_pre, int ldg, const float* __re
   const float m1 = acc[0] / (float)(3 * D), m2 = acc[1] / (float)(3 * D);
   for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) {
     const float xh = (row[i] - mean) * rstd;
-    d_g_pre[(size_t)r * ldp + i] = rstd * (dparts[i] * g[i] - m1 - xh * m2);
+    const float dp = rstd * (dparts[i] * g[i] - m1 - xh * m2);
+    d_g_pre[(size_t)r * ldp + i] = dp;
+    put_split(so, r, i, dp);
   }
 }
 
 int gru_gates_bwd(const float* g_pre, int ldg, const float* g, const float* b, float eps,
                   const float* h, int ldh, const float* const dh_in[4], const int ld_in[4], int M,
                   int D, float* d_g_pre, int ldp, float* d_g_ln, int ldl, float* dh_direct,
-                  int ldd, cudaStream_t st) {
+                  int ldd, cudaStream_t st, SplitOut so) {
   if (M <= 0) return 0;
   DhIn dh;
   for (int q = 0; q < 4; ++q) { dh.p[q] = dh_in[q]; dh.ld[q] = ld_in[q]; }
@@ -244,7 +270,7 @@ int gru_gates_bwd(const float* g_pre, int ldg, const float* g, const float* b, f
   }
   DV3_REQUIRE(smem <= 200 * 1024, DV3_ERR_BAD_SHAPE, "gru_gates_bwd: deter %d too wide", D);
   gru_gates_bwd_kernel<<<M, ROW_THREADS, smem, st>>>(g_pre, ldg, g, b, eps, h, ldh, dh, D, d_g_pre,
-                                                     ldp, d_g_ln, ldl, dh_direct, ldd);
+                                                     ldp, d_g_ln, ldl, dh_direct, ldd, so);
   DV3_CHECK_LAUNCH("gru_gates_bwd_kernel");
   return 0;
 }
@@ -299,7 +325,7 @@ __global__ void __launch_bounds__(256)
 onehot_st_bwd_kernel(const float* __restrict__ logits, int ldl, const float* __restrict__ g1,
                      int ldg1, const float* __restrict__ g2, int ldg2,
                      const float* __restrict__ ext, int lde, float unimix, int M, int S, int C,
-                     float* __restrict__ d_logits, int ldd) {
+                     float* __restrict__ d_logits, int ldd, SplitOut so) {
   const int lane = threadIdx.x & 31;
   const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (w >= (long long)M * S) return;
@@ -320,18 +346,19 @@ onehot_st_bwd_kernel(const float* __restrict__ logits, int ldl, const float* __r
   if (valid) {
     if (ext) d += ext[(size_t)r * lde + col];
     d_logits[(size_t)r * ldd + col] = d;
+    put_split(so, r, col, d);
   }
 }
 
 int onehot_st_bwd(const float* logits, int ldl, const float* g1, int ldg1, const float* g2,
                   int ldg2, const float* ext, int lde, float unimix, int M, int S, int C,
-                  float* d_logits, int ldd, cudaStream_t st) {
+                  float* d_logits, int ldd, cudaStream_t st, SplitOut so) {
   if (M <= 0) return 0;
   DV3_REQUIRE(C >= 1 && C <= 32, DV3_ERR_BAD_SHAPE, "onehot_st_bwd: classes=%d (max 32)", C);
   const long long warps = (long long)M * S;
   const int grid = (int)((warps + 7) / 8);
   onehot_st_bwd_kernel<<<grid, 256, 0, st>>>(logits, ldl, g1, ldg1, g2, ldg2, ext, lde, unimix, M,
-                                             S, C, d_logits, ldd);
+                                             S, C, d_logits, ldd, so);
   DV3_CHECK_LAUNCH("onehot_st_bwd_kernel");
   return 0;
 }
@@ -518,6 +545,25 @@ extern "C" int dv3_ln_silu_fwd(const float* pre, int32_t ld, const float* g, con
   return ln_silu_fwd(pre, ld, g, b, eps, M, n, out, ldo, ST(stream));
 }
 
+extern "C" int dv3_ln_silu_fwd_split(const float* pre, int32_t ld, const float* g, const float* b,
+                                     float eps, int32_t M, int32_t n, float* out, int32_t ldo,
+                                     float* hi, float* lo, int32_t lds, void* stream) {
+  DV3_REQUIRE(pre && g && b && out && hi && lo && lds >= n, DV3_ERR_NULL,
+              "ln_silu_fwd_split: null pointer / short plane pitch");
+  SplitOut so;
+  so.hi = hi; so.lo = lo; so.ld = lds;
+  return ln_silu_fwd(pre, ld, g, b, eps, M, n, out, ldo, ST(stream), so);
+}
+extern "C" int dv3_ln_silu_bwd_split(const float* pre, int32_t ld, const float* g, const float* b,
+                                     float eps, const float* d_out, int32_t ldd, int32_t M,
+                                     int32_t n, float* d_pre, float* d_ln, int32_t ldp, float* hi,
+                                     float* lo, int32_t lds, void* stream) {
+  DV3_REQUIRE(pre && g && b && d_out && d_pre && hi && lo && lds >= n, DV3_ERR_NULL,
+              "ln_silu_bwd_split: null pointer / short plane pitch");
+  SplitOut so;
+  so.hi = hi; so.lo = lo; so.ld = lds;
+  return ln_silu_bwd(pre, ld, g, b, eps, d_out, ldd, M, n, d_pre, ldp, d_ln, ldp, ST(stream), so);
+}
 extern "C" int dv3_ln_silu_bwd(const float* pre, int32_t ld, const float* g, const float* b,
                                float eps, const float* d_out, int32_t ldd, int32_t M, int32_t n,
                                float* d_pre, float* d_ln, int32_t ldp, void* stream) {

@@ -168,22 +168,38 @@ def kl_balance(post_logit, prior_logit, free, dyn_scale, rep_scale, unimix):
 # --------------------------------------------------------------------------------------
 # building blocks (used by tests and by the bulk actor backward)
 # --------------------------------------------------------------------------------------
-def ln_silu_fwd(pre, g, b, eps=LN_EPS):
+def ln_silu_fwd(pre, g, b, eps=LN_EPS, with_split=False):
+    """SiLU(LayerNorm(pre)); with_split also returns the tf32 hi/lo planes of the result, written
+    by the same kernel (the A operand of the next layer's GEMM)."""
     M, n = pre.shape
     out = torch.empty_like(pre)
+    if with_split and n % 4 == 0:
+        hi, lo = torch.empty_like(pre), torch.empty_like(pre)
+        L.check(L.lib().dv3_ln_silu_fwd_split(L.fptr(pre), n, L.fptr(g), L.fptr(b), eps, M, n,
+                                              L.fptr(out), n, L.fptr(hi), L.fptr(lo), n,
+                                              L.stream_ptr()), "ln_silu_fwd_split")
+        return out, Split(hi, lo, M, n)
     L.check(L.lib().dv3_ln_silu_fwd(L.fptr(pre), n, L.fptr(g), L.fptr(b), eps, M, n, L.fptr(out),
                                     n, L.stream_ptr()), "ln_silu_fwd")
-    return out
+    return (out, split(out)) if with_split else out
 
 
-def ln_silu_bwd(pre, g, b, d_out, eps=LN_EPS):
-    """-> (d_pre, d_ln): gradient w.r.t. the Linear output and w.r.t. the LN affine output."""
+def ln_silu_bwd(pre, g, b, d_out, eps=LN_EPS, with_split=False):
+    """-> (d_pre, d_ln): gradient w.r.t. the Linear output and w.r.t. the LN affine output
+    (+ the Split of d_pre when with_split)."""
     M, n = pre.shape
     d_pre, d_ln = torch.empty_like(pre), torch.empty_like(pre)
+    if with_split and n % 4 == 0:
+        hi, lo = torch.empty_like(pre), torch.empty_like(pre)
+        L.check(L.lib().dv3_ln_silu_bwd_split(L.fptr(pre), n, L.fptr(g), L.fptr(b), eps,
+                                              L.fptr(d_out), n, M, n, L.fptr(d_pre), L.fptr(d_ln),
+                                              n, L.fptr(hi), L.fptr(lo), n, L.stream_ptr()),
+                "ln_silu_bwd_split")
+        return d_pre, d_ln, Split(hi, lo, M, n)
     L.check(L.lib().dv3_ln_silu_bwd(L.fptr(pre), n, L.fptr(g), L.fptr(b), eps, L.fptr(d_out), n,
                                     M, n, L.fptr(d_pre), L.fptr(d_ln), n, L.stream_ptr()),
             "ln_silu_bwd")
-    return d_pre, d_ln
+    return (d_pre, d_ln, split(d_pre)) if with_split else (d_pre, d_ln)
 
 
 def linear_fwd(a1, w1, a2=None, w2=None, bias=None, addend=None):
@@ -337,6 +353,34 @@ def linear_tc2(a1, w, a2=None, bias=None, addend=None, out=None, accumulate=Fals
     return out
 
 
+def _tag(t):
+    return (t._version, t.data_ptr(), tuple(t.shape))
+
+
+def attach_split(t, sp):
+    """Remember the hi/lo planes of activation tensor ``t`` on the tensor object (valid while the
+    tensor is not modified in place: version counter + storage pointer are checked)."""
+    t._dv3_split = (_tag(t), sp)
+    return t
+
+
+def split_of(x2d, src=None):
+    """Split of a 2-D activation; reuses planes attached to ``src`` (the tensor the caller was
+    handed, possibly a higher-rank view of the same memory) or to ``x2d`` itself."""
+    for t in (src, x2d):
+        hit = getattr(t, "_dv3_split", None) if t is not None else None
+        if hit is not None and hit[0] == _tag(t) and hit[1].rows == x2d.shape[0] \
+                and hit[1].cols == x2d.shape[1]:
+            return hit[1]
+    sp = split(x2d)
+    if src is not None and src.is_contiguous():
+        attach_split(src, sp)
+    return sp
+
+
+_LAST_OUT_SPLIT = [None]
+
+
 class _DenseLnSilu(torch.autograd.Function):
     """SiLU(LayerNorm(x W^T)) for x [M,K], W [U,K]: the Linear(no bias)+LN(eps 1e-3)+SiLU block of
     the reference MLPs (networks.py:623-632).  All three contractions (y, dx, dW) run on the
@@ -344,10 +388,11 @@ class _DenseLnSilu(torch.autograd.Function):
     kernels."""
 
     @staticmethod
-    def forward(ctx, x, W, g, b):
-        xs, Ws = split(_f32(x)), split_param(W)
+    def forward(ctx, x, W, g, b, xs):
+        Ws = split_param(W)
         pre = gemm_tc(xs, Ws)
-        out = ln_silu_fwd(pre, _c(g.detach()), _c(b.detach()))
+        out, osp = ln_silu_fwd(pre, _c(g.detach()), _c(b.detach()), with_split=True)
+        _LAST_OUT_SPLIT[0] = osp
         ctx.save_for_backward(g.detach(), b.detach(), pre, xs.hi, xs.lo, Ws.hi, Ws.lo)
         ctx.shapes = (xs.rows, xs.cols, Ws.rows, Ws.cols)
         return out
@@ -357,24 +402,23 @@ class _DenseLnSilu(torch.autograd.Function):
         g, b, pre, xh, xl, Wh, Wl = ctx.saved_tensors
         M, Kd, U, _ = ctx.shapes
         xs, Ws = Split(xh, xl, M, Kd), Split(Wh, Wl, U, Kd)
-        d_pre, d_ln = ln_silu_bwd(pre, _c(g), _c(b), _f32(d_out))
+        d_pre, d_ln, ds = ln_silu_bwd(pre, _c(g), _c(b), _f32(d_out), with_split=True)
         dx = dW = dg = db = None
-        ds = split(d_pre)
         if ctx.needs_input_grad[0]:
             dx = gemm_tc(ds, Ws, b_t=True)                    # dy W
         if ctx.needs_input_grad[1]:
             dW = gemm_tc(ds, xs, a_t=True, b_t=True, split_k=True)   # dy^T x
         if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
             dg, db = _ln_grads(pre, d_ln)
-        return dx, dW, dg, db
+        return dx, dW, dg, db, None
 
 
 class _LinearBias(torch.autograd.Function):
     """x W^T + bias (the MLP output heads, networks.py:640-655) on the tensor-core GEMM."""
 
     @staticmethod
-    def forward(ctx, x, W, bias):
-        xs, Ws = split(_f32(x)), split_param(W)
+    def forward(ctx, x, W, bias, xs):
+        Ws = split_param(W)
         ctx.save_for_backward(xs.hi, xs.lo, Ws.hi, Ws.lo)
         ctx.shapes = (xs.rows, xs.cols, Ws.rows, Ws.cols)
         return gemm_tc(xs, Ws, bias=None if bias is None else _c(bias.detach()))
@@ -393,18 +437,26 @@ class _LinearBias(torch.autograd.Function):
             dW = gemm_tc(ds, xs, a_t=True, b_t=True, split_k=True)
         if ctx.needs_input_grad[2]:
             db = d_out.sum(0)
-        return dx, dW, db
+        return dx, dW, db, None
 
 
 def dense_ln_silu(x, W, g, b):
+    """Linear(no bias) + LayerNorm + SiLU over the last axis.  The hi/lo planes of the result are
+    attached to the returned tensor, so the next layer's GEMM starts without a split pass; the
+    planes of ``x`` are looked up on ``x`` the same way (several heads reading one feature tensor
+    split it once)."""
     lead = x.shape[:-1]
-    out = _DenseLnSilu.apply(x.reshape(-1, x.shape[-1]), W, g, b)
-    return out.reshape(tuple(lead) + (W.shape[0],))
+    x2 = _f32(x).reshape(-1, x.shape[-1])
+    out = _DenseLnSilu.apply(x2, W, g, b, split_of(x2, x))
+    osp, _LAST_OUT_SPLIT[0] = _LAST_OUT_SPLIT[0], None
+    out = out.reshape(tuple(lead) + (W.shape[0],))
+    return attach_split(out, osp) if osp is not None else out
 
 
 def linear_bias(x, W, bias):
     lead = x.shape[:-1]
-    out = _LinearBias.apply(x.reshape(-1, x.shape[-1]), W, bias)
+    x2 = _f32(x).reshape(-1, x.shape[-1])
+    out = _LinearBias.apply(x2, W, bias, split_of(x2, x))
     return out.reshape(tuple(lead) + (W.shape[0],))
 
 
@@ -739,9 +791,8 @@ class _Imagine(torch.autograd.Function):
             d_act = d_act + ds @ actor_params[3 * Lr + 2]
         for i in range(Lr - 1, -1, -1):
             pre = a_pre[i].reshape(HN, U)
-            d_pre, d_ln = ln_silu_bwd(pre, actor_params[3 * i + 1], actor_params[3 * i + 2],
-                                      _c(d_act))
-            dps = split(d_pre)
+            d_pre, d_ln, dps = ln_silu_bwd(pre, actor_params[3 * i + 1], actor_params[3 * i + 2],
+                                           _c(d_act), with_split=True)
             inp = feat.reshape(HN, -1) if i == 0 else a_act[i - 1].reshape(HN, U)
             ga[3 * i] = dw(dps, inp)
             ga[3 * i + 1], ga[3 * i + 2] = _ln_grads(pre, d_ln)

@@ -382,6 +382,16 @@ int dv3_ln_silu_fwd(const float* pre, int32_t ld, const float* g, const float* b
 int dv3_ln_silu_bwd(const float* pre, int32_t ld, const float* g, const float* b, float eps,
                     const float* d_out, int32_t ldd, int32_t M, int32_t n, float* d_pre,
                     float* d_ln, int32_t ldp, void* stream);
+/* The same two kernels also writing the tf32 hi/lo planes (row pitch lds >= n, n % 4 == 0 keeps
+ * pad columns out of play) of their output -- the A operand of the dv3_gemm_tc that consumes it,
+ * so no separate dv3_split_tf32 pass is needed. */
+int dv3_ln_silu_fwd_split(const float* pre, int32_t ld, const float* g, const float* b, float eps,
+                          int32_t M, int32_t n, float* out, int32_t ldo, float* hi, float* lo,
+                          int32_t lds, void* stream);
+int dv3_ln_silu_bwd_split(const float* pre, int32_t ld, const float* g, const float* b, float eps,
+                          const float* d_out, int32_t ldd, int32_t M, int32_t n, float* d_pre,
+                          float* d_ln, int32_t ldp, float* hi, float* lo, int32_t lds,
+                          void* stream);
 /* LayerNorm affine-parameter gradients over all M rows: dg[j] = sum_r d_ln[r,j]*xhat[r,j],
  * db[j] = sum_r d_ln[r,j]; xhat is recomputed from the saved pre-LN rows.  n <= 2048. */
 int dv3_ln_param_grads(const float* pre, int32_t ld, const float* d_ln, int32_t ldl, float eps,

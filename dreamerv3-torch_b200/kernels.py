@@ -235,6 +235,10 @@ class Split:
     def ld(self):
         return self.hi.shape[1]
 
+    def prefix(self, rows):
+        """The first ``rows`` rows (a contiguous view of the same planes)."""
+        return Split(self.hi[:rows], self.lo[:rows], rows, self.cols)
+
     def operand(self, transposed):
         o = L.TcOperand()
         o.hi, o.lo, o.ld, o.mn_major = _raw(self.hi), _raw(self.lo), self.ld, int(transposed)
@@ -362,6 +366,11 @@ def attach_split(t, sp):
     tensor is not modified in place: version counter + storage pointer are checked)."""
     t._dv3_split = (_tag(t), sp)
     return t
+
+
+def split_of_attached(t):
+    hit = getattr(t, "_dv3_split", None)
+    return hit[1] if hit is not None and hit[0] == _tag(t) else None
 
 
 def split_of(x2d, src=None):

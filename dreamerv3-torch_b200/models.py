@@ -209,7 +209,17 @@ class ImagBehavior(nn.Module):
         SC = S * Cc
         states = dict(stoch=feat[..., :SC].reshape(horizon, N, S, Cc), deter=feat[..., SC:],
                       logit=logit)
-        return feat.detach(), states, action
+        # feat rows are [one-hot stoch | deter]: get_feat(states) is feat itself, and every head
+        # that reads the rollout features (reward, cont, critic, slow critic, actor) shares one
+        # tf32 split of it
+        for v in (states["stoch"], states["deter"]):
+            v._dv3_feat, v._dv3_feat_version = feat, feat._version
+        imag_feat = feat.detach()
+        if horizon * N >= 64:
+            sp = K.split(imag_feat.reshape(horizon * N, -1))
+            K.attach_split(feat, sp)
+            K.attach_split(imag_feat, sp)
+        return imag_feat, states, action
 
     # ---- training step -------------------------------------------------------------------
     def losses(self, start, objective, noise=None):
@@ -230,10 +240,14 @@ class ImagBehavior(nn.Module):
             actor_loss = torch.mean(actor_loss)
             metrics.update(mets)
         with tools.RequiresGrad(self.value):
-            value = self.value(imag_feat[:-1].detach())
+            feat_m1 = imag_feat[:-1].detach()
+            sp = K.split_of_attached(imag_feat)
+            if sp is not None:
+                K.attach_split(feat_m1, sp.prefix(feat_m1.shape[0] * feat_m1.shape[1]))
+            value = self.value(feat_m1)
             value_loss = -value.log_prob(target.detach())
             if cfg.critic["slow_target"]:
-                slow = self._slow_value(imag_feat[:-1].detach())
+                slow = self._slow_value(feat_m1)
                 value_loss = value_loss - value.log_prob(slow.mode().detach())
             value_loss = torch.mean(weights[:-1] * value_loss[:, :, None])
         metrics.update(tools.tensorstats(value.mode(), "value"))

@@ -159,7 +159,14 @@ class RSSM(nn.Module):
         return {k: v[:, 0] for k, v in out.items()}
 
     def get_feat(self, state):
+        """cat(flat(stoch), deter) (reference networks.py:154-159).  The imagination kernel already
+        lays its states out as [one-hot stoch | deter] rows of one buffer; when ``stoch`` and
+        ``deter`` are the two column ranges of that buffer it is returned as is (no copy)."""
         s = state["stoch"]
+        base = getattr(s, "_dv3_feat", None)
+        if base is not None and getattr(state["deter"], "_dv3_feat", None) is base \
+                and base._version == s._dv3_feat_version:
+            return base
         return torch.cat([s.reshape(list(s.shape[:-2]) + [self._stoch * self._discrete]),
                           state["deter"]], -1)
 

@@ -219,6 +219,18 @@ int tc_gemm_ops(const TcOperand& A1, int K1, const TcOperand* A2, int K2, const 
 int observe_fwd_persistent(const dv3_rssm_dims* d, const dv3_rssm_params* p,
                            const dv3_observe_io* io, const float* WinT, const float* pre_e,
                            unsigned* bar, cudaStream_t st, bool* used);
+// buffers dv3_observe_bwd shares with its persistent recurrence kernel
+// (dv3_observe_persistent_bwd.cu); the transposed weights are the stepwise path's
+struct ObsBwdShared {
+  const float *dh_prior, *WosT, *WobsT, *WgruT, *WinT;
+  float *ds_rec, *dh_rec, *dinit_s, *dinit_h;      // [B,SC], [B,D], [B,SC], [B,D]; zeroed by caller
+  float *d_z, *dh_z, *dhdir, *dxh;                 // scratch [B,Hd], [B,D], [B,D], [B,Hd+D]
+  unsigned* bar;
+};
+int observe_bwd_persistent(const dv3_rssm_dims* d, const dv3_rssm_params* p,
+                           const dv3_observe_bwd_io* io, const ObsBwdShared& w, cudaStream_t st,
+                           bool* used);
+unsigned long long* po_timing_buffer();   // debug stamps (DV3_OBSERVE_TIMING=1 fwd, =2 bwd)
 // rows below this go to the CUDA-core kernels (a 128-row MMA tile would be mostly padding)
 constexpr int TC_MIN_ROWS = 64;
 

@@ -215,6 +215,7 @@ struct ObsBwdWs {
   float *ds_tmp, *ds_rec, *dh_rec; // [B, SC], [B, SC], [B, D]
   float *dinit_s, *dinit_h;        // [B, SC], [B, D] per-row accumulators (deterministic)
   float* ascr;
+  unsigned* bar;                   // grid-barrier word of the persistent kernel
   LinW ims, out, obs_e;            // bulk products over the transposed weights
 };
 
@@ -238,6 +239,7 @@ static void carve_bwd(Arena& a, const dv3_rssm_dims* d, int B, int T, ObsBwdWs& 
   w.dh_rec = a.take<float>((size_t)B * D);
   w.dinit_s = a.take<float>((size_t)B * SC);
   w.dinit_h = a.take<float>((size_t)B * D);
+  w.bar = a.take<unsigned>(64);
   const bool tc = B * T >= TC_MIN_ROWS;
   w.ims.reserve(a, tc, (int)Hd, (int)SC);     // d_y      = d_prior_logit @ W_ims   (K = SC)
   w.out.reserve(a, tc, (int)D, (int)Hd);      // dh_prior = d_y_pre @ W_out         (K = Hd)
@@ -338,8 +340,15 @@ extern "C" int dv3_observe_bwd(const dv3_rssm_dims* d, const dv3_rssm_params* p,
   DV3_TRY(fill_zero(w.dinit_h, (size_t)B * D * 4, st));
   DV3_TRY(fill_zero(w.dxh_add, (size_t)B * (Hd + D) * 4, st));
 
-  // ---- reverse time ----
-  for (int t = T - 1; t >= 0; --t) {
+  // ---- reverse time: one persistent kernel when the shapes allow it ----
+  ObsBwdShared sh{};
+  sh.dh_prior = w.dh_prior; sh.WosT = w.WosT; sh.WobsT = w.WobsT; sh.WgruT = w.WgruT;
+  sh.WinT = w.WinT; sh.ds_rec = w.ds_rec; sh.dh_rec = w.dh_rec; sh.dinit_s = w.dinit_s;
+  sh.dinit_h = w.dinit_h; sh.d_z = w.d_z; sh.dh_z = w.dh_z; sh.dhdir = w.dxh_add; sh.dxh = w.dxh;
+  sh.bar = w.bar;
+  bool persistent = false;
+  DV3_TRY(observe_bwd_persistent(d, p, io, sh, st, &persistent));
+  for (int t = persistent ? -1 : T - 1; t >= 0; --t) {
     const float* gps = io->g_post_stoch ? io->g_post_stoch + (size_t)t * SC : nullptr;
     const float* gpl = io->g_post_logit ? io->g_post_logit + (size_t)t * SC : nullptr;
     DV3_TRY(onehot_st_bwd(io->post_logit + (size_t)t * SC, T * SC, gps, T * SC, w.ds_rec, SC, gpl,

@@ -115,6 +115,47 @@ def cpu_oracle_rate(suite, steps, warmup, seed=0, device="cpu"):
                 steps=len(times))
 
 
+def large_imagination(pkg, device, iters=3):
+    """BASELINE config 4: 1024 start states x H=15 with the large model (dyn_deter 4096,
+    dyn_hidden / units 1024, 5-layer one-hot actor, 17 actions), ``ImagBehavior._imagine`` forward:
+    imagined states/s and the tcgen05 GEMM's rate (CUDA events around every GEMM launch)."""
+    import torch
+    cfgs, lib = pkg.configs, pkg._lib.lib()
+    torch.manual_seed(0)
+    cfg = cfgs.make_config("crafter", device=device, device_metrics=True,
+                           encoder=dict(mlp_keys=".*", cnn_keys="$^"),
+                           decoder=dict(mlp_keys=".*", cnn_keys="$^"))
+    wm = pkg.models.WorldModel(cfgs.ObsSpace(cfgs.PROPRIO_SHAPES), None, 0, cfg)
+    beh = pkg.models.ImagBehavior(cfg, wm)
+    B, T, S, C, D, H = 16, 64, cfg.dyn_stoch, cfg.dyn_discrete, cfg.dyn_deter, cfg.imag_horizon
+    g = torch.Generator(device=device).manual_seed(1)
+    idx = torch.randint(0, C, (B, T, S), device=device, generator=g)
+    start = dict(stoch=torch.nn.functional.one_hot(idx, C).float(),
+                 deter=torch.tanh(torch.randn(B, T, D, device=device, generator=g)),
+                 logit=torch.randn(B, T, S, C, device=device, generator=g))
+    with torch.no_grad():
+        for _ in range(2):
+            beh._imagine(start, beh.actor, H)
+        torch.cuda.synchronize()
+        lib.dv3_prof_enable(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            beh._imagine(start, beh.actor, H)
+        e1.record()
+        torch.cuda.synchronize()
+        lib.dv3_prof_enable(0)
+    ms = e0.elapsed_time(e1) / iters
+    pm, pf, pl = (ctypes.c_double * 2)(), (ctypes.c_double * 2)(), (ctypes.c_longlong * 2)()
+    lib.dv3_prof_read(pm, pf, pl)
+    tf = pf[1] / (pm[1] / 1e3) / 1e12 if pm[1] > 0 else 0.0
+    return {"workload": "1024 starts x H=15, dyn_deter 4096, dyn_hidden/units 1024, 5-layer one-hot actor",
+            "imagine_fwd_ms": ms, "imagined_states_per_s": B * T * H / (ms / 1e3),
+            "gemm_ms": pm[1] / iters, "gemm_share": pm[1] / iters / ms,
+            "gemm_fp32_tflops": tf, "gemm_tf32_mma_tflops": 3 * tf,
+            "tf32_peak_tflops_nominal": 1100.0, "tensor_pipe_frac_of_nominal_tf32": 3 * tf / 1100.0}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -342,6 +383,13 @@ def run_ours(args):
                             "achieved_gflops": (skinny_fl / (skinny_ms / 1e3) / 1e9) if skinny_ms > 0 else 0.0},
         },
     }
+    if world == 1:
+        del graph
+        torch.cuda.empty_cache()
+        try:
+            line["large_imagination"] = large_imagination(pkg, device)
+        except Exception as e:      # informational only
+            line["large_imagination"] = {"error": str(e)[:160]}
     if world == 1 and not args.no_cpu_baseline:
         r = cpu_oracle_rate(args.suite, steps=3, warmup=1)
         line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",

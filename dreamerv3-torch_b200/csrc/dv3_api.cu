@@ -1,6 +1,7 @@
 // Library-level entry points: version, thread-local error text, device probe, and the
 // single-step wrappers (obs_step / img_step) over the sequence kernels.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <atomic>
 #include <mutex>
 #include <vector>
@@ -20,6 +21,15 @@ void set_error(const char* fmt, ...) {
 int cuda_fail(cudaError_t e, const char* what) {
   set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
   return DV3_ERR_CUDA;
+}
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("DV3_PDL");
+    on = (e && e[0] == '1') ? 1 : 0;   // measured: 16.76 ms/step with it, 16.33 without -> off
+  }
+  return on != 0;
 }
 
 // ---- launch counter + optional GEMM timing --------------------------------------------

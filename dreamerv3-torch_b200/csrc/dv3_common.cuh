@@ -49,6 +49,36 @@ int cuda_fail(cudaError_t e, const char* what);
     if (_rc != 0) return _rc;    \
   } while (0)
 
+// ---- programmatic dependent launch ---------------------------------------------------------
+// Kernels of the long dependent chains (imagination steps, MLP layers) are launched with the
+// programmatic-stream-serialization attribute: the next kernel's CTAs become resident and run
+// their prologue (barrier init, TMEM allocation, tensor-map fetch) while the previous kernel
+// drains; pdl_wait() then blocks until the previous grid has completed and its memory is
+// visible.  Every kernel launched through launch_pdl() must call pdl_wait() before its first
+// global-memory access.  Off by default (DV3_PDL=1 turns it on): on the dmc_proprio step the early
+// residency of 200 KB GEMM CTAs cost more than the hidden prologues saved (16.76 vs 16.33 ms).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // ---- device helpers ----------------------------------------------------------------------
 constexpr int WARP = 32;
 constexpr unsigned FULL = 0xffffffffu;

@@ -63,6 +63,8 @@ actor_head_kernel(const float* __restrict__ top, int ldt, const float* __restric
                   const float* __restrict__ b_std, const float* __restrict__ eps, float min_std,
                   float max_std, int N, int U, int A, float* __restrict__ mean_raw,
                   float* __restrict__ std_raw, float* __restrict__ action) {
+  pdl_wait();
+  pdl_launch_dependents();
   extern __shared__ __align__(16) float ah_smem[];
   const int nh = w_std ? 2 : 1;
   float* ws = ah_smem;                         // [nh*A][U]
@@ -281,9 +283,10 @@ extern "C" int dv3_imagine_fwd(const dv3_rssm_dims* d, const dv3_rssm_params* p,
         const int nw = AH_THREADS / 32;
         int grid = (N + nw - 1) / nw;
         if (grid > 148) grid = 148;
-        actor_head_kernel<<<grid, AH_THREADS, ah_smem, st>>>(
-            top, U, a->w_mean, a->b_mean, a->dist == 0 ? a->w_std : nullptr, a->b_std,
-            io->act_noise + (size_t)k * N * A, a->min_std, a->max_std, N, U, A, mraw, sraw, actk);
+        DV3_CHECK_CUDA(launch_pdl(actor_head_kernel, dim3(grid), dim3(AH_THREADS), ah_smem, st, top, U,
+                                  a->w_mean, a->b_mean, a->dist == 0 ? a->w_std : nullptr, a->b_std,
+                                  io->act_noise + (size_t)k * N * A, a->min_std, a->max_std, N, U, A,
+                                  mraw, sraw, actk));
         DV3_CHECK_LAUNCH("actor_head_kernel");
       } else {
         DV3_TRY(linear1(top, U, a->w_mean, U, U, a->b_mean, mraw, A, N, A, 0, st));

@@ -47,6 +47,8 @@ __global__ void __launch_bounds__(ROW_THREADS)
 ln_silu_fwd_kernel(const float* __restrict__ pre, int ld, const float* __restrict__ g,
                    const float* __restrict__ b, float eps, int n, float* __restrict__ out,
                    int ldo, SplitOut so) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ float red[4 * 32];
   const float* row = pre + (size_t)blockIdx.x * ld;
   float mean, rstd;
@@ -62,7 +64,8 @@ ln_silu_fwd_kernel(const float* __restrict__ pre, int ld, const float* __restric
 int ln_silu_fwd(const float* pre, int ld, const float* g, const float* b, float eps, int M, int n,
                 float* out, int ldo, cudaStream_t st, SplitOut so) {
   if (M <= 0) return 0;
-  ln_silu_fwd_kernel<<<M, ROW_THREADS, 0, st>>>(pre, ld, g, b, eps, n, out, ldo, so);
+  DV3_CHECK_CUDA(launch_pdl(ln_silu_fwd_kernel, dim3(M), dim3(ROW_THREADS), 0, st, pre, ld, g, b, eps,
+                            n, out, ldo, so));
   DV3_CHECK_LAUNCH("ln_silu_fwd_kernel");
   return 0;
 }
@@ -74,6 +77,8 @@ ln_silu_bwd_kernel(const float* __restrict__ pre, int ld, const float* __restric
                    const float* __restrict__ b, float eps, const float* __restrict__ d_out,
                    int ldd, int n, float* __restrict__ d_pre, int ldp, float* __restrict__ d_ln,
                    int ldl, SplitOut so) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ float red[4 * 32];
   const float* row = pre + (size_t)blockIdx.x * ld;
   const float* dor = d_out + (size_t)blockIdx.x * ldd;
@@ -105,8 +110,8 @@ int ln_silu_bwd(const float* pre, int ld, const float* g, const float* b, float 
                 const float* d_out, int ldd, int M, int n, float* d_pre, int ldp, float* d_ln,
                 int ldl, cudaStream_t st, SplitOut so) {
   if (M <= 0) return 0;
-  ln_silu_bwd_kernel<<<M, ROW_THREADS, 0, st>>>(pre, ld, g, b, eps, d_out, ldd, n, d_pre, ldp,
-                                                d_ln, ldl, so);
+  DV3_CHECK_CUDA(launch_pdl(ln_silu_bwd_kernel, dim3(M), dim3(ROW_THREADS), 0, st, pre, ld, g, b, eps,
+                            d_out, ldd, n, d_pre, ldp, d_ln, ldl, so));
   DV3_CHECK_LAUNCH("ln_silu_bwd_kernel");
   return 0;
 }
@@ -121,6 +126,8 @@ gather_ln_silu_kernel(const int32_t* __restrict__ idx, int ldi, int S, int C,
                       const float* __restrict__ addend, int ldadd, const float* __restrict__ g,
                       const float* __restrict__ b, float eps, int n, float* __restrict__ pre,
                       int ldp, float* __restrict__ out, int ldo, SplitOut so) {
+  pdl_wait();
+  pdl_launch_dependents();
   extern __shared__ float sm[];
   float* rowbuf = sm;                                   // n
   float* red = sm + n;                                  // 128
@@ -155,8 +162,9 @@ int gather_ln_silu(const int32_t* idx, int ldi, int S, int C, const float* act, 
   if (M <= 0) return 0;
   const size_t smem = (size_t)(n + 4 * 32 + S + A) * 4;
   DV3_REQUIRE(smem <= 48 * 1024, DV3_ERR_BAD_SHAPE, "gather_ln_silu: row of %d too wide", n);
-  gather_ln_silu_kernel<<<M, ROW_THREADS, smem, st>>>(idx, ldi, S, C, act, lda, A, WT, addend,
-                                                      ldadd, g, b, eps, n, pre, ldp, out, ldo, so);
+  DV3_CHECK_CUDA(launch_pdl(gather_ln_silu_kernel, dim3(M), dim3(ROW_THREADS), smem, st, idx, ldi, S,
+                            C, act, lda, A, WT, addend, ldadd, g, b, eps, n, pre, ldp, out, ldo,
+                            so));
   DV3_CHECK_LAUNCH("gather_ln_silu_kernel");
   return 0;
 }
@@ -169,6 +177,8 @@ __global__ void __launch_bounds__(ROW_THREADS)
 gru_gates_fwd_kernel(const float* __restrict__ g_pre, int ldg, const float* __restrict__ g,
                      const float* __restrict__ b, float eps, const float* __restrict__ h, int ldh,
                      int D, float* __restrict__ h_new, int ldn, SplitOut so) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ float red[4 * 32];
   const float* row = g_pre + (size_t)blockIdx.x * ldg;
   float mean, rstd;
@@ -191,8 +201,8 @@ int gru_gates_fwd(const float* g_pre, int ldg, const float* g, const float* b, f
                   const float* h, int ldh, int M, int D, float* h_new, int ldn, cudaStream_t st,
                   SplitOut so) {
   if (M <= 0) return 0;
-  gru_gates_fwd_kernel<<<M, ROW_THREADS, 0, st>>>(g_pre, ldg, g, b, eps, h, ldh, D, h_new, ldn,
-                                                  so);
+  DV3_CHECK_CUDA(launch_pdl(gru_gates_fwd_kernel, dim3(M), dim3(ROW_THREADS), 0, st, g_pre, ldg, g, b,
+                            eps, h, ldh, D, h_new, ldn, so));
   DV3_CHECK_LAUNCH("gru_gates_fwd_kernel");
   return 0;
 }
@@ -208,6 +218,8 @@ gru_gates_bwd_kernel(const float* __restrict__ g_pre, int ldg, const float* __re
                      DhIn dh, int D, float* __restrict__ d_g_pre, int ldp,
                      float* __restrict__ d_g_ln, int ldl, float* __restrict__ dh_direct, int ldd,
                      SplitOut so) {
+  pdl_wait();
+  pdl_launch_dependents();
   extern __shared__ float sm[];
   float* dparts = sm;             // 3D: gradient w.r.t. the LN affine output
   float* red = sm + 3 * D;        // 128
@@ -269,8 +281,8 @@ int gru_gates_bwd(const float* g_pre, int ldg, const float* g, const float* b, f
     attr_set = true;
   }
   DV3_REQUIRE(smem <= 200 * 1024, DV3_ERR_BAD_SHAPE, "gru_gates_bwd: deter %d too wide", D);
-  gru_gates_bwd_kernel<<<M, ROW_THREADS, smem, st>>>(g_pre, ldg, g, b, eps, h, ldh, dh, D, d_g_pre,
-                                                     ldp, d_g_ln, ldl, dh_direct, ldd, so);
+  DV3_CHECK_CUDA(launch_pdl(gru_gates_bwd_kernel, dim3(M), dim3(ROW_THREADS), smem, st, g_pre, ldg, g,
+                            b, eps, h, ldh, dh, D, d_g_pre, ldp, d_g_ln, ldl, dh_direct, ldd, so));
   DV3_CHECK_LAUNCH("gru_gates_bwd_kernel");
   return 0;
 }
@@ -286,6 +298,8 @@ __global__ void __launch_bounds__(256)
 onehot_sample_kernel(const float* __restrict__ logits, int ldl, const float* __restrict__ u,
                      int ldu, int permT, int permB, float unimix, int M, int S, int C,
                      int32_t* __restrict__ idx, int ldi, float* __restrict__ onehot, int ldo) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
   const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (w >= (long long)M * S) return;
@@ -313,8 +327,8 @@ int onehot_sample(const float* logits, int ldl, const float* u, int ldu, int per
   DV3_REQUIRE(C >= 1 && C <= 32, DV3_ERR_BAD_SHAPE, "onehot_sample: classes=%d (max 32)", C);
   const long long warps = (long long)M * S;
   const int grid = (int)((warps + 7) / 8);
-  onehot_sample_kernel<<<grid, 256, 0, st>>>(logits, ldl, u, ldu, permT, permB, unimix, M, S, C,
-                                             idx, ldi, onehot, ldo);
+  DV3_CHECK_CUDA(launch_pdl(onehot_sample_kernel, dim3(grid), dim3(256), 0, st, logits, ldl, u, ldu,
+                            permT, permB, unimix, M, S, C, idx, ldi, onehot, ldo));
   DV3_CHECK_LAUNCH("onehot_sample_kernel");
   return 0;
 }
@@ -326,6 +340,8 @@ onehot_st_bwd_kernel(const float* __restrict__ logits, int ldl, const float* __r
                      int ldg1, const float* __restrict__ g2, int ldg2,
                      const float* __restrict__ ext, int lde, float unimix, int M, int S, int C,
                      float* __restrict__ d_logits, int ldd, SplitOut so) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
   const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (w >= (long long)M * S) return;
@@ -357,8 +373,8 @@ int onehot_st_bwd(const float* logits, int ldl, const float* g1, int ldg1, const
   DV3_REQUIRE(C >= 1 && C <= 32, DV3_ERR_BAD_SHAPE, "onehot_st_bwd: classes=%d (max 32)", C);
   const long long warps = (long long)M * S;
   const int grid = (int)((warps + 7) / 8);
-  onehot_st_bwd_kernel<<<grid, 256, 0, st>>>(logits, ldl, g1, ldg1, g2, ldg2, ext, lde, unimix, M,
-                                             S, C, d_logits, ldd, so);
+  DV3_CHECK_CUDA(launch_pdl(onehot_st_bwd_kernel, dim3(grid), dim3(256), 0, st, logits, ldl, g1, ldg1,
+                            g2, ldg2, ext, lde, unimix, M, S, C, d_logits, ldd, so));
   DV3_CHECK_LAUNCH("onehot_st_bwd_kernel");
   return 0;
 }

@@ -23,6 +23,8 @@ namespace dv3 {
 __global__ void split_tf32_kernel(const float* __restrict__ a1, int ld1, int K1,
                                   const float* __restrict__ a2, int ld2, int K2, int M, int Kp,
                                   float* __restrict__ hi, float* __restrict__ lo) {
+  pdl_wait();
+  pdl_launch_dependents();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)M * Kp) return;
   const int r = (int)(i / Kp), c = (int)(i % Kp);
@@ -72,8 +74,8 @@ int tc_split(const float* a1, int ld1, int K1, const float* a2, int ld2, int K2,
   if (Kp < K) Kp = K;
   const long long tot = (long long)M * Kp;
   if (tot <= 0) return 0;
-  split_tf32_kernel<<<(int)((tot + 255) / 256), 256, 0, st>>>(a1, ld1, K1, a2, ld2, a2 ? K2 : 0, M,
-                                                              Kp, hi, lo);
+  DV3_CHECK_CUDA(launch_pdl(split_tf32_kernel, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, st,
+                            a1, ld1, K1, a2, ld2, a2 ? K2 : 0, M, Kp, hi, lo));
   DV3_CHECK_LAUNCH("split_tf32_kernel");
   return 0;
 }

@@ -126,6 +126,10 @@ umma2_gemm_kernel(const __grid_constant__ Gemm2Maps mp, Gemm2Args g) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // the prologue above overlapped the previous kernel's tail; its outputs (our operands, addend,
+  // C when accumulating) may only be touched from here on
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
@@ -417,7 +421,7 @@ static int launch_umma2(const Gemm2Maps& mp, Gemm2Args g, double flops, cudaStre
   const int grid = g.units < sm_count() ? g.units : sm_count();
   const bool prof = prof_on();
   if (prof) prof_begin(st);
-  kern<<<grid, G2_THREADS, Cfg::SMEM, st>>>(mp, g);
+  DV3_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(G2_THREADS), Cfg::SMEM, st, mp, g));
   if (prof) prof_end(st, 1, flops);
   DV3_CHECK_LAUNCH("umma2_gemm_kernel");
   return 0;

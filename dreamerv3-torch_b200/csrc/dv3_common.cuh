@@ -244,6 +244,10 @@ struct TcOperand {
 int tc_gemm_ops(const TcOperand& A1, int K1, const TcOperand* A2, int K2, const TcOperand& B,
                 const float* bias, const float* addend, int ldadd, float* C, int ldc, int M, int N,
                 int accumulate, cudaStream_t st);
+// the same product on CTA pairs (cta_group::2, 256 x BN tiles; dv3_umma2x.cu)
+int tc_gemm_pair(const TcOperand& A1, int K1, const TcOperand* A2, int K2, const TcOperand& B,
+                 const float* bias, const float* addend, int ldadd, float* C, int ldc, int M, int N,
+                 int accumulate, int BN, int splitk, cudaStream_t st);
 // persistent (single cooperative launch) forward recurrence of observe; *used == false -> not
 // applicable for these shapes, run the stepwise launches instead (dv3_observe_persistent.cu)
 int observe_fwd_persistent(const dv3_rssm_dims* d, const dv3_rssm_params* p,

@@ -75,6 +75,28 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
       : "r"(taddr))
 
 
+// UMMA shared-memory descriptor from the operand's 16-byte unit index ((smem address >> 4), 14
+// bits).  Only the unit index varies between MMAs, so the issuing thread adds small constants to
+// it instead of rebuilding the 64-bit word (the single issuing thread is the GEMM's critical
+// resource: 140 uniform-datapath instructions per k-block were costing more than the 12 MMAs).
+//   K-major : 128B swizzle (layout type 2), SBO = 1024 B, LBO unused (1)
+//   MN-major: 128B swizzle with 32B atoms (layout type 1), SBO = 512 B, LBO = 4096 B
+template <bool MN>
+__device__ __forceinline__ uint64_t umma_desc_units(uint32_t unit) {
+  constexpr uint32_t hi = MN ? (32u | (1u << 14) | (1u << 29)) : (64u | (1u << 14) | (2u << 29));
+  constexpr uint32_t lbo = MN ? (256u << 16) : (1u << 16);
+  return ((uint64_t)hi << 32) | (uint64_t)(unit | lbo);
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }

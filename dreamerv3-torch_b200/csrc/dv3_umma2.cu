@@ -163,12 +163,16 @@ umma2_gemm_kernel(const __grid_constant__ Gemm2Maps mp, Gemm2Args g) {
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------ MMA issuer --------------------------------
-    if (lane == 0) {
+    // The warp stays converged; one elected lane issues the MMAs and commits.
+    {
       // c=F32, a=b=TF32; bit 15/16 = A/B MN-major; N>>3 at [17,23), M>>4 at [24,29)
       constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)AMN << 15) |
                                  ((uint32_t)BMN << 16) | ((uint32_t)(BN >> 3) << 17) |
                                  ((uint32_t)(G2_BM >> 4) << 24);
-      constexpr uint32_t A_KSTEP = AMN ? 1024 : 32, B_KSTEP = BMN ? 1024 : 32;
+      constexpr uint32_t A_KU = (AMN ? 1024 : 32) >> 4, B_KU = (BMN ? 1024 : 32) >> 4;
+      constexpr uint32_t A_PU = A_BYTES >> 4, B_PU = B_BYTES >> 4, ST_U = STAGE_BYTES >> 4;
+      const bool issuer = elect_one();
+      const uint32_t unit0 = (smem_u32(smem) >> 4) & 0x3FFF;
       int it = 0, cc = 0, tl = 0;
       for (int unit = blockIdx.x; unit < g.units; unit += gridDim.x, ++tl) {
         const int kb0 = (unit / g.tiles) * g.nkp, kb1 = min(nk, kb0 + g.nkp);
@@ -184,32 +188,31 @@ umma2_gemm_kernel(const __grid_constant__ Gemm2Maps mp, Gemm2Args g) {
           if (kin == 0) {
             buf = cc & 1;
             mbar_wait(tempty0 + 8 * buf, ((cc >> 1) & 1) ^ 1);
-            tc_fence_after();
           }
           mbar_wait((RAW ? conv0 : full0) + 8 * s, ph);
           tc_fence_after();
-          const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
+          const uint32_t au = unit0 + s * ST_U, bu = au + 2 * A_PU;
           const uint32_t acc_hi = tmem_base + buf * BN;
+          const bool last = kin == G2_CH - 1 || kb == kb1 - 1;
+          if (issuer) {
 #pragma unroll
-          for (int k = 0; k < G2_BK / 8; ++k) {
-            const uint32_t ao = base + k * A_KSTEP, bo = base + 2 * A_BYTES + k * B_KSTEP;
-            const uint64_t ah = AMN ? umma_desc_mn(ao) : umma_desc(ao);
-            const uint64_t al = AMN ? umma_desc_mn(ao + A_BYTES) : umma_desc(ao + A_BYTES);
-            const uint64_t bh = BMN ? umma_desc_mn(bo) : umma_desc(bo);
-            const uint64_t bl = BMN ? umma_desc_mn(bo + B_BYTES) : umma_desc(bo + B_BYTES);
-            umma_tf32(acc_lo, al, bh, idesc, ((kb - kb0) | k) != 0);
-            umma_tf32(acc_lo, ah, bl, idesc, 1);
-            umma_tf32(acc_hi, ah, bh, idesc, (kin | k) != 0);
+            for (int k = 0; k < G2_BK / 8; ++k) {
+              const uint64_t ah = umma_desc_units<AMN>(au + k * A_KU);
+              const uint64_t al = umma_desc_units<AMN>(au + A_PU + k * A_KU);
+              const uint64_t bh = umma_desc_units<BMN>(bu + k * B_KU);
+              const uint64_t bl = umma_desc_units<BMN>(bu + B_PU + k * B_KU);
+              umma_tf32(acc_lo, al, bh, idesc, ((kb - kb0) | k) != 0);
+              umma_tf32(acc_lo, ah, bl, idesc, 1);
+              umma_tf32(acc_hi, ah, bh, idesc, (kin | k) != 0);
+            }
+            umma_commit(empty0 + 8 * s);
+            if (last) umma_commit(tfull0 + 8 * buf);
           }
-          umma_commit(empty0 + 8 * s);
-          if (kin == G2_CH - 1 || kb == kb1 - 1) {
-            umma_commit(tfull0 + 8 * buf);
-            ++cc;
-          }
+          if (last) ++cc;
+          __syncwarp();
         }
       }
     }
-    __syncwarp();
   } else if (RAW && warp >= G2_CONV_WARP0) {
     // ------------------------------ converters --------------------------------
     const int ct = threadIdx.x - G2_CONV_WARP0 * 32;     // 0..127
@@ -366,8 +369,7 @@ static EncodeTiledFn2 encode_fn2() {
 
 // Tensor map of one operand plane.  K-major: memory is [rows, K] (row stride ld), box = 32 k x
 // box_rows rows.  MN-major: memory is [K, rows] (row stride ld), box = 32 rows x 32 k.
-static int make_map2(CUtensorMap* m, const float* base, int rows, int K, int ld, int box_rows,
-                     bool mn) {
+int make_map2(CUtensorMap* m, const float* base, int rows, int K, int ld, int box_rows, bool mn) {
   EncodeTiledFn2 fn = encode_fn2();
   DV3_REQUIRE(fn, DV3_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[2] = {(cuuint64_t)(mn ? rows : K), (cuuint64_t)(mn ? K : rows)};
@@ -384,7 +386,7 @@ static int make_map2(CUtensorMap* m, const float* base, int rows, int K, int ld,
   return 0;
 }
 
-static int sm_count() {
+int sm_count() {
   static int sms = 0;
   if (!sms) {
     int dev = 0;
@@ -444,26 +446,36 @@ static bool tma_ok(const float* p, int ld) {
 // waves x k-blocks x (time per k-block).  The k-block time is set by shared-memory traffic (TMA
 // writes + UMMA operand reads at 128 B/clk: 160 / 120 / 100 KB per k-block for BN = 128 / 64 /
 // 32), measured 1250 / 940 / 780 clk.  Split-K pays a memset and an atomic epilogue.
-static void pick_shape(int M, int N, int nk, bool allow_splitk, int* bn_out, int* splitk_out) {
+static void pick_shape(int M, int N, int nk, bool allow_splitk, bool allow_pair, bool b_mn,
+                       int* bn_out, int* splitk_out, int* pair_out) {
   const int tm = (M + G2_BM - 1) / G2_BM, sms = sm_count();
-  const int bns[3] = {128, 64, 32};
-  const long long cost[3] = {1250, 940, 780};
+  // single-CTA tiles 128 x {128,64,32}; pair tiles 256 x {128,64} (dv3_umma2x.cu): per CTA and
+  // k-block 120 / 100 KB of shared-memory traffic -> 940 / 780 clk
+  const int bns[5] = {128, 64, 32, 128, 64};
+  const long long cost[5] = {1250, 940, 780, 940, 780};
   long long best_t = -1;
-  *bn_out = 32; *splitk_out = 1;
-  for (int i = 0; i < 3; ++i) {
+  *bn_out = 32; *splitk_out = 1; *pair_out = 0;
+  for (int i = 0; i < 5; ++i) {
+    const bool pair = i >= 3;
+    if (pair && (!allow_pair || M <= G2_BM)) continue;
     if (bns[i] > 32 && N <= bns[i] / 2) continue;          // mostly padding
-    const int tiles = tm * ((N + bns[i] - 1) / bns[i]);
+    (void)b_mn;
+    const int slots = pair ? sms / 2 : sms;
+    const int tiles = (pair ? (M + 2 * G2_BM - 1) / (2 * G2_BM) : tm) * ((N + bns[i] - 1) / bns[i]);
     int sk = 1;
-    if (allow_splitk && tiles < sms) {
-      sk = sms / tiles;
+    if (allow_splitk && tiles < slots) {
+      sk = slots / tiles;
       const int cap = nk / 8;                              // >= 8 k-blocks per partition
       if (sk > cap) sk = cap;
       if (sk < 1) sk = 1;
     }
     const int nkp = (nk + sk - 1) / sk;
-    long long t = (long long)((tiles * sk + sms - 1) / sms) * nkp * cost[i];
+    long long t = (long long)((tiles * sk + slots - 1) / slots) * nkp * cost[i];
     if (sk > 1) t += 8000;
-    if (best_t < 0 || t < best_t) { best_t = t; *bn_out = bns[i]; *splitk_out = sk; }
+    if (pair) t += t / 50;                                 // ties go to the single-CTA kernel
+    if (best_t < 0 || t < best_t) {
+      best_t = t; *bn_out = bns[i]; *splitk_out = sk; *pair_out = pair ? 1 : 0;
+    }
   }
 }
 
@@ -488,8 +500,16 @@ int tc_gemm_ops(const TcOperand& A1, int K1, const TcOperand* A2, int K2, const 
   DV3_REQUIRE(!A2 || A2->mn == A1.mn, DV3_ERR_BAD_SHAPE, "tc_gemm: A segments differ in order");
   const int K = K1 + K2;
   const int nk_all = (K1 + G2_BK - 1) / G2_BK + (K2 + G2_BK - 1) / G2_BK;
-  int BN = 32, splitk = 1;
-  pick_shape(M, N, nk_all, (accumulate & 2) != 0, &BN, &splitk);
+  int BN = 32, splitk = 1, pair = 0;
+  static int allow_pair = -1;
+  if (allow_pair < 0) {
+    const char* e = getenv("DV3_TC_PAIR");
+    allow_pair = (e && e[0] == '0') ? 0 : 1;
+  }
+  pick_shape(M, N, nk_all, (accumulate & 2) != 0, allow_pair && !raw, B.mn, &BN, &splitk, &pair);
+  if (pair)
+    return tc_gemm_pair(A1, K1, A2, K2, B, bias, addend, ldadd, C, ldc, M, N, accumulate, BN, splitk,
+                        st);
   Gemm2Maps mp;
   DV3_TRY(make_map2(&mp.a1h, A1.hi, M, K1, A1.ld, G2_BM, A1.mn));
   if (!raw) DV3_TRY(make_map2(&mp.a1l, A1.lo, M, K1, A1.ld, G2_BM, A1.mn));

@@ -369,8 +369,8 @@ def run_ours(args):
         "imagined_states_per_s": imag_states,
         "imagine_fwd_ms": imag_ms,
         "roofline": {
-            "kernel": "umma2_gemm_kernel (persistent tcgen05 3xTF32 GEMM: every imagination-step and bulk-row "
-                      "contraction, y / dx / dW; dominant by time)",
+            "kernel": "umma2x_gemm_kernel / umma2_gemm_kernel (persistent tcgen05 3xTF32 GEMM on CTA pairs / single "
+                      "CTAs: every imagination-step and bulk-row contraction, y / dx / dW; dominant by time)",
             "bound": "tensor", "achieved": ach, "peak": peaks["tf"], "unit": "TFLOP/s",
             "frac": ach / peaks["tf"], "traffic": None, "peak_source": peaks["src"],
             "flops": "algorithmic 2*M*N*K per launch (fp32 result); the kernel issues 3 tf32 MMAs per product, "

@@ -738,10 +738,16 @@ class _Imagine(torch.autograd.Function):
         ctx.n_saved = len(saved)
         ctx.save_for_backward(*saved, *[p.detach() for p in params])
         ctx.mark_non_differentiable(o["idx"])
-        return o["feat"], o["logit"], o["action"], o["idx"]
+        # the actor heads' raw outputs at every step are returned as differentiable outputs: the
+        # caller builds the policy distribution (entropy, log-prob) from them instead of running
+        # the actor MLP a second time over all H*N rows (reference models.py:349 re-evaluates)
+        empty = o["action"].new_zeros(0)
+        mean_raw = o["a_mean_raw"] if spec is not None else empty
+        std_raw = o["a_std_raw"] if spec is not None and spec.dist == "normal" else empty
+        return o["feat"], o["logit"], o["action"], o["idx"], mean_raw, std_raw
 
     @staticmethod
-    def backward(ctx, g_feat, g_logit, g_action, _g_idx):
+    def backward(ctx, g_feat, g_logit, g_action, _g_idx, g_mean_raw=None, g_std_raw=None):
         S, Cc, D, Hd, A, E, unimix = ctx.dims
         spec = ctx.spec
         N, H = ctx.NH
@@ -788,6 +794,8 @@ class _Imagine(torch.autograd.Function):
         Lr, U = spec.layers, spec.units
         HN = H * N
         dm = o["d_mean_raw"].reshape(HN, A)
+        if g_mean_raw is not None and g_mean_raw.numel():
+            dm = dm + _f32(g_mean_raw).reshape(HN, A)
         top = a_act[Lr - 1].reshape(HN, U)
         ga = [None] * len(actor_params)
         dw = lambda d, inp: gemm_tc(d, inp, a_t=True, b_t=True, split_k=True)
@@ -796,6 +804,8 @@ class _Imagine(torch.autograd.Function):
         d_act = dm @ actor_params[3 * Lr]
         if spec.dist == "normal":
             ds = o["d_std_raw"].reshape(HN, A)
+            if g_std_raw is not None and g_std_raw.numel():
+                ds = ds + _f32(g_std_raw).reshape(HN, A)
             ga[3 * Lr + 2], ga[3 * Lr + 3] = dw(ds, tops), ds.sum(0)
             d_act = d_act + ds @ actor_params[3 * Lr + 2]
         for i in range(Lr - 1, -1, -1):
@@ -812,7 +822,16 @@ class _Imagine(torch.autograd.Function):
         return (None, None, None, None, None, None, None, None, None, *([None] * 17), *ga)
 
 
-def imagine(start_idx, start_deter, act_noise, u_state, given_action, H, dims, spec, rssm_params,
-            actor_params, start_logit=None):
+def imagine_full(start_idx, start_deter, act_noise, u_state, given_action, H, dims, spec,
+                 rssm_params, actor_params, start_logit=None):
+    """-> feat, logit, action, idx, actor mean_raw [H,N,A], actor std_raw [H,N,A] (empty for a
+    one-hot actor / no actor); the last two are differentiable w.r.t. the actor parameters."""
     return _Imagine.apply(start_idx, start_deter, act_noise, u_state, given_action, start_logit, H,
                           dims, spec, *rssm_params, *actor_params)
+
+
+def imagine(start_idx, start_deter, act_noise, u_state, given_action, H, dims, spec, rssm_params,
+            actor_params, start_logit=None):
+    """-> feat [H,N,F], logit [H,N,S,C], action [H,N,A], idx int32 [H,N,S]."""
+    return imagine_full(start_idx, start_deter, act_noise, u_state, given_action, H, dims, spec,
+                        rssm_params, actor_params, start_logit)[:4]

@@ -202,7 +202,7 @@ class ImagBehavior(nn.Module):
             an = (torch.randn(horizon, N, A, device=dev) if spec.dist == "normal"
                   else torch.rand(horizon, N, A, device=dev))
             noise = (an, torch.rand(horizon, N, S, Cc, device=dev))
-        feat, logit, action, _ = K.imagine(
+        feat, logit, action, _, mean_raw, std_raw = K.imagine_full(
             dyn._to_idx(flat["stoch"]), flat["deter"].detach(), noise[0], noise[1], None, horizon,
             dyn.dims, spec, dyn.kernel_params(), policy.actor_params(),
             start_logit=flat.get("logit"))
@@ -215,6 +215,9 @@ class ImagBehavior(nn.Module):
         for v in (states["stoch"], states["deter"]):
             v._dv3_feat, v._dv3_feat_version = feat, feat._version
         imag_feat = feat.detach()
+        # raw head outputs of the in-loop actor (differentiable w.r.t. the actor parameters):
+        # losses() builds the policy distribution from them instead of re-running the actor
+        action._dv3_policy_raw = (policy, mean_raw, std_raw if std_raw.numel() else None)
         if horizon * N >= 64:
             sp = K.split(imag_feat.reshape(horizon * N, -1))
             K.attach_split(feat, sp)
@@ -230,12 +233,26 @@ class ImagBehavior(nn.Module):
         with tools.RequiresGrad(self.actor):
             imag_feat, imag_state, imag_action = self._imagine(start, self.actor,
                                                                cfg.imag_horizon, noise)
+            # One critic forward over all H steps serves the lambda-return target, the baseline
+            # and the value loss: the reference evaluates self.value three times on the same
+            # (detached) features with unchanged weights (models.py:629, 421, 662).
+            with tools.RequiresGrad(self.value):
+                v_all = self.value(imag_feat)
+            v_mode = v_all.mode().detach() if isinstance(v_all, tools.DiscDist) else None
             reward = objective(imag_feat, imag_state, imag_action)
-            policy = self.actor(imag_feat)
+            raw = getattr(imag_action, "_dv3_policy_raw", None)
+            if raw is not None and raw[0] is self.actor:
+                # same numbers the reference gets from self.actor(imag_feat) (models.py:349): the
+                # rollout already evaluated the actor on these very features
+                std = raw[2] if raw[2] is not None else self.actor._std
+                policy = self.actor.dist(self.actor._dist, raw[1], std, self.actor._shape)
+            else:
+                policy = self.actor(imag_feat)
             actor_ent = policy.entropy()
-            target, weights, base = self._compute_target(imag_feat, imag_state, reward)
+            target, weights, base = self._compute_target(imag_feat, imag_state, reward,
+                                                         value_mode=v_mode)
             actor_loss, mets = self._compute_actor_loss(imag_feat, imag_action, target, weights,
-                                                        base, policy)
+                                                        base, policy, value_mode=v_mode)
             actor_loss = actor_loss - cfg.actor["entropy"] * actor_ent[:-1, ..., None]
             actor_loss = torch.mean(actor_loss)
             metrics.update(mets)
@@ -244,13 +261,14 @@ class ImagBehavior(nn.Module):
             sp = K.split_of_attached(imag_feat)
             if sp is not None:
                 K.attach_split(feat_m1, sp.prefix(feat_m1.shape[0] * feat_m1.shape[1]))
-            value = self.value(feat_m1)
+            value = (tools.DiscDist(logits=v_all.logits[:-1]) if v_mode is not None
+                     else self.value(feat_m1))
             value_loss = -value.log_prob(target.detach())
             if cfg.critic["slow_target"]:
                 slow = self._slow_value(feat_m1)
                 value_loss = value_loss - value.log_prob(slow.mode().detach())
             value_loss = torch.mean(weights[:-1] * value_loss[:, :, None])
-        metrics.update(tools.tensorstats(value.mode(), "value"))
+        metrics.update(tools.tensorstats(v_mode[:-1] if v_mode is not None else value.mode(), "value"))
         metrics.update(tools.tensorstats(target, "target"))
         metrics.update(tools.tensorstats(reward, "imag_reward"))
         if cfg.actor["dist"] in ["onehot"]:
@@ -274,8 +292,9 @@ class ImagBehavior(nn.Module):
             metrics = tools.to_host(metrics)
         return imag_feat, imag_state, imag_action, weights, metrics
 
-    def _compute_target(self, imag_feat, imag_state, reward):
-        """reference models.py:620-638; the target comes back stacked [H-1,N,1]."""
+    def _compute_target(self, imag_feat, imag_state, reward, value_mode=None):
+        """reference models.py:620-638; the target comes back stacked [H-1,N,1].  ``value_mode``:
+        the critic's mode over all H steps when the caller already evaluated it."""
         cfg = self._config
         wm = self._world_model
         if "cont" in wm.heads:
@@ -283,14 +302,15 @@ class ImagBehavior(nn.Module):
             discount = cfg.discount * wm.heads["cont"](inp).mean
         else:
             discount = cfg.discount * torch.ones_like(reward)
-        value = self.value(imag_feat).mode()
+        value = value_mode if value_mode is not None else self.value(imag_feat).mode()
         target = tools.lambda_return_stacked(reward[1:], value[:-1], discount[1:], value[-1],
                                              cfg.discount_lambda)
         weights = torch.cumprod(torch.cat([torch.ones_like(discount[:1]), discount[:-1]], 0),
                                 0).detach()
         return target, weights, value[:-1]
 
-    def _compute_actor_loss(self, imag_feat, imag_action, target, weights, base, policy=None):
+    def _compute_actor_loss(self, imag_feat, imag_action, target, weights, base, policy=None,
+                            value_mode=None):
         cfg = self._config
         metrics = {}
         if policy is None:
@@ -311,7 +331,8 @@ class ImagBehavior(nn.Module):
             actor_target = adv
         elif cfg.imag_gradient in ("reinforce", "both"):
             actor_target = (policy.log_prob(imag_action)[:-1][:, :, None]
-                            * (target - self.value(imag_feat[:-1]).mode()).detach())
+                            * (target - (value_mode[:-1] if value_mode is not None
+                                         else self.value(imag_feat[:-1]).mode())).detach())
             if cfg.imag_gradient == "both":
                 mix = cfg.imag_gradient_mix
                 actor_target = mix * target + (1 - mix) * actor_target

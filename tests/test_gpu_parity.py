@@ -146,3 +146,28 @@ def test_ln_param_grads(pkg, device, M, n):
     rg, rb = (d_ln.double() * xh).sum(0), d_ln.double().sum(0)
     assert float((dg.double() - rg).abs().max() / rg.abs().max()) < 1e-5
     assert float((db.double() - rb).abs().max() / rb.abs().max()) < 1e-5
+
+
+def test_observe_backward_runs_persistent(pkg, device):
+    """At dmc sizes both directions of observe are single cooperative launches: count the
+    library's launches around a forward + backward (bulk products and row kernels excluded by a
+    generous bound -- the stepwise backward alone would be > 800 launches)."""
+    import torch
+    cfgs = pkg.configs
+    torch.manual_seed(0)
+    cfg = cfgs.make_config("dmc_proprio", device=device)
+    wm = pkg.models.WorldModel(cfgs.ObsSpace(cfgs.PROPRIO_SHAPES), None, 0, cfg)
+    B, T, A = 16, 64, cfg.num_actions
+    action = torch.rand(B, T, A, device=device)
+    first = torch.zeros(B, T, device=device)
+    first[:, 0] = 1
+    lib = pkg._lib.lib()
+    e = torch.randn(B, T, 1024, device=device, requires_grad=True)
+    with pkg.tools.RequiresGrad(wm.dynamics):
+        n0 = lib.dv3_launch_count()
+        post, prior = wm.dynamics.observe(e, action, first)
+        n1 = lib.dv3_launch_count()
+        (post["deter"].sum() + post["stoch"].sum() + prior["logit"].sum() + post["logit"].sum()).backward()
+        n2 = lib.dv3_launch_count()
+    assert n1 - n0 < 40, n1 - n0
+    assert n2 - n1 < 120, n2 - n1

@@ -306,6 +306,13 @@ class GradSync:
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
 
+    def flat(self, flat_grad):
+        """Average one flat gradient buffer in place (tools.Optimizer's CUDA path)."""
+        if self.world == 1:
+            return
+        self.dist.all_reduce(flat_grad, op=self.dist.ReduceOp.SUM, group=self.group)
+        flat_grad.div_(self.world)
+
     def __call__(self, params):
         if self.world == 1:
             return
@@ -324,7 +331,16 @@ class GradSync:
 
 class Optimizer:
     """Adam + global-norm clip, the reference's tools.Optimizer call sequence
-    (tools.py:760-776): zero_grad -> backward -> [DP allreduce] -> clip -> (wd) -> step."""
+    (tools.py:760-776): zero_grad -> backward -> [DP allreduce] -> clip -> (wd) -> step.
+
+    On CUDA the parameters of one optimizer are re-homed into ONE flat fp32 buffer (each
+    parameter becomes a view; ``state_dict`` names and values are unchanged), their ``.grad``s are
+    persistent views of a second flat buffer that autograd accumulates into, and clip + Adam run
+    as the fused ``dv3_adam_clip_step`` (three launches; step counter on the device, so the call
+    is graph-capturable).  The data-parallel allreduce then runs on the flat gradient buffer
+    directly.  CPU parameters (the gloo tests) keep the torch.optim.Adam path."""
+
+    BETAS = (0.9, 0.999)
 
     def __init__(self, name, parameters, lr, eps=1e-4, clip=None, wd=None, wd_pattern=r".*",
                  opt="adam", use_amp=False, grad_sync=None):
@@ -338,39 +354,108 @@ class Optimizer:
         self._params = list(parameters)
         self._clip = clip
         self._wd = wd
-        fused = bool(self._params) and self._params[0].is_cuda
-        # capturable: the step counter lives on the device, so that a whole train step can be
-        # recorded into a CUDA graph (graphs.TrainStepGraph)
-        self._opt = torch.optim.Adam(self._params, lr=lr, eps=eps, fused=fused, capturable=fused)
+        self._lr, self._eps = float(lr), float(eps)
         self._sync = grad_sync
+        self._flat = (bool(self._params) and
+                      all(p.is_cuda and p.dtype == torch.float32 for p in self._params))
+        if self._flat:
+            self._build_flat()
+            self._opt = None
+        else:
+            self._opt = torch.optim.Adam(self._params, lr=lr, eps=eps)
+
+    # ---- flat buffers ------------------------------------------------------------------
+    def _build_flat(self):
+        dev = self._params[0].device
+        self._offsets, total = [], 0
+        for p in self._params:
+            self._offsets.append(total)
+            total += (p.numel() + 3) & ~3              # every parameter starts 16-byte aligned
+        z = lambda: torch.zeros(total, dtype=torch.float32, device=dev)
+        self._fp, self._fg, self._fm, self._fv = z(), z(), z(), z()
+        self._step = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._ctl = torch.zeros(4, dtype=torch.float32, device=dev)
+        self._scratch = torch.empty(1024, dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            for p, off in zip(self._params, self._offsets):
+                n = p.numel()
+                view = self._fp[off:off + n].view(p.shape)
+                view.copy_(p.data)
+                p.data = view
+                p.grad = self._fg[off:off + n].view(p.shape)
+
+    def _views(self, flat):
+        return [flat[off:off + p.numel()].view(p.shape) for p, off in zip(self._params, self._offsets)]
 
     def set_grad_sync(self, sync):
         self._sync = sync
 
     def state_dict(self):
-        return self._opt.state_dict()
+        """torch.optim.Adam's layout (what the reference checkpoints, dreamer.py:502-506)."""
+        if not self._flat:
+            return self._opt.state_dict()
+        state = {}
+        if float(self._step) > 0:
+            ms, vs = self._views(self._fm), self._views(self._fv)
+            for i in range(len(self._params)):
+                state[i] = {"step": self._step.clone().reshape(()), "exp_avg": ms[i].clone(),
+                            "exp_avg_sq": vs[i].clone()}
+        group = dict(lr=self._lr, betas=self.BETAS, eps=self._eps, weight_decay=0, amsgrad=False,
+                     maximize=False, foreach=None, capturable=True, differentiable=False,
+                     fused=True, params=list(range(len(self._params))))
+        return {"state": state, "param_groups": [group]}
 
     def load_state_dict(self, sd):
-        self._opt.load_state_dict(sd)
+        if not self._flat:
+            self._opt.load_state_dict(sd)
+            return
+        ms, vs = self._views(self._fm), self._views(self._fv)
+        with torch.no_grad():
+            for i, st in sd.get("state", {}).items():
+                ms[int(i)].copy_(st["exp_avg"])
+                vs[int(i)].copy_(st["exp_avg_sq"])
+                self._step.fill_(float(st["step"]))
+        if sd.get("param_groups"):
+            self._lr = float(sd["param_groups"][0].get("lr", self._lr))
+            self._eps = float(sd["param_groups"][0].get("eps", self._eps))
 
+    # ---- one optimisation step ---------------------------------------------------------
     def __call__(self, loss, params=None, retain_graph=False):
         if loss.dim() != 0:
             raise AssertionError(loss.shape)
         params = self._params
         metrics = {f"{self._name}_loss": loss.detach()}
-        self._opt.zero_grad(set_to_none=True)
+        if not self._flat:
+            self._opt.zero_grad(set_to_none=True)
+            loss.backward(retain_graph=retain_graph)
+            if self._sync is not None:
+                self._sync(params)
+            norm = nn.utils.clip_grad_norm_(params, self._clip)
+            if self._wd:
+                with torch.no_grad():
+                    for p in params:
+                        p.mul_(1 - self._wd)
+            self._opt.step()
+            K.invalidate_weight_splits()
+            self._opt.zero_grad(set_to_none=True)
+            metrics[f"{self._name}_grad_norm"] = norm.detach()
+            return metrics
+        self._fg.zero_()
+        for p, g in zip(params, self._views(self._fg)):
+            if p.grad is None or p.grad.data_ptr() != g.data_ptr():
+                p.grad = g                                 # someone reset it (set_to_none)
         loss.backward(retain_graph=retain_graph)
         if self._sync is not None:
-            self._sync(params)
-        norm = nn.utils.clip_grad_norm_(params, self._clip)
-        if self._wd:
-            with torch.no_grad():
-                for p in params:
-                    p.mul_(1 - self._wd)
-        self._opt.step()
+            self._sync.flat(self._fg)
+        L_ = K.L
+        L_.check(L_.lib().dv3_adam_clip_step(
+            L_.fptr(self._fp), L_.fptr(self._fg), L_.fptr(self._fm), L_.fptr(self._fv),
+            self._fp.numel(), self._lr, self.BETAS[0], self.BETAS[1], self._eps,
+            float(self._clip) if self._clip else 0.0, 1.0 - float(self._wd) if self._wd else 1.0,
+            L_.fptr(self._step), L_.fptr(self._ctl), L_.fptr(self._scratch), L_.stream_ptr()),
+            "adam_clip_step")
         K.invalidate_weight_splits()
-        self._opt.zero_grad(set_to_none=True)
-        metrics[f"{self._name}_grad_norm"] = norm.detach()
+        metrics[f"{self._name}_grad_norm"] = self._ctl[0].clone()
         return metrics
 
 

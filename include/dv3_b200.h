@@ -424,6 +424,16 @@ int dv3_onehot_st_bwd(const float* logits, const float* g_sample, const float* e
 int dv3_idx_to_onehot(const int32_t* idx, int32_t M, int32_t S, int32_t C, float* out, int32_t ld,
                       void* stream);
 
+/* tools.Optimizer.__call__ (tools.py:760-776) after backward, on one flat fp32 buffer of n
+ * (multiple of 4) parameters: global-norm clip (coef = min(1, clip / (norm + 1e-6)); clip <= 0
+ * disables it) + torch.optim.Adam update; p *= decay_mul first (decoupled weight decay of the
+ * reference, 1.0 = off).  step: device float, incremented here.  ctl: 4 floats out (grad norm
+ * before clipping, clip coefficient, lr / bias_correction1, sqrt(bias_correction2)).
+ * scratch: >= 512 floats. */
+int dv3_adam_clip_step(float* p, const float* g, float* m, float* v, long long n, float lr,
+                       float beta1, float beta2, float eps, float clip, float decay_mul,
+                       float* step, float* ctl, float* scratch, void* stream);
+
 /* Debug aid: with DV3_OBSERVE_TIMING=1 in the environment the persistent observe kernel stamps
  * %globaltimer (ns) at its 8 phase boundaries per step on CTA 0; this copies [T][8] stamps out. */
 int dv3_debug_observe_timing(unsigned long long* host, int32_t T);

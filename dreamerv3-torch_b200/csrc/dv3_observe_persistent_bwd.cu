@@ -51,29 +51,41 @@ __device__ __forceinline__ void pb_stamp(const PbArgs& p, int t, int slot) {
   }
 }
 
-// LN+SiLU backward of one row held by a warp (lane owns columns lane + 32 i, i < HV).
-//   in : pre (saved Linear output), dout (gradient w.r.t. the SiLU output; overwritten by d_ln)
+// LN+SiLU backward of one row shared by the two warps of a row pair (half 0 / 1): each warp owns
+// the columns half*n/2 + lane + 32 i (i < HV2) and the three row-wide sums (mean, variance, the
+// two LN-backward moments) meet in shared memory.  Halving the per-lane element count halves the
+// serial chain of expf / divide latencies that dominates these phases (measured 4.6 of 7.6 us
+// with one warp per row).  Must be called by ALL threads of the CTA (three block barriers);
+// `act` gates the row.  xr: shared scratch, 8 floats per row.
+//   in : pre (saved Linear output), dout (gradient w.r.t. the SiLU output) for the owned columns
 //   emit(j, d_pre, d_ln) is called once per owned column
-template <int HV, typename Emit>
-__device__ __forceinline__ void warp_ln_silu_bwd(const float (&pre)[HV], float (&dout)[HV], int n,
-                                                 int lane, const float* g, const float* b,
-                                                 float eps, Emit emit) {
+template <int HV2, typename Emit>
+__device__ __forceinline__ void pair_ln_silu_bwd(bool act, const float (&pre)[HV2], float (&dout)[HV2],
+                                                 int n, int lane, int half, const float* g,
+                                                 const float* b, float eps, float* xr, Emit emit) {
+  const int nh = n >> 1, j0 = half * nh;
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < HV; ++i) s += (lane + 32 * i < n) ? pre[i] : 0.f;
-  const float mean = warp_sum(s) / (float)n;
+  for (int i = 0; i < HV2; ++i) s += (lane + 32 * i < nh) ? pre[i] : 0.f;
+  s = warp_sum(s);
+  if (act && lane == 0) xr[half] = s;
+  __syncthreads();
+  const float mean = (xr[0] + xr[1]) / (float)n;
   float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < HV; ++i) {
-    const float d = (lane + 32 * i < n) ? pre[i] - mean : 0.f;
+  for (int i = 0; i < HV2; ++i) {
+    const float d = (lane + 32 * i < nh) ? pre[i] - mean : 0.f;
     q = fmaf(d, d, q);
   }
-  const float rstd = 1.f / sqrtf(warp_sum(q) / (float)n + eps);
+  q = warp_sum(q);
+  if (act && lane == 0) xr[2 + half] = q;
+  __syncthreads();
+  const float rstd = 1.f / sqrtf((xr[2] + xr[3]) / (float)n + eps);
   float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-  for (int i = 0; i < HV; ++i) {
-    const int j = lane + 32 * i;
-    if (j < n) {
+  for (int i = 0; i < HV2; ++i) {
+    const int j = j0 + lane + 32 * i;
+    if (act && lane + 32 * i < nh) {
       const float xh = (pre[i] - mean) * rstd;
       const float v = fmaf(xh, g[j], b[j]);
       const float dv = dout[i] * silu_grad(v);
@@ -83,11 +95,15 @@ __device__ __forceinline__ void warp_ln_silu_bwd(const float (&pre)[HV], float (
       a1 = fmaf(dx, xh, a1);
     }
   }
-  const float m1 = warp_sum(a0) / (float)n, m2 = warp_sum(a1) / (float)n;
+  a0 = warp_sum(a0);
+  a1 = warp_sum(a1);
+  if (act && lane == 0) { xr[4 + half] = a0; xr[6 + half] = a1; }
+  __syncthreads();
+  const float m1 = (xr[4] + xr[5]) / (float)n, m2 = (xr[6] + xr[7]) / (float)n;
 #pragma unroll
-  for (int i = 0; i < HV; ++i) {
-    const int j = lane + 32 * i;
-    if (j < n) {
+  for (int i = 0; i < HV2; ++i) {
+    const int j = j0 + lane + 32 * i;
+    if (act && lane + 32 * i < nh) {
       const float xh = (pre[i] - mean) * rstd;
       emit(j, rstd * (dout[i] * g[j] - m1 - xh * m2), dout[i]);
     }
@@ -114,7 +130,7 @@ __global__ void __launch_bounds__(PO_THREADS, 1) observe_persistent_bwd_kernel(P
   float* part = rows + (size_t)4 * Hd;              // gemv16 fold
   float* xch = part + PO_WARPS * PO_NV;             // [4][32] warp-pair exchange
   float* dsl = xch + 4 * 32;                        // [4][32] recurrent d stoch of (rows, group cb)
-  float* pr2 = dsl + 4 * 32;                        // [4][2][2] pair reduction of phase 3a
+  float* pr2 = dsl + 4 * 32;                        // [4][8] warp-pair reductions (LN sums)
 
   const int rb = cta % p.nrb, cb = cta / p.nrb;
   const int r0 = rb * 4, rn = max(0, min(4, B - r0));
@@ -155,6 +171,27 @@ __global__ void __launch_bounds__(PO_THREADS, 1) observe_persistent_bwd_kernel(P
     const size_t bt = (size_t)b * T + t;
 
     pb_stamp(p, t, 0);
+    // The saved activations of step t-1 were written by the forward pass milliseconds ago and
+    // have left L2; the warps that idle through phase 1a pull them in now so that the phases of
+    // the next step start from L2 instead of DRAM latency.
+    if (half == 1 && ract && t > 0) {
+      const size_t bp = bt - 1;
+      auto pf = [&](const float* base, int nfloats) {
+        for (int i = lane * 32; i < nfloats; i += 32 * 32)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(base + i));
+      };
+      pf(p.z_pre + bp * Hd, Hd);
+      pf(p.x_pre + bp * Hd, Hd);
+      pf(p.post_logit + bp * SC + (size_t)cb * C, C);
+      if (p.g_post_stoch) pf(p.g_post_stoch + bp * SC + (size_t)cb * C, C);
+      if (p.g_post_logit) pf(p.g_post_logit + bp * SC + (size_t)cb * C, C);
+      if (cb == 0) {
+        pf(p.g_pre + bp * D3, D3);
+        pf(p.hprev + bp * D, D);
+        pf(p.dh_prior + bp * D, D);
+        if (p.g_deter) pf(p.g_deter + bp * D, D);
+      }
+    }
     // ---------------- phase 1a: straight-through backward of the posterior sample ------------
     if (half == 0 && ract) {
       const bool valid = lane < C;
@@ -188,20 +225,24 @@ __global__ void __launch_bounds__(PO_THREADS, 1) observe_persistent_bwd_kernel(P
     pb_stamp(p, t, 2);
     // ---------------- phase 2: LN+SiLU backward of z rows; dh_z = d_z_pre W_obs_d ------------
     {
-      if (ract && half == 0) {
-        float pre[HV], dout[HV];
+      {
+        constexpr int HV2 = (HV + 1) / 2;
+        float pre[HV2], dout[HV2];
+        const int nh = Hd >> 1;
 #pragma unroll
-        for (int i = 0; i < HV; ++i) {
-          const int j = lane + 32 * i;
-          pre[i] = j < Hd ? p.z_pre[bt * Hd + j] : 0.f;
-          dout[i] = j < Hd ? __ldcg(p.d_z + (size_t)b * Hd + j) : 0.f;
+        for (int i = 0; i < HV2; ++i) {
+          const int j = half * nh + lane + 32 * i;
+          const bool on = ract && lane + 32 * i < nh;
+          pre[i] = on ? p.z_pre[bt * Hd + j] : 0.f;
+          dout[i] = on ? __ldcg(p.d_z + (size_t)b * Hd + j) : 0.f;
         }
         float* rrow = rows + (size_t)rl * Hd;
         const bool wr = cb == 0;
-        warp_ln_silu_bwd<HV>(pre, dout, Hd, lane, lzg, lzb, p.eps, [&](int j, float dp_, float dl_) {
-          rrow[j] = dp_;
-          if (wr) { p.d_z_pre[bt * Hd + j] = dp_; p.d_z_ln[bt * Hd + j] = dl_; }
-        });
+        pair_ln_silu_bwd<HV2>(ract, pre, dout, Hd, lane, half, lzg, lzb, p.eps, pr2 + rl * 8,
+                              [&](int j, float dp_, float dl_) {
+                                rrow[j] = dp_;
+                                if (wr) { p.d_z_pre[bt * Hd + j] = dp_; p.d_z_ln[bt * Hd + j] = dl_; }
+                              });
       }
       __syncthreads();
       const int cl = lane & 15, kq = half * 2 + (lane >> 4);
@@ -328,20 +369,24 @@ __global__ void __launch_bounds__(PO_THREADS, 1) observe_persistent_bwd_kernel(P
     // ---------------- phase 4: LN+SiLU backward of x rows; d stoch_prev of group cb; routing --
     {
       const bool first = ract ? (p.first_eff[bt] != 0.f) : false;
-      if (ract && half == 0) {
-        float pre[HV], dout[HV];
+      {
+        constexpr int HV2 = (HV + 1) / 2;
+        float pre[HV2], dout[HV2];
+        const int nh = Hd >> 1;
 #pragma unroll
-        for (int i = 0; i < HV; ++i) {
-          const int j = lane + 32 * i;
-          pre[i] = j < Hd ? p.x_pre[bt * Hd + j] : 0.f;
-          dout[i] = j < Hd ? __ldcg(p.dxh + (size_t)b * HD + j) : 0.f;
+        for (int i = 0; i < HV2; ++i) {
+          const int j = half * nh + lane + 32 * i;
+          const bool on = ract && lane + 32 * i < nh;
+          pre[i] = on ? p.x_pre[bt * Hd + j] : 0.f;
+          dout[i] = on ? __ldcg(p.dxh + (size_t)b * HD + j) : 0.f;
         }
         float* rrow = rows + (size_t)rl * Hd;
         const bool wr = cb == 0;
-        warp_ln_silu_bwd<HV>(pre, dout, Hd, lane, lxg, lxb, p.eps, [&](int j, float dp_, float dl_) {
-          rrow[j] = dp_;
-          if (wr) { p.d_x_pre[bt * Hd + j] = dp_; p.d_x_ln[bt * Hd + j] = dl_; }
-        });
+        pair_ln_silu_bwd<HV2>(ract, pre, dout, Hd, lane, half, lxg, lxb, p.eps, pr2 + rl * 8,
+                              [&](int j, float dp_, float dl_) {
+                                rrow[j] = dp_;
+                                if (wr) { p.d_x_pre[bt * Hd + j] = dp_; p.d_x_ln[bt * Hd + j] = dl_; }
+                              });
       }
       if (ract) {
         // reset routing of the deter gradient (this block's rows, once: CTAs with cb == 0)

@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(PO_THREADS, 1) observe_persistent_fwd_kernel(P
     // ---------------- phase B: GRU pre-activations, own columns ----------------
     if (gn > 0) {
       float* gp = p.g_pre;
-      gemv16<true>(Wg, gn, Kg, p.x + (size_t)t * Hd, T * Hd, Hd, p.hprev + (size_t)t * D, T * D, B,
+      gemv16<true, 6, 1>(Wg, gn, Kg, p.x + (size_t)t * Hd, T * Hd, Hd, p.hprev + (size_t)t * D, T * D, B,
                    part, [&](int m, int c, float r) {
                      gp[((size_t)m * T + t) * D3 + g0 + c] = r;
                    });

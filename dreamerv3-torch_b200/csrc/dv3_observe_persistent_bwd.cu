@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(PO_THREADS, 1) observe_persistent_bwd_kernel(P
     // ---------------- phase 1b: d_z = d_post_logit W_os, own columns, all rows ---------------
     if (zn > 0) {
       float* dz = p.d_z;
-      gemv16<true>(Wz, zn, SC, p.d_post_logit + (size_t)t * SC, T * SC, SC, nullptr, 0, B, part,
+      gemv16<true, 4, 1>(Wz, zn, SC, p.d_post_logit + (size_t)t * SC, T * SC, SC, nullptr, 0, B, part,
                    [&](int m, int c, float r) { dz[(size_t)m * Hd + z0 + c] = r; });
     }
     grid_barrier(p.bar, G, gen);
@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(PO_THREADS, 1) observe_persistent_bwd_kernel(P
     if (xn > 0) {
       float* dxh = p.dxh;
       const float* dhd = p.dhdir;
-      gemv16<true>(Wx, xn, D3, p.d_g_pre + (size_t)t * D3, T * D3, D3, nullptr, 0, B, part,
+      gemv16<true, 4, 1>(Wx, xn, D3, p.d_g_pre + (size_t)t * D3, T * D3, D3, nullptr, 0, B, part,
                    [&](int m, int c, float r) {
                      const int n = x0 + c;
                      if (n >= Hd) r += __ldcg(dhd + (size_t)m * D + (n - Hd));

@@ -34,57 +34,71 @@ __device__ __forceinline__ float4 load4(const float* p) {
 }
 
 // out[m][c] = sum_k Ws[c*K + k] * in[m][k] for m < B <= 16, c < ncols; in = [in1 (K1) | in2];
-// K split over all threads, weights from smem, 96 partials folded by butterfly + smem.
-template <bool GLOBAL_IN, typename Epi>
+// K split over all threads (k-quads of 4), weights from smem, the 16*CP partial sums of a column
+// pass folded by a shuffle butterfly + shared memory.
+//   CP: columns per pass (6 -> 96 accumulators; 4 when few columns are owned)
+//   NQ: k-quads a thread keeps in registers; when K/4 <= NQ*256 the inputs are loaded from L2
+//       exactly once (all loads in flight together) and reused by every column pass -- otherwise
+//       they are re-read per pass and per quad, one L2 round trip each.
+template <bool GLOBAL_IN, int CP, int NQ, typename Epi>
 __device__ __forceinline__ void gemv16(const float* Ws, int ncols, int K, const float* in1, int ld1,
                                        int K1, const float* in2, int ld2, int B, float* part,
                                        Epi epi) {
+  constexpr int NV = PO_ROWS * CP, PL = NV / 32;     // partials per thread / per lane after the fold
+  static_assert(NV % 32 == 0 && NV <= PO_NV, "gemv16: CP must be 2, 4 or 6");
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const bool once = (K >> 2) <= PO_THREADS;      // one k-quad per thread: load the inputs once
-  float4 a[PO_ROWS];
-  if (once) {
-    const int k = tid << 2;
-    const bool live = k < K;
+  const int nq = K >> 2;
+  const bool once = nq <= NQ * PO_THREADS;
+  float4 a[NQ][PO_ROWS];
+  auto load_quad = [&](int q, float4 (&dst)[PO_ROWS]) {
+    const int k = q << 2;
+    const bool live = q < nq;
     const float* src = live ? ((k < K1) ? in1 + k : in2 + (k - K1)) : in1;
     const int ld = (k < K1) ? ld1 : ld2;
 #pragma unroll
     for (int m = 0; m < PO_ROWS; ++m)
-      a[m] = (live && m < B) ? load4<GLOBAL_IN>(src + (size_t)m * ld) : make_float4(0.f, 0.f, 0.f, 0.f);
+      dst[m] = (live && m < B) ? load4<GLOBAL_IN>(src + (size_t)m * ld) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  if (once) {
+#pragma unroll
+    for (int j = 0; j < NQ; ++j) load_quad(tid + j * PO_THREADS, a[j]);
   }
-  for (int cb = 0; cb < ncols; cb += PO_CP) {
-    float acc[PO_NV];
+  for (int cb = 0; cb < ncols; cb += CP) {
+    float acc[NV];
 #pragma unroll
-    for (int i = 0; i < PO_NV; ++i) acc[i] = 0.f;
-#pragma unroll 1
-    for (int q = tid; q < (K >> 2); q += PO_THREADS) {
+    for (int i = 0; i < NV; ++i) acc[i] = 0.f;
+    auto fma_quad = [&](int q, const float4 (&av)[PO_ROWS]) {
       const int k = q << 2;
-      if (!once) {
-        const float* src;
-        int ld;
-        if (k < K1) { src = in1 + k; ld = ld1; } else { src = in2 + (k - K1); ld = ld2; }
 #pragma unroll
-        for (int m = 0; m < PO_ROWS; ++m)
-          a[m] = (m < B) ? load4<GLOBAL_IN>(src + (size_t)m * ld) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-#pragma unroll
-      for (int c = 0; c < PO_CP; ++c) {
-        const float4 w = (cb + c < ncols)
+      for (int c = 0; c < CP; ++c) {
+        const float4 w = (cb + c < ncols && q < nq)
                              ? *reinterpret_cast<const float4*>(Ws + (size_t)(cb + c) * K + k)
                              : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int m = 0; m < PO_ROWS; ++m) {
-          float s = acc[m * PO_CP + c];
-          s = fmaf(a[m].x, w.x, s);
-          s = fmaf(a[m].y, w.y, s);
-          s = fmaf(a[m].z, w.z, s);
-          s = fmaf(a[m].w, w.w, s);
-          acc[m * PO_CP + c] = s;
+          float s = acc[m * CP + c];
+          s = fmaf(av[m].x, w.x, s);
+          s = fmaf(av[m].y, w.y, s);
+          s = fmaf(av[m].z, w.z, s);
+          s = fmaf(av[m].w, w.w, s);
+          acc[m * CP + c] = s;
         }
       }
-    }
-    // butterfly fold 96 -> 3 per lane (lane L ends with indices 3L .. 3L+2)
+    };
+    if (once) {
 #pragma unroll
-    for (int off = 16, nv = PO_NV; off > 0; off >>= 1, nv >>= 1) {
+      for (int j = 0; j < NQ; ++j)
+        if (tid + j * PO_THREADS < nq) fma_quad(tid + j * PO_THREADS, a[j]);
+    } else {
+#pragma unroll 1
+      for (int q = tid; q < nq; q += PO_THREADS) {
+        load_quad(q, a[0]);
+        fma_quad(q, a[0]);
+      }
+    }
+    // butterfly fold NV -> PL per lane (lane L ends with indices PL*L .. PL*L + PL-1)
+#pragma unroll
+    for (int off = 16, nv = NV; off > 0; off >>= 1, nv >>= 1) {
       const bool up = (lane & off) != 0;
       const int half = nv >> 1;
 #pragma unroll
@@ -95,13 +109,13 @@ __device__ __forceinline__ void gemv16(const float* Ws, int ncols, int K, const 
       }
     }
 #pragma unroll
-    for (int j = 0; j < 3; ++j) part[warp * PO_NV + lane * 3 + j] = acc[j];
+    for (int j = 0; j < PL; ++j) part[warp * NV + lane * PL + j] = acc[j];
     __syncthreads();
-    if (tid < PO_NV) {
+    if (tid < NV) {
       float r = 0.f;
 #pragma unroll
-      for (int w2 = 0; w2 < PO_WARPS; ++w2) r += part[w2 * PO_NV + tid];
-      const int m = tid / PO_CP, c = cb + tid % PO_CP;
+      for (int w2 = 0; w2 < PO_WARPS; ++w2) r += part[w2 * NV + tid];
+      const int m = tid / CP, c = cb + tid % CP;
       if (m < B && c < ncols) epi(m, c, r);
     }
     __syncthreads();

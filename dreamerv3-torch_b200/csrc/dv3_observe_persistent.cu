@@ -236,8 +236,8 @@ __global__ void __launch_bounds__(PO_THREADS, 1) observe_persistent_fwd_kernel(P
     po_stamp(p, t, 6);
 
     // ------- phase E.  CTA (group, row block): two warps per row, lane = class.  Each warp
-    // normalises the whole z row into its own smem row and dots its half of Hd; the pair meets
-    // in smem, then the unimix draw -------
+    // normalises and dots its own half of the z row (the serial expf / divide chain per lane is
+    // what these phases cost); row sums and partial logits meet in smem, then the unimix draw ---
     {
       const int rl = warp & 3, half = warp >> 2;
       const bool act = rl < rEn;
@@ -245,39 +245,47 @@ __global__ void __launch_bounds__(PO_THREADS, 1) observe_persistent_fwd_kernel(P
       const size_t bt = (size_t)b * T + t;
       const bool valid = lane < C;
       float uu = 1.f, a0 = 0.f, a1 = 0.f;
+      // LN + SiLU of the z row, split over the pair: each warp normalises the half of the row it
+      // will dot against W_os (columns half*Hd/2 ..), the two row sums meet in shared memory
+      if (act && half == 0 && valid) uu = __ldcs(p.u_post + (((size_t)t * B + b) * S + gE) * C + lane);
+      const int nh = Hd >> 1, j0 = half * nh;
+      float zv[16];
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        zv[i] = (act && lane + 32 * i < nh) ? __ldcg(p.z_pre + bt * Hd + j0 + lane + 32 * i) : 0.f;
+        s += zv[i];
+      }
+      s = warp_sum(s);
+      if (act && lane == 0) red[rl * 8 + half] = s;
+      __syncthreads();
+      const float mean = (red[rl * 8] + red[rl * 8 + 1]) / (float)Hd;
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float dd = (lane + 32 * i < nh) ? zv[i] - mean : 0.f;
+        q = fmaf(dd, dd, q);
+      }
+      q = warp_sum(q);
+      if (act && lane == 0) red[rl * 8 + 2 + half] = q;
+      __syncthreads();
       if (act) {
-        if (half == 0 && valid) uu = __ldcs(p.u_post + (((size_t)t * B + b) * S + gE) * C + lane);
-        float zv[32];
-        float s = 0.f;
+        const float rstd = 1.f / sqrtf((red[rl * 8 + 2] + red[rl * 8 + 3]) / (float)Hd + p.eps);
+        float* zr = zs + (size_t)rl * Hd;
+        const bool wr = gE == 0;
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          zv[i] = (lane + 32 * i < Hd) ? __ldcg(p.z_pre + bt * Hd + lane + 32 * i) : 0.f;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) s += zv[i];
-        const float mean = warp_sum(s) / (float)Hd;
-        float q = 0.f;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float dd = (lane + 32 * i < Hd) ? zv[i] - mean : 0.f;
-          q = fmaf(dd, dd, q);
-        }
-        const float rstd = 1.f / sqrtf(warp_sum(q) / (float)Hd + p.eps);
-        float* zr = zs + (size_t)warp * Hd;
-        const bool wr = gE == 0 && half == 0;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int j = lane + 32 * i;
-          if (j < Hd) {
+        for (int i = 0; i < 16; ++i) {
+          const int j = j0 + lane + 32 * i;
+          if (lane + 32 * i < nh) {
             const float y = siluf_(fmaf((zv[i] - mean) * rstd, lzg[j], lzb[j]));
             zr[j] = y;
             if (wr) p.z[bt * Hd + j] = y;
           }
         }
         __syncwarp();
-        const int k0 = half * (Hd >> 1);
-        const float* wrow = Ws + (size_t)min(lane, C - 1) * (Hd + 4) + k0;
-        const float* x = zr + k0;
-        for (int k = 0; k < (Hd >> 1); k += 4) {
+        const float* wrow = Ws + (size_t)min(lane, C - 1) * (Hd + 4) + j0;
+        const float* x = zr + j0;
+        for (int k = 0; k < nh; k += 4) {
           const float4 w = *reinterpret_cast<const float4*>(wrow + k);
           const float4 xv = *reinterpret_cast<const float4*>(x + k);
           a0 = fmaf(xv.x, w.x, a0); a1 = fmaf(xv.y, w.y, a1);

@@ -361,6 +361,9 @@ def run_ours(args):
                                f"H=15 imagination from 1024 starts, fp32, WM+actor+critic Adam updates",
                    "suite": args.suite, "batch": [B, T], "horizon": cfg.imag_horizon,
                    "parallelism": f"dp{world}",
+                   "why_this_config": "the north star quotes its target at dmc_proprio sizes; dmc_vision / atari100k "
+                                      "(--suite) have the same RSSM / imagination sizes (embed 4096) and add conv "
+                                      "encoder/decoder stacks that SURVEY 8f ranks as a later row (cuDNN here)",
                    "l2": "no explicit flush: one step touches ~75 MB of weights+Adam state x3 and >1 GB of "
                          "activations, far above the 126 MB L2"},
         "clocks": sampler.summary() if sampler else None,

@@ -6,8 +6,8 @@
 //        128-bit weight / activation load of the CTA in flight at once, butterfly + smem fold.
 //   * M = 1024+ rows (imagination, bulk backward): a real contraction.
 //     -> linear_tiled_kernel: 128x64x16 register-tiled SIMT GEMM (8x4 per thread), register
-//        staged double buffering.  This is the exact-fp32 path used for parity; the tcgen05
-//        split-bf16 kernel (dv3_umma.cu) replaces it where the tolerance allows.
+//        staged double buffering.  Plain fp32 FMA path: used below 64 rows and when K % 4 != 0;
+//        everything else goes to the tcgen05 3xTF32 kernels (dv3_umma2.cu / dv3_umma2x.cu).
 #include "dv3_common.cuh"
 
 namespace dv3 {

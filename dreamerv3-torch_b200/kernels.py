@@ -2,8 +2,13 @@
 
 Each Function allocates its outputs / saved activations / workspace as torch tensors (the
 library owns no memory), enqueues the kernels on torch's current stream and, in backward,
-turns the per-row deltas the recurrent kernels return into parameter gradients with plain
-contractions over all rows (dW = delta^T @ input) -- those do not sit inside a time loop.
+turns the per-row deltas the recurrent kernels return into parameter gradients with split-K
+tensor-core contractions over all rows (dW = delta^T @ input) -- those do not sit inside a time
+loop.
+
+Every contraction goes through ``gemm_tc`` on ``Split`` operands (tf32 hi/lo planes): planes are
+made once per tensor -- by the kernel that produces the activation, or ``split`` -- and reused by
+the forward product and both backward products in either storage order.
 """
 from __future__ import annotations
 

@@ -303,6 +303,10 @@ def run_ours(args):
     # ---- roofline pass: the same step, eagerly, with CUDA events around every GEMM launch
     # (events cannot be recorded per kernel while a graph replays) ------------------------
     psteps = min(args.steps, 5)
+    try:    # the eager pass runs on the default stream after a side-stream capture: expected
+        torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+    except AttributeError:
+        pass
     step(resident)
     stage("first eager step after graph done")
     barrier()

@@ -380,6 +380,7 @@ def run_ours(args):
                       "CTAs: every imagination-step and bulk-row contraction, y / dx / dW; dominant by time)",
             "bound": "tensor", "achieved": ach, "peak": peaks["tf"], "unit": "TFLOP/s",
             "frac": ach / peaks["tf"], "traffic": None, "peak_source": peaks["src"],
+            "ceiling_3xtf32": peaks["tf"] / 6.0, "frac_of_3xtf32_ceiling": ach / (peaks["tf"] / 6.0),
             "flops": "algorithmic 2*M*N*K per launch (fp32 result); the kernel issues 3 tf32 MMAs per product, "
                      "so the tensor pipe does 3x this against a tf32 peak of half the bf16 figure",
             "timed_in": f"separate eager pass of {psteps} identical steps ({eager_ms:.2f} ms/step), CUDA events "
@@ -394,7 +395,10 @@ def run_ours(args):
         del graph
         torch.cuda.empty_cache()
         try:
-            line["large_imagination"] = large_imagination(pkg, device)
+            li = large_imagination(pkg, device)
+            li["gemm_frac_of_measured_bf16_peak"] = li["gemm_fp32_tflops"] / peaks["tf"]
+            li["gemm_frac_of_3xtf32_ceiling"] = li["gemm_fp32_tflops"] / (peaks["tf"] / 6.0)
+            line["large_imagination"] = li
         except Exception as e:      # informational only
             line["large_imagination"] = {"error": str(e)[:160]}
     if world == 1 and not args.no_cpu_baseline:

@@ -334,8 +334,8 @@ class Optimizer:
     (tools.py:760-776): zero_grad -> backward -> [DP allreduce] -> clip -> (wd) -> step.
 
     On CUDA the parameters of one optimizer are re-homed into ONE flat fp32 buffer (each
-    parameter becomes a view; ``state_dict`` names and values are unchanged), their ``.grad``s are
-    persistent views of a second flat buffer that autograd accumulates into, and clip + Adam run
+    parameter becomes a view; ``state_dict`` names and values are unchanged), the gradients are
+    gathered into a second flat buffer by one batched copy after backward, and clip + Adam run
     as the fused ``dv3_adam_clip_step`` (three launches; step counter on the device, so the call
     is graph-capturable).  The data-parallel allreduce then runs on the flat gradient buffer
     directly.  CPU parameters (the gloo tests) keep the torch.optim.Adam path."""
@@ -376,13 +376,17 @@ class Optimizer:
         self._step = torch.zeros(1, dtype=torch.float32, device=dev)
         self._ctl = torch.zeros(4, dtype=torch.float32, device=dev)
         self._scratch = torch.empty(1024, dtype=torch.float32, device=dev)
+        self._zero_like, self._pads = [], []
         with torch.no_grad():
             for p, off in zip(self._params, self._offsets):
                 n = p.numel()
                 view = self._fp[off:off + n].view(p.shape)
                 view.copy_(p.data)
                 p.data = view
-                p.grad = self._fg[off:off + n].view(p.shape)
+                p.grad = None
+                gap = ((n + 3) & ~3) - n
+                self._zero_like.append(torch.zeros(n, dtype=torch.float32, device=dev))
+                self._pads.append(torch.zeros(gap, dtype=torch.float32, device=dev) if gap else None)
 
     def _views(self, flat):
         return [flat[off:off + p.numel()].view(p.shape) for p, off in zip(self._params, self._offsets)]
@@ -440,11 +444,20 @@ class Optimizer:
             self._opt.zero_grad(set_to_none=True)
             metrics[f"{self._name}_grad_norm"] = norm.detach()
             return metrics
-        self._fg.zero_()
-        for p, g in zip(params, self._views(self._fg)):
-            if p.grad is None or p.grad.data_ptr() != g.data_ptr():
-                p.grad = g                                 # someone reset it (set_to_none)
+        # Gradients are produced as fresh tensors (autograd hands the first gradient of a leaf over
+        # without a kernel; accumulating into persistent views would cost one add launch per
+        # parameter) and gathered into the flat buffer by one batched copy.
+        for p in params:
+            p.grad = None
         loss.backward(retain_graph=retain_graph)
+        pieces = []
+        for p, z, pad in zip(params, self._zero_like, self._pads):
+            pieces.append(p.grad.reshape(-1) if p.grad is not None else z)
+            if pad is not None:
+                pieces.append(pad)
+        torch.cat(pieces, out=self._fg)
+        for p in params:
+            p.grad = None
         if self._sync is not None:
             self._sync.flat(self._fg)
         L_ = K.L

@@ -55,5 +55,9 @@ for k, v in agg.items():
              "dv3 other" if "dv3::" in k else "torch gemm" if ("gemm" in k or "cutlass" in k) else "torch other")
     groups[gname] += v[1] / 2 / 1e3
 print({k: round(v, 2) for k, v in groups.items()})
+print("---- non-library kernels ----")
+for k, v in sorted(((k, v) for k, v in agg.items() if "dv3::" not in k), key=lambda kv: -kv[1][1])[:40]:
+    print(f"{v[1]/2/1e3:8.3f} ms  n={v[0]//2:5d} avg={v[1]/v[0]:7.1f}us  {k[:150]}")
+print("---- all ----")
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:45]:
     print(f"{v[1]/2/1e3:8.3f} ms  n={v[0]//2:5d} avg={v[1]/v[0]:7.1f}us  {k[:100]}")

@@ -351,8 +351,11 @@ int dv3_linear_tc_fwd(const float* A, int32_t lda, int32_t transA, const float* 
  * accumulate: bit 0 = add into C; bit 1 = allow split-K (deep contractions with few output tiles
  * -- the dW products -- are partitioned along K and combined with fp32 atomics; the summation
  * order is then not fixed, so callers that need run-to-run bit-identical results leave it 0).
- * Persistent kernel (grid = min(tiles, SMs)), 128 x {128,64,32} tiles, TMA 128B-swizzled stages,
- * fp32 accumulation in TMEM promoted to registers every 128 k. */
+ * Persistent kernels: single-CTA 128 x {128,64,32} tiles (dv3_umma2.cu) or cta_group::2 CTA pairs
+ * with 256 x {128,64} tiles (dv3_umma2x.cu), chosen per shape by a cost model; TMA 128B-swizzled
+ * stages, fp32 accumulation in TMEM promoted to registers every 128 k.
+ * Replaces: every nn.Linear product of the path (networks.py:48-78 RSSM layers, 623-655 MLP,
+ * 742-768 GRUCell) and the dx / dW matmuls autograd derives from them. */
 typedef struct {
   const float* hi;
   const float* lo;
@@ -393,7 +396,8 @@ int dv3_ln_silu_bwd_split(const float* pre, int32_t ld, const float* g, const fl
                           float* d_ln, int32_t ldp, float* hi, float* lo, int32_t lds,
                           void* stream);
 /* LayerNorm affine-parameter gradients over all M rows: dg[j] = sum_r d_ln[r,j]*xhat[r,j],
- * db[j] = sum_r d_ln[r,j]; xhat is recomputed from the saved pre-LN rows.  n <= 2048. */
+ * db[j] = sum_r d_ln[r,j]; xhat is recomputed from the saved pre-LN rows.  n <= 2048.
+ * (autograd of nn.LayerNorm's weight / bias, networks.py:56, 628, 758) */
 int dv3_ln_param_grads(const float* pre, int32_t ld, const float* d_ln, int32_t ldl, float eps,
                        int32_t M, int32_t n, float* dg, float* db, void* stream);
 /* LayerNorm-GRU gate block (networks.py:760-768): parts = LN_3D(g_pre); r = sig(p0);

@@ -507,6 +507,13 @@ int tc_gemm_ops(const TcOperand& A1, int K1, const TcOperand* A2, int K2, const 
     allow_pair = (e && e[0] == '0') ? 0 : 1;
   }
   pick_shape(M, N, nk_all, (accumulate & 2) != 0, allow_pair && !raw, B.mn, &BN, &splitk, &pair);
+  if (const char* f = getenv("DV3_TC_FORCE")) {       // experiment knob: "<BN>,<pair>"
+    int fb = 0, fp = 0;
+    if (sscanf(f, "%d,%d", &fb, &fp) == 2 && (fb == 32 || fb == 64 || fb == 128) &&
+        !(fp && (fb == 32 || raw || M <= G2_BM))) {
+      BN = fb; pair = fp; splitk = 1;
+    }
+  }
   if (pair)
     return tc_gemm_pair(A1, K1, A2, K2, B, bias, addend, ldadd, C, ldc, M, N, accumulate, BN, splitk,
                         st);

@@ -86,7 +86,11 @@ __device__ __forceinline__ void load_tile(uint32_t dst, const CUtensorMap* map, 
   }
 }
 
-template <int BN, bool AMN, bool BMN, bool RAW>
+// WIDE: the B_hi and B_lo tiles sit back to back in a stage, so one MMA of width 2 BN computes
+// A_hi [B_hi; B_lo]^T -- hi*hi into columns [0, BN) and hi*lo into [BN, 2 BN) -- and a second of
+// width BN adds A_lo B_hi^T onto the latter: the A tile is read from shared memory twice per
+// k-step instead of three times.  Both halves are then chunk accumulators (drained together).
+template <int BN, bool AMN, bool BMN, bool RAW, bool WIDE = false>
 __global__ void __launch_bounds__(G2_THREADS, 1)
 umma2_gemm_kernel(const __grid_constant__ Gemm2Maps mp, Gemm2Args g) {
   constexpr bool MASK_HI = true;
@@ -177,8 +181,10 @@ umma2_gemm_kernel(const __grid_constant__ Gemm2Maps mp, Gemm2Args g) {
       for (int unit = blockIdx.x; unit < g.units; unit += gridDim.x, ++tl) {
         const int kb0 = (unit / g.tiles) * g.nkp, kb1 = min(nk, kb0 + g.nkp);
         const int lb = tl & 1;
-        mbar_wait(lempty0 + 8 * lb, ((tl >> 1) & 1) ^ 1);
-        tc_fence_after();
+        if (!WIDE) {
+          mbar_wait(lempty0 + 8 * lb, ((tl >> 1) & 1) ^ 1);
+          tc_fence_after();
+        }
         const uint32_t acc_lo = tmem_base + (2 + lb) * BN;
         int buf = 0;
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
@@ -194,7 +200,18 @@ umma2_gemm_kernel(const __grid_constant__ Gemm2Maps mp, Gemm2Args g) {
           const uint32_t au = unit0 + s * ST_U, bu = au + 2 * A_PU;
           const uint32_t acc_hi = tmem_base + buf * BN;
           const bool last = kin == G2_CH - 1 || kb == kb1 - 1;
-          if (issuer) {
+          if (issuer && WIDE) {
+            constexpr uint32_t idesc_w = (idesc & ~(0x3Fu << 17)) | ((uint32_t)(2 * BN >> 3) << 17);
+            const uint32_t acc = tmem_base + buf * (2 * BN);
+#pragma unroll
+            for (int k = 0; k < G2_BK / 8; ++k) {
+              const uint64_t ah = umma_desc_units<AMN>(au + k * A_KU);
+              const uint64_t al = umma_desc_units<AMN>(au + A_PU + k * A_KU);
+              const uint64_t bh = umma_desc_units<BMN>(bu + k * B_KU);    // [B_hi; B_lo] when 2 BN wide
+              umma_tf32(acc, ah, bh, idesc_w, (kin | k) != 0);
+              umma_tf32(acc + BN, al, bh, idesc, 1);
+            }
+          } else if (issuer) {
 #pragma unroll
             for (int k = 0; k < G2_BK / 8; ++k) {
               const uint64_t ah = umma_desc_units<AMN>(au + k * A_KU);
@@ -205,6 +222,8 @@ umma2_gemm_kernel(const __grid_constant__ Gemm2Maps mp, Gemm2Args g) {
               umma_tf32(acc_lo, ah, bl, idesc, 1);
               umma_tf32(acc_hi, ah, bh, idesc, (kin | k) != 0);
             }
+          }
+          if (issuer) {
             umma_commit(empty0 + 8 * s);
             if (last) umma_commit(tfull0 + 8 * buf);
           }
@@ -271,28 +290,39 @@ umma2_gemm_kernel(const __grid_constant__ Gemm2Maps mp, Gemm2Args g) {
         tc_fence_after();
 #pragma unroll
         for (int c0 = 0; c0 < HW; c0 += 32) {
+          if (WIDE) {
+            uint32_t v[32], w[32];
+            DV3_TMEM_LD32(v, lane_addr + (uint32_t)(buf * 2 * BN + c0));
+            DV3_TMEM_LD32(w, lane_addr + (uint32_t)(buf * 2 * BN + BN + c0));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sum[c0 + j] += __uint_as_float(v[j]) + __uint_as_float(w[j]);
+          } else {
+            uint32_t v[32];
+            DV3_TMEM_LD32(v, lane_addr + (uint32_t)(buf * BN + c0));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sum[c0 + j] += __uint_as_float(v[j]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+      }
+      if (!WIDE) {
+        // the last chunk commit also covers the cross-term accumulator of this tile
+#pragma unroll
+        for (int c0 = 0; c0 < HW; c0 += 32) {
           uint32_t v[32];
-          DV3_TMEM_LD32(v, lane_addr + (uint32_t)(buf * BN + c0));
+          DV3_TMEM_LD32(v, lane_addr + (uint32_t)((2 + lb) * BN + c0));
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
           for (int j = 0; j < 32; ++j) sum[c0 + j] += __uint_as_float(v[j]);
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+        if (lane == 0) mbar_arrive(lempty0 + 8 * lb);
       }
-      // the last chunk commit also covers the cross-term accumulator of this tile
-#pragma unroll
-      for (int c0 = 0; c0 < HW; c0 += 32) {
-        uint32_t v[32];
-        DV3_TMEM_LD32(v, lane_addr + (uint32_t)((2 + lb) * BN + c0));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-        for (int j = 0; j < 32; ++j) sum[c0 + j] += __uint_as_float(v[j]);
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(lempty0 + 8 * lb);
 
       if (row < g.M && g.splitk > 1) {
         // split-K: partial sums meet in C through fp32 atomics (C zeroed / preloaded by the host
@@ -397,10 +427,10 @@ int sm_count() {
   return sms;
 }
 
-template <int BN, bool AMN, bool BMN, bool RAW>
+template <int BN, bool AMN, bool BMN, bool RAW, bool WIDE = false>
 static int launch_umma2(const Gemm2Maps& mp, Gemm2Args g, double flops, cudaStream_t st) {
   using Cfg = G2Cfg<BN>;
-  auto kern = umma2_gemm_kernel<BN, AMN, BMN, RAW>;
+  auto kern = umma2_gemm_kernel<BN, AMN, BMN, RAW, WIDE>;
   static bool attr = false;
   if (!attr) {
     DV3_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -429,13 +459,13 @@ static int launch_umma2(const Gemm2Maps& mp, Gemm2Args g, double flops, cudaStre
   return 0;
 }
 
-template <int BN, bool RAW>
+template <int BN, bool RAW, bool WIDE = false>
 static int dispatch_major(bool amn, bool bmn, const Gemm2Maps& mp, const Gemm2Args& g, double flops,
                           cudaStream_t st) {
-  if (RAW || (!amn && !bmn)) return launch_umma2<BN, false, false, RAW>(mp, g, flops, st);
-  if (!amn && bmn) return launch_umma2<BN, false, true, false>(mp, g, flops, st);
-  if (amn && !bmn) return launch_umma2<BN, true, false, false>(mp, g, flops, st);
-  return launch_umma2<BN, true, true, false>(mp, g, flops, st);
+  if (RAW || (!amn && !bmn)) return launch_umma2<BN, false, false, RAW, WIDE>(mp, g, flops, st);
+  if (!amn && bmn) return launch_umma2<BN, false, true, false, WIDE>(mp, g, flops, st);
+  if (amn && !bmn) return launch_umma2<BN, true, false, false, WIDE>(mp, g, flops, st);
+  return launch_umma2<BN, true, true, false, WIDE>(mp, g, flops, st);
 }
 
 static bool tma_ok(const float* p, int ld) {
@@ -452,7 +482,8 @@ static void pick_shape(int M, int N, int nk, bool allow_splitk, bool allow_pair,
   // single-CTA tiles 128 x {128,64,32}; pair tiles 256 x {128,64} (dv3_umma2x.cu): per CTA and
   // k-block 120 / 100 KB of shared-memory traffic -> 940 / 780 clk
   const int bns[5] = {128, 64, 32, 128, 64};
-  const long long cost[5] = {1250, 940, 780, 940, 780};
+  // single-CTA tiles issue two MMAs per k-step (WIDE): 1130 (single wave) / 790 / 650 clk
+  const long long cost[5] = {1250, 790, 650, 940, 780};
   long long best_t = -1;
   *bn_out = 32; *splitk_out = 1; *pair_out = 0;
   for (int i = 0; i < 5; ++i) {
@@ -470,7 +501,8 @@ static void pick_shape(int M, int N, int nk, bool allow_splitk, bool allow_pair,
       if (sk < 1) sk = 1;
     }
     const int nkp = (nk + sk - 1) / sk;
-    long long t = (long long)((tiles * sk + slots - 1) / slots) * nkp * cost[i];
+    const long long ck = (i == 0 && tiles * sk <= slots) ? 1130 : cost[i];
+    long long t = (long long)((tiles * sk + slots - 1) / slots) * nkp * ck;
     if (sk > 1) t += 8000;
     if (pair) t += t / 50;                                 // ties go to the single-CTA kernel
     if (best_t < 0 || t < best_t) {
@@ -541,6 +573,21 @@ int tc_gemm_ops(const TcOperand& A1, int K1, const TcOperand* A2, int K2, const 
     if (BN == 128) return dispatch_major<128, true>(false, false, mp, g, flops, st);
     if (BN == 64) return dispatch_major<64, true>(false, false, mp, g, flops, st);
     return dispatch_major<32, true>(false, false, mp, g, flops, st);
+  }
+  // two-MMA issue: measured 12-20 % faster for BN = 32, 10-12 % for BN = 64, 5 % for BN = 128
+  // while the launch is a single wave, 1-3 % slower for multi-wave BN = 128 (tensor-pipe bound)
+  static int wide = -1;
+  if (wide < 0) {
+    const char* e = getenv("DV3_TC_WIDE");
+    wide = (e && e[0] == '0') ? 0 : 1;
+  }
+  const int units128 = ((M + G2_BM - 1) / G2_BM) * ((N + 127) / 128) * splitk;
+  if (wide) {
+    if (BN == 128 && units128 <= sm_count())
+      return dispatch_major<128, false, true>(A1.mn, B.mn, mp, g, flops, st);
+    if (BN == 128) return dispatch_major<128, false>(A1.mn, B.mn, mp, g, flops, st);
+    if (BN == 64) return dispatch_major<64, false, true>(A1.mn, B.mn, mp, g, flops, st);
+    return dispatch_major<32, false, true>(A1.mn, B.mn, mp, g, flops, st);
   }
   if (BN == 128) return dispatch_major<128, false>(A1.mn, B.mn, mp, g, flops, st);
   if (BN == 64) return dispatch_major<64, false>(A1.mn, B.mn, mp, g, flops, st);

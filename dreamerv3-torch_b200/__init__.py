@@ -11,8 +11,9 @@ Submodules mirror the reference's files: ``tools`` (lambda_return, DiscDist, One
 Optimizer), ``networks`` (RSSM, MLP, encoders / decoders), ``models`` (WorldModel,
 ImagBehavior).  ``kernels`` holds the autograd bindings and ``_lib`` the ctypes layer over
 libdv3_b200.so; there is no CPU fallback -- calling a hot-path op without the built library
-raises ``_lib.Dv3Error``.  ``graphs.TrainStepGraph`` replays a whole WM+AC train step as one CUDA graph.
+raises ``_lib.Dv3Error``.  ``graphs.TrainStepGraph`` replays a whole WM+AC train step as one CUDA
+graph; ``replay`` cuts the reference's replay windows and feeds them to HBM through pinned buffers.
 """
-from . import _lib, kernels, tools, networks, models, configs, graphs  # noqa: F401
+from . import _lib, kernels, tools, networks, models, configs, graphs, replay  # noqa: F401
 
-__all__ = ["_lib", "kernels", "tools", "networks", "models", "configs", "graphs"]
+__all__ = ["_lib", "kernels", "tools", "networks", "models", "configs", "graphs", "replay"]

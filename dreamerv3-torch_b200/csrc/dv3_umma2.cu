@@ -46,7 +46,17 @@ struct Gemm2Args {
   int m_fast;                            // tile order: consecutive tiles walk M (1) or N (0)
   int splitk, nkp, units;                // K partitions, k-blocks per partition, tiles * splitk
   int accumulate;
+  unsigned long long* stamps;            // debug: globaltimer stamps of CTA 0 (DV3_GEMM_TIMING=1)
 };
+
+#define G2_STAMP(slot)                                                      \
+  do {                                                                      \
+    if (g.stamps && blockIdx.x == 0) {                                      \
+      unsigned long long t_;                                                \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                \
+      g.stamps[slot] = t_;                                                  \
+    }                                                                       \
+  } while (0)
 
 template <int BN>
 struct G2Cfg {
@@ -90,10 +100,20 @@ __device__ __forceinline__ void load_tile(uint32_t dst, const CUtensorMap* map, 
 // A_hi [B_hi; B_lo]^T -- hi*hi into columns [0, BN) and hi*lo into [BN, 2 BN) -- and a second of
 // width BN adds A_lo B_hi^T onto the latter: the A tile is read from shared memory twice per
 // k-step instead of three times.  Both halves are then chunk accumulators (drained together).
-template <int BN, bool AMN, bool BMN, bool RAW, bool WIDE = false>
+// SK > 1: the launch is one wave of clusters of SK CTAs; the CTAs of a cluster take the K
+// partitions of ONE tile and combine their partial sums through distributed shared memory in a
+// fixed order (deterministic, no memset, no atomics): CTA r reduces columns [r BN/SK, (r+1) BN/SK).
+// This lets the skinny M = 1024 products use 128 x 128 tiles (2.2x less operand traffic per
+// flop than 128 x 32) and still fill the machine.
+template <int BN, bool AMN, bool BMN, bool RAW, bool WIDE = false, int SK = 1>
 __global__ void __launch_bounds__(G2_THREADS, 1)
 umma2_gemm_kernel(const __grid_constant__ Gemm2Maps mp, Gemm2Args g) {
   constexpr bool MASK_HI = true;
+  static_assert(SK == 1 || (!RAW && BN % (8 * SK) == 0), "cluster split-K: pre-split operands");
+  // SK mode: exactly one work unit per CTA, unit = tile + partition * tiles like split-K
+  const int unit_first = SK > 1 ? (int)(blockIdx.x / SK) + (int)(blockIdx.x % SK) * g.tiles
+                                : (int)blockIdx.x;
+  const int unit_step = SK > 1 ? g.units : (int)gridDim.x;
   using Cfg = G2Cfg<BN>;
   constexpr int ST = Cfg::STAGES;
   constexpr uint32_t A_BYTES = Cfg::A_BYTES, B_BYTES = Cfg::B_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES;
@@ -106,6 +126,7 @@ umma2_gemm_kernel(const __grid_constant__ Gemm2Maps mp, Gemm2Args g) {
                  tfull0 = empty0 + 8 * ST, tempty0 = tfull0 + 16, lempty0 = tempty0 + 16;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nk = g.nk;
+  if (threadIdx.x == 0) G2_STAMP(0);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < ST; ++s) {
@@ -134,12 +155,13 @@ umma2_gemm_kernel(const __grid_constant__ Gemm2Maps mp, Gemm2Args g) {
   // C when accumulating) may only be touched from here on
   pdl_wait();
   pdl_launch_dependents();
+  if (threadIdx.x == 0) G2_STAMP(1);
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
       int it = 0;
-      for (int unit = blockIdx.x; unit < g.units; unit += gridDim.x) {
+      for (int unit = unit_first; unit < g.units; unit += unit_step) {
         const int tile = unit % g.tiles, kb0 = (unit / g.tiles) * g.nkp;
         const int kb1 = min(nk, kb0 + g.nkp);
         const int tm = g.m_fast ? tile % g.tiles_m : tile / g.tiles_n;
@@ -161,6 +183,7 @@ umma2_gemm_kernel(const __grid_constant__ Gemm2Maps mp, Gemm2Args g) {
             load_tile<AMN>(base + A_BYTES, seg1 ? &mp.a1l : &mp.a2l, bar, ak, m0, G2_BM);
             load_tile<BMN>(base + 2 * A_BYTES + B_BYTES, &mp.bl, bar, wk, n0, BN);
           }
+          if (it == 0) G2_STAMP(2);
         }
       }
     }
@@ -178,7 +201,7 @@ umma2_gemm_kernel(const __grid_constant__ Gemm2Maps mp, Gemm2Args g) {
       const bool issuer = elect_one();
       const uint32_t unit0 = (smem_u32(smem) >> 4) & 0x3FFF;
       int it = 0, cc = 0, tl = 0;
-      for (int unit = blockIdx.x; unit < g.units; unit += gridDim.x, ++tl) {
+      for (int unit = unit_first; unit < g.units; unit += unit_step, ++tl) {
         const int kb0 = (unit / g.tiles) * g.nkp, kb1 = min(nk, kb0 + g.nkp);
         const int lb = tl & 1;
         if (!WIDE) {
@@ -197,6 +220,7 @@ umma2_gemm_kernel(const __grid_constant__ Gemm2Maps mp, Gemm2Args g) {
           }
           mbar_wait((RAW ? conv0 : full0) + 8 * s, ph);
           tc_fence_after();
+          if (it == 0 && issuer) G2_STAMP(3);
           const uint32_t au = unit0 + s * ST_U, bu = au + 2 * A_PU;
           const uint32_t acc_hi = tmem_base + buf * BN;
           const bool last = kin == G2_CH - 1 || kb == kb1 - 1;
@@ -226,6 +250,7 @@ umma2_gemm_kernel(const __grid_constant__ Gemm2Maps mp, Gemm2Args g) {
           if (issuer) {
             umma_commit(empty0 + 8 * s);
             if (last) umma_commit(tfull0 + 8 * buf);
+            if (kb == kb1 - 1) G2_STAMP(4);
           }
           if (last) ++cc;
           __syncwarp();
@@ -236,7 +261,7 @@ umma2_gemm_kernel(const __grid_constant__ Gemm2Maps mp, Gemm2Args g) {
     // ------------------------------ converters --------------------------------
     const int ct = threadIdx.x - G2_CONV_WARP0 * 32;     // 0..127
     int it = 0;
-    for (int unit = blockIdx.x; unit < g.units; unit += gridDim.x) {
+    for (int unit = unit_first; unit < g.units; unit += unit_step) {
       const int kb0 = (unit / g.tiles) * g.nkp, kb1 = min(nk, kb0 + g.nkp);
       for (int kb = kb0; kb < kb1; ++kb, ++it) {
         const int s = it % ST;
@@ -273,7 +298,7 @@ umma2_gemm_kernel(const __grid_constant__ Gemm2Maps mp, Gemm2Args g) {
     const int q = warp & 3, half = (warp - G2_EPI_WARP0) >> 2;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * HW);
     int cc = 0, tl = 0;
-    for (int unit = blockIdx.x; unit < g.units; unit += gridDim.x, ++tl) {
+    for (int unit = unit_first; unit < g.units; unit += unit_step, ++tl) {
       const int tile = unit % g.tiles, ks = unit / g.tiles;
       const int nchunks = (min(nk, (ks + 1) * g.nkp) - ks * g.nkp + G2_CH - 1) / G2_CH;
       const int tm = g.m_fast ? tile % g.tiles_m : tile / g.tiles_n;
@@ -288,6 +313,7 @@ umma2_gemm_kernel(const __grid_constant__ Gemm2Maps mp, Gemm2Args g) {
         const int buf = cc & 1;
         mbar_wait(tfull0 + 8 * buf, (cc >> 1) & 1);
         tc_fence_after();
+        if (c == nchunks - 1 && threadIdx.x == G2_EPI_WARP0 * 32) G2_STAMP(5);
 #pragma unroll
         for (int c0 = 0; c0 < HW; c0 += 32) {
           if (WIDE) {
@@ -324,7 +350,15 @@ umma2_gemm_kernel(const __grid_constant__ Gemm2Maps mp, Gemm2Args g) {
         if (lane == 0) mbar_arrive(lempty0 + 8 * lb);
       }
 
-      if (row < g.M && g.splitk > 1) {
+      if (threadIdx.x == G2_EPI_WARP0 * 32) G2_STAMP(6);
+      if (SK > 1) {
+        // cluster split-K: park the partial sums in shared memory (the pipeline stages are idle:
+        // this CTA has a single unit and its last MMA has completed); reduced after the role code
+        float* stg = reinterpret_cast<float*>(smem) + (size_t)(q * 32 + lane) * (BN + 4) + half * HW;
+#pragma unroll
+        for (int j = 0; j < HW; j += 4)
+          *reinterpret_cast<float4*>(stg + j) = make_float4(sum[j], sum[j + 1], sum[j + 2], sum[j + 3]);
+      } else if (row < g.M && g.splitk > 1) {
         // split-K: partial sums meet in C through fp32 atomics (C zeroed / preloaded by the host
         // side of the launch); bias and addend ride on partition 0
         float* crow = g.C + (size_t)row * g.ldc;
@@ -370,8 +404,73 @@ umma2_gemm_kernel(const __grid_constant__ Gemm2Maps mp, Gemm2Args g) {
       }
     }
   }
+  if (SK > 1) {
+    __syncthreads();
+    cluster_sync_all();                  // every partition's partial tile is parked
+    if (threadIdx.x == G2_EPI_WARP0 * 32) G2_STAMP(8);
+    if (warp >= G2_EPI_WARP0 && warp < G2_EPI_WARP0 + 8) {
+      constexpr int CW = BN / SK, PT = CW / 2;          // columns per CTA / per thread
+      const int rank = (int)cluster_ctarank();
+      const int te = threadIdx.x - G2_EPI_WARP0 * 32;   // 0..255
+      const int rl = te >> 1, c0 = rank * CW + (te & 1) * PT;
+      const int tile = (int)(blockIdx.x / SK);
+      const int tm = g.m_fast ? tile % g.tiles_m : tile / g.tiles_n;
+      const int tn = g.m_fast ? tile / g.tiles_m : tile % g.tiles_n;
+      const int row = tm * G2_BM + rl, n0 = tn * BN + c0;
+      const uint32_t local = smem_u32(reinterpret_cast<float*>(smem) + (size_t)rl * (BN + 4) + c0);
+      float acc[PT];
+#pragma unroll
+      for (int j = 0; j < PT; ++j) acc[j] = 0.f;
+#pragma unroll
+      for (int r = 0; r < SK; ++r) {
+        uint32_t ra;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local), "r"(r));
+#pragma unroll
+        for (int j = 0; j < PT; j += 4) {
+          float4 v;
+          asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                       : "r"(ra + j * 4));
+          acc[j] += v.x; acc[j + 1] += v.y; acc[j + 2] += v.z; acc[j + 3] += v.w;
+        }
+      }
+      if (row < g.M) {
+        float* crow = g.C + (size_t)row * g.ldc;
+        const float* arow = g.addend ? g.addend + (size_t)row * g.ldadd : nullptr;
+        const bool vec = ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) &&
+                         (n0 + PT <= g.N) && !g.accumulate && !arow;
+        if (vec) {
+#pragma unroll
+          for (int j = 0; j < PT; j += 4) {
+            float4 o = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+            if (g.bias) {
+              o.x += __ldg(g.bias + n0 + j); o.y += __ldg(g.bias + n0 + j + 1);
+              o.z += __ldg(g.bias + n0 + j + 2); o.w += __ldg(g.bias + n0 + j + 3);
+            }
+            *reinterpret_cast<float4*>(crow + n0 + j) = o;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < PT; ++j) {
+            const int col = n0 + j;
+            if (col < g.N) {
+              float r = acc[j];
+              if (g.bias) r += g.bias[col];
+              if (arow) r += arow[col];
+              if (g.accumulate) r += crow[col];
+              crow[col] = r;
+            }
+          }
+        }
+      }
+    }
+    if (threadIdx.x == G2_EPI_WARP0 * 32) G2_STAMP(9);
+    cluster_sync_all();                  // nobody's shared memory goes away under a peer's reads
+    if (threadIdx.x == G2_EPI_WARP0 * 32) G2_STAMP(10);
+  }
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) G2_STAMP(7);
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
                  ::"r"(tmem_base), "n"(Cfg::TMEM_COLS)
@@ -427,10 +526,14 @@ int sm_count() {
   return sms;
 }
 
-template <int BN, bool AMN, bool BMN, bool RAW, bool WIDE = false>
+// resident clusters of `sk` CTAs of the 128-wide kernel (0 = cluster launch unavailable)
+template <int SK>
+static int max_clusters_sk();
+
+template <int BN, bool AMN, bool BMN, bool RAW, bool WIDE = false, int SK = 1>
 static int launch_umma2(const Gemm2Maps& mp, Gemm2Args g, double flops, cudaStream_t st) {
   using Cfg = G2Cfg<BN>;
-  auto kern = umma2_gemm_kernel<BN, AMN, BMN, RAW, WIDE>;
+  auto kern = umma2_gemm_kernel<BN, AMN, BMN, RAW, WIDE, SK>;
   static bool attr = false;
   if (!attr) {
     DV3_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -446,12 +549,30 @@ static int launch_umma2(const Gemm2Maps& mp, Gemm2Args g, double flops, cudaStre
   g.m_fast = g.N > g.M ? 1 : 0;
   if (g.splitk < 1) g.splitk = 1;
   g.nkp = (g.nk + g.splitk - 1) / g.splitk;
-  g.splitk = (g.nk + g.nkp - 1) / g.nkp;           // no empty partition
+  if (SK == 1) g.splitk = (g.nk + g.nkp - 1) / g.nkp;   // no empty partition (a cluster tolerates them)
   g.units = g.tiles * g.splitk;
-  if (g.splitk > 1 && !g.accumulate)
+  if (SK == 1 && g.splitk > 1 && !g.accumulate)
     DV3_CHECK_CUDA(cudaMemset2DAsync(g.C, (size_t)g.ldc * 4, 0, (size_t)g.N * 4, g.M, st));
-  const int grid = g.units < sm_count() ? g.units : sm_count();
   const bool prof = prof_on();
+  if (SK > 1) {
+    DV3_REQUIRE(g.splitk == SK, DV3_ERR_BAD_SHAPE, "cluster split-K: %d partitions for SK=%d",
+                g.splitk, SK);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(g.units);
+    cfg.blockDim = dim3(G2_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = SK; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    if (prof) prof_begin(st);
+    DV3_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, mp, g));
+    if (prof) prof_end(st, 1, flops);
+    DV3_CHECK_LAUNCH("umma2_gemm_kernel<cluster split-K>");
+    return 0;
+  }
+  const int grid = g.units < sm_count() ? g.units : sm_count();
   if (prof) prof_begin(st);
   DV3_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(G2_THREADS), Cfg::SMEM, st, mp, g));
   if (prof) prof_end(st, 1, flops);
@@ -459,13 +580,36 @@ static int launch_umma2(const Gemm2Maps& mp, Gemm2Args g, double flops, cudaStre
   return 0;
 }
 
-template <int BN, bool RAW, bool WIDE = false>
+template <int BN, bool RAW, bool WIDE = false, int SK = 1>
 static int dispatch_major(bool amn, bool bmn, const Gemm2Maps& mp, const Gemm2Args& g, double flops,
                           cudaStream_t st) {
-  if (RAW || (!amn && !bmn)) return launch_umma2<BN, false, false, RAW, WIDE>(mp, g, flops, st);
-  if (!amn && bmn) return launch_umma2<BN, false, true, false, WIDE>(mp, g, flops, st);
-  if (amn && !bmn) return launch_umma2<BN, true, false, false, WIDE>(mp, g, flops, st);
-  return launch_umma2<BN, true, true, false, WIDE>(mp, g, flops, st);
+  if (RAW || (!amn && !bmn)) return launch_umma2<BN, false, false, RAW, WIDE, SK>(mp, g, flops, st);
+  if (!amn && bmn) return launch_umma2<BN, false, true, false, WIDE, SK>(mp, g, flops, st);
+  if (amn && !bmn) return launch_umma2<BN, true, false, false, WIDE, SK>(mp, g, flops, st);
+  return launch_umma2<BN, true, true, false, WIDE, SK>(mp, g, flops, st);
+}
+
+template <int SK>
+static int max_clusters_sk() {
+  static int n = -1;
+  if (n < 0) {
+    using Cfg = G2Cfg<128>;
+    auto kern = umma2_gemm_kernel<128, false, false, false, true, SK>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(sm_count() / SK * SK);
+    cfg.blockDim = dim3(G2_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = SK; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int m = 0;
+    if (cudaOccupancyMaxActiveClusters(&m, kern, &cfg) != cudaSuccess) m = 0;
+    cudaGetLastError();
+    n = m;
+  }
+  return n;
 }
 
 static bool tma_ok(const float* p, int ld) {
@@ -476,8 +620,12 @@ static bool tma_ok(const float* p, int ld) {
 // waves x k-blocks x (time per k-block).  The k-block time is set by shared-memory traffic (TMA
 // writes + UMMA operand reads at 128 B/clk: 160 / 120 / 100 KB per k-block for BN = 128 / 64 /
 // 32), measured 1250 / 940 / 780 clk.  Split-K pays a memset and an atomic epilogue.
-static void pick_shape(int M, int N, int nk, bool allow_splitk, bool allow_pair, bool b_mn,
-                       int* bn_out, int* splitk_out, int* pair_out) {
+static int max_clusters(int sk) {
+  return sk == 2 ? max_clusters_sk<2>() : sk == 4 ? max_clusters_sk<4>() : max_clusters_sk<8>();
+}
+
+static void pick_shape(int M, int N, int nk, bool allow_splitk, bool allow_pair, bool allow_csk,
+                       int* bn_out, int* splitk_out, int* pair_out, int* csk_out) {
   const int tm = (M + G2_BM - 1) / G2_BM, sms = sm_count();
   // single-CTA tiles 128 x {128,64,32}; pair tiles 256 x {128,64} (dv3_umma2x.cu): per CTA and
   // k-block 120 / 100 KB of shared-memory traffic -> 940 / 780 clk
@@ -485,12 +633,11 @@ static void pick_shape(int M, int N, int nk, bool allow_splitk, bool allow_pair,
   // single-CTA tiles issue two MMAs per k-step (WIDE): 1130 (single wave) / 790 / 650 clk
   const long long cost[5] = {1250, 790, 650, 940, 780};
   long long best_t = -1;
-  *bn_out = 32; *splitk_out = 1; *pair_out = 0;
+  *bn_out = 32; *splitk_out = 1; *pair_out = 0; *csk_out = 0;
   for (int i = 0; i < 5; ++i) {
     const bool pair = i >= 3;
     if (pair && (!allow_pair || M <= G2_BM)) continue;
     if (bns[i] > 32 && N <= bns[i] / 2) continue;          // mostly padding
-    (void)b_mn;
     const int slots = pair ? sms / 2 : sms;
     const int tiles = (pair ? (M + 2 * G2_BM - 1) / (2 * G2_BM) : tm) * ((N + bns[i] - 1) / bns[i]);
     int sk = 1;
@@ -507,6 +654,18 @@ static void pick_shape(int M, int N, int nk, bool allow_splitk, bool allow_pair,
     if (pair) t += t / 50;                                 // ties go to the single-CTA kernel
     if (best_t < 0 || t < best_t) {
       best_t = t; *bn_out = bns[i]; *splitk_out = sk; *pair_out = pair ? 1 : 0;
+    }
+  }
+  // 128 x 128 tiles with K partitioned over a cluster (one wave by construction); the reduction
+  // through distributed shared memory and the cluster launch cost about CSK_OVERHEAD clk
+  if (allow_csk) {
+    const int tiles = tm * ((N + 127) / 128);
+    for (int sk = 2; sk <= 8; sk *= 2) {
+      if (nk / sk < G2_CH || tiles > max_clusters(sk)) continue;
+      const long long t = (long long)((nk + sk - 1) / sk) * 1130 + 2500;
+      if (t < best_t) {
+        best_t = t; *bn_out = 128; *splitk_out = sk; *pair_out = 0; *csk_out = sk;
+      }
     }
   }
 }
@@ -532,18 +691,27 @@ int tc_gemm_ops(const TcOperand& A1, int K1, const TcOperand* A2, int K2, const 
   DV3_REQUIRE(!A2 || A2->mn == A1.mn, DV3_ERR_BAD_SHAPE, "tc_gemm: A segments differ in order");
   const int K = K1 + K2;
   const int nk_all = (K1 + G2_BK - 1) / G2_BK + (K2 + G2_BK - 1) / G2_BK;
-  int BN = 32, splitk = 1, pair = 0;
-  static int allow_pair = -1;
+  int BN = 32, splitk = 1, pair = 0, csk = 0;
+  static int allow_pair = -1, allow_csk = -1;
   if (allow_pair < 0) {
     const char* e = getenv("DV3_TC_PAIR");
     allow_pair = (e && e[0] == '0') ? 0 : 1;
+    e = getenv("DV3_TC_CSK");            // cluster split-K: opt-in until its fixed cost is paid down
+    allow_csk = (e && e[0] == '1') ? 1 : 0;
   }
-  pick_shape(M, N, nk_all, (accumulate & 2) != 0, allow_pair && !raw, B.mn, &BN, &splitk, &pair);
-  if (const char* f = getenv("DV3_TC_FORCE")) {       // experiment knob: "<BN>,<pair>"
-    int fb = 0, fp = 0;
-    if (sscanf(f, "%d,%d", &fb, &fp) == 2 && (fb == 32 || fb == 64 || fb == 128) &&
+  pick_shape(M, N, nk_all, (accumulate & 2) != 0, allow_pair && !raw, allow_csk && !raw, &BN,
+             &splitk, &pair, &csk);
+  if (const char* f = getenv("DV3_TC_FORCE")) {       // experiment knob: "<BN>,<pair>[,<cluster K>]"
+    int fb = 0, fp = 0, fc = 0;
+    const int got = sscanf(f, "%d,%d,%d", &fb, &fp, &fc);
+    if (got >= 2 && (fb == 32 || fb == 64 || fb == 128) &&
         !(fp && (fb == 32 || raw || M <= G2_BM))) {
-      BN = fb; pair = fp; splitk = 1;
+      BN = fb; pair = fp; splitk = 1; csk = 0;
+      const int tiles = ((M + G2_BM - 1) / G2_BM) * ((N + 127) / 128);
+      if (got == 3 && (fc == 2 || fc == 4 || fc == 8) && fb == 128 && !fp && !raw &&
+          nk_all / fc >= 1 && tiles <= max_clusters(fc)) {
+        csk = fc; splitk = fc;
+      }
     }
   }
   if (pair)
@@ -568,6 +736,7 @@ int tc_gemm_ops(const TcOperand& A1, int K1, const TcOperand* A2, int K2, const 
   g.K1 = K1; g.nk1 = (K1 + G2_BK - 1) / G2_BK; g.nk = g.nk1 + (K2 + G2_BK - 1) / G2_BK;
   g.accumulate = accumulate & 1;
   g.splitk = splitk;
+  if (const char* te = getenv("DV3_GEMM_TIMING")) g.stamps = te[0] == '1' ? po_timing_buffer() : nullptr;
   const double flops = 2.0 * M * N * K;
   if (raw) {
     if (BN == 128) return dispatch_major<128, true>(false, false, mp, g, flops, st);
@@ -581,6 +750,9 @@ int tc_gemm_ops(const TcOperand& A1, int K1, const TcOperand* A2, int K2, const 
     const char* e = getenv("DV3_TC_WIDE");
     wide = (e && e[0] == '0') ? 0 : 1;
   }
+  if (csk == 2) return dispatch_major<128, false, true, 2>(A1.mn, B.mn, mp, g, flops, st);
+  if (csk == 4) return dispatch_major<128, false, true, 4>(A1.mn, B.mn, mp, g, flops, st);
+  if (csk == 8) return dispatch_major<128, false, true, 8>(A1.mn, B.mn, mp, g, flops, st);
   const int units128 = ((M + G2_BM - 1) / G2_BM) * ((N + 127) / 128) * splitk;
   if (wide) {
     if (BN == 128 && units128 <= sm_count())

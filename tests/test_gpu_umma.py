@@ -156,3 +156,36 @@ def test_gemm_pair_kernel_is_used(pkg, device):
         torch.cuda.synchronize()
     names = [e.name for e in prof.events() if e.device_type.name == "CUDA"]
     assert any("umma2x_gemm_kernel" in n for n in names), names
+
+
+@pytest.mark.parametrize("force", ["32,0", "64,0", "128,0", "128,0,2", "128,0,4", "128,0,8"])
+@pytest.mark.parametrize("M,N,K", [(1024, 512, 512), (1000, 255, 1030), (1024, 1024, 96)])
+def test_gemm_forced_tilings_agree(pkg, device, monkeypatch, force, M, N, K):
+    """Every tiling of the single-CTA kernel -- the two-MMA issue at BN = 32 / 64 / 128 and the
+    cluster split-K mode (K over 2 / 4 / 8 CTAs of a cluster, partial tiles reduced through
+    distributed shared memory in a fixed order) -- against fp64, with bias + addend + accumulate
+    into a strided view, and bit-identical from run to run."""
+    monkeypatch.setenv("DV3_TC_FORCE", force)
+    g = torch.Generator().manual_seed(M + 3 * N + 5 * K)
+    Kp = (K + 3) // 4 * 4
+    a = torch.zeros(M, Kp); a[:, :K] = torch.randn(M, K, generator=g)
+    b = torch.zeros(N, Kp); b[:, :K] = torch.randn(N, K, generator=g) / K ** 0.5
+    a, b = a.to(device), b.to(device)
+    bias = torch.randn(N, generator=g).to(device)
+    add = torch.randn(M, N, generator=g).to(device)
+    ref = a.double() @ b.double().t()
+    As, Bs = pkg.kernels.split(a), pkg.kernels.split(b)
+    out = pkg.kernels.gemm_tc(As, Bs).clone()
+    assert float((out.double() - ref).abs().max() / ref.abs().max()) < 5e-6
+    assert torch.equal(out, pkg.kernels.gemm_tc(As, Bs))
+    big = torch.randn(M, N + 8, generator=g).to(device)
+    view = big[:, 4:4 + N]
+    base = view.clone()
+    pkg.kernels.gemm_tc(As, Bs, bias=bias, addend=add, out=view, accumulate=True)
+    ref2 = ref + bias.double() + add.double() + base.double()
+    assert float((view.double() - ref2).abs().max() / ref2.abs().max()) < 5e-6
+    # transposed storage of both operands
+    if M % 4 == 0 and N % 4 == 0:
+        At, Bt = pkg.kernels.split(a.t().contiguous()), pkg.kernels.split(b.t().contiguous())
+        out = pkg.kernels.gemm_tc(At, Bt, a_t=True, b_t=True)
+        assert float((out.double() - ref).abs().max() / ref.abs().max()) < 5e-6

@@ -84,6 +84,57 @@ struct Gemm2Maps {
   CUtensorMap a1h, a1l, a2h, a2l, bh, bl;   // raw mode uses a1h, a2h, bh only
 };
 
+// Four consecutive columns of one result row: + bias + addend (`extras`: only K partition 0 adds
+// them), then store, add into C, or -- split-K over CTAs -- fp32 atomics.
+__device__ __forceinline__ void g2_emit4(const Gemm2Args& g, int row, int col, float4 v, bool extras,
+                                         bool atomic, bool vec_ok) {
+  if (row >= g.M || col >= g.N) return;
+  float* cp = g.C + (size_t)row * g.ldc + col;
+  const float* bp = (g.bias && extras) ? g.bias + col : nullptr;
+  const float* ap = (g.addend && extras) ? g.addend + (size_t)row * g.ldadd + col : nullptr;
+  if (vec_ok && col + 4 <= g.N) {
+    if (bp) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(bp));
+      v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+    }
+    if (ap) {
+      const float4 a = *reinterpret_cast<const float4*>(ap);
+      v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+    }
+    if (atomic) {
+      atomicAdd(cp, v.x); atomicAdd(cp + 1, v.y); atomicAdd(cp + 2, v.z); atomicAdd(cp + 3, v.w);
+    } else {
+      if (g.accumulate) {
+        const float4 c = *reinterpret_cast<const float4*>(cp);
+        v.x += c.x; v.y += c.y; v.z += c.z; v.w += c.w;
+      }
+      *reinterpret_cast<float4*>(cp) = v;
+    }
+  } else {
+    const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (col + j < g.N) {
+        float r = e[j];
+        if (bp) r += bp[j];
+        if (ap) r += ap[j];
+        if (atomic) {
+          atomicAdd(cp + j, r);
+        } else {
+          if (g.accumulate) r += cp[j];
+          cp[j] = r;
+        }
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ bool g2_vec_ok(const Gemm2Args& g) {
+  return ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) &&
+         (!g.bias || (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0) &&
+         (!g.addend || ((g.ldadd & 3) == 0 && (reinterpret_cast<uintptr_t>(g.addend) & 15) == 0));
+}
+
 // one operand tile of `rows` rows for k-block starting at k0: K-major = one box [rows x 32 k],
 // MN-major = rows/32 boxes [32 k x 32 rows], 4 KB apart
 template <bool MN>
@@ -140,6 +191,11 @@ umma2_gemm_kernel(const __grid_constant__ Gemm2Maps mp, Gemm2Args g) {
       mbar_init(lempty0 + 8 * b, Cfg::EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&mp.a1h); prefetch_tensormap(&mp.bh);
+    if (!RAW) { prefetch_tensormap(&mp.a1l); prefetch_tensormap(&mp.bl); }
+    if (g.nk1 < g.nk) { prefetch_tensormap(&mp.a2h); if (!RAW) prefetch_tensormap(&mp.a2l); }
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
@@ -409,63 +465,41 @@ umma2_gemm_kernel(const __grid_constant__ Gemm2Maps mp, Gemm2Args g) {
     cluster_sync_all();                  // every partition's partial tile is parked
     if (threadIdx.x == G2_EPI_WARP0 * 32) G2_STAMP(8);
     if (warp >= G2_EPI_WARP0 && warp < G2_EPI_WARP0 + 8) {
-      constexpr int CW = BN / SK, PT = CW / 2;          // columns per CTA / per thread
+      // this CTA's share: columns [rank CW, (rank+1) CW) of all 128 rows, one float4 per thread
+      // and pass, consecutive lanes on consecutive 16 B of a row (coalesced both ways)
+      constexpr int CW = BN / SK, C4 = CW / 4, PER = G2_BM * C4 / 256;
       const int rank = (int)cluster_ctarank();
       const int te = threadIdx.x - G2_EPI_WARP0 * 32;   // 0..255
-      const int rl = te >> 1, c0 = rank * CW + (te & 1) * PT;
       const int tile = (int)(blockIdx.x / SK);
       const int tm = g.m_fast ? tile % g.tiles_m : tile / g.tiles_n;
       const int tn = g.m_fast ? tile / g.tiles_m : tile % g.tiles_n;
-      const int row = tm * G2_BM + rl, n0 = tn * BN + c0;
-      const uint32_t local = smem_u32(reinterpret_cast<float*>(smem) + (size_t)rl * (BN + 4) + c0);
-      float acc[PT];
+      const bool vec_ok = g2_vec_ok(g);
+      const uint32_t stage0 = smem_u32(smem);
+      uint32_t peer[SK];
 #pragma unroll
-      for (int j = 0; j < PT; ++j) acc[j] = 0.f;
+      for (int r = 0; r < SK; ++r)
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer[r]) : "r"(stage0), "r"(r));
 #pragma unroll
-      for (int r = 0; r < SK; ++r) {
-        uint32_t ra;
-        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local), "r"(r));
+      for (int i = 0; i < PER; ++i) {
+        const int idx = i * 256 + te, rl = idx / C4, c4 = idx % C4;
+        const uint32_t off = (uint32_t)(rl * (BN + 4) + rank * CW + 4 * c4) * 4;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int j = 0; j < PT; j += 4) {
+        for (int r = 0; r < SK; ++r) {
           float4 v;
           asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
                        : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                       : "r"(ra + j * 4));
-          acc[j] += v.x; acc[j + 1] += v.y; acc[j + 2] += v.z; acc[j + 3] += v.w;
+                       : "r"(peer[r] + off));
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
         }
-      }
-      if (row < g.M) {
-        float* crow = g.C + (size_t)row * g.ldc;
-        const float* arow = g.addend ? g.addend + (size_t)row * g.ldadd : nullptr;
-        const bool vec = ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) &&
-                         (n0 + PT <= g.N) && !g.accumulate && !arow;
-        if (vec) {
-#pragma unroll
-          for (int j = 0; j < PT; j += 4) {
-            float4 o = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
-            if (g.bias) {
-              o.x += __ldg(g.bias + n0 + j); o.y += __ldg(g.bias + n0 + j + 1);
-              o.z += __ldg(g.bias + n0 + j + 2); o.w += __ldg(g.bias + n0 + j + 3);
-            }
-            *reinterpret_cast<float4*>(crow + n0 + j) = o;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < PT; ++j) {
-            const int col = n0 + j;
-            if (col < g.N) {
-              float r = acc[j];
-              if (g.bias) r += g.bias[col];
-              if (arow) r += arow[col];
-              if (g.accumulate) r += crow[col];
-              crow[col] = r;
-            }
-          }
-        }
+        g2_emit4(g, tm * G2_BM + rl, tn * BN + rank * CW + 4 * c4, acc, true, false, vec_ok);
       }
     }
     if (threadIdx.x == G2_EPI_WARP0 * 32) G2_STAMP(9);
-    cluster_sync_all();                  // nobody's shared memory goes away under a peer's reads
+    // nobody's shared memory goes away under a peer's reads; nothing to publish, so the arrive
+    // is relaxed (a release would first drain this CTA's result stores: ~1 us)
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
     if (threadIdx.x == G2_EPI_WARP0 * 32) G2_STAMP(10);
   }
   tc_fence_before();
@@ -656,13 +690,16 @@ static void pick_shape(int M, int N, int nk, bool allow_splitk, bool allow_pair,
       best_t = t; *bn_out = bns[i]; *splitk_out = sk; *pair_out = pair ? 1 : 0;
     }
   }
-  // 128 x 128 tiles with K partitioned over a cluster (one wave by construction); the reduction
-  // through distributed shared memory and the cluster launch cost about CSK_OVERHEAD clk
+  // 128 x 128 tiles with K partitioned over a cluster (one wave by construction).  Measured
+  // (scratch/csk_test.py, 1024 x 512 x K): 7.9 us + 0.15 us per k-block against 3.4 + 0.32 for
+  // BN = 32, i.e. the parked partial tile, two cluster barriers and the DSMEM reduction cost
+  // about 8500 clk more per launch than the plain epilogue
+  constexpr long long CSK_OVERHEAD = 8500;
   if (allow_csk) {
     const int tiles = tm * ((N + 127) / 128);
     for (int sk = 2; sk <= 8; sk *= 2) {
       if (nk / sk < G2_CH || tiles > max_clusters(sk)) continue;
-      const long long t = (long long)((nk + sk - 1) / sk) * 1130 + 2500;
+      const long long t = (long long)((nk + sk - 1) / sk) * 1130 + CSK_OVERHEAD;
       if (t < best_t) {
         best_t = t; *bn_out = 128; *splitk_out = sk; *pair_out = 0; *csk_out = sk;
       }
@@ -696,8 +733,8 @@ int tc_gemm_ops(const TcOperand& A1, int K1, const TcOperand* A2, int K2, const 
   if (allow_pair < 0) {
     const char* e = getenv("DV3_TC_PAIR");
     allow_pair = (e && e[0] == '0') ? 0 : 1;
-    e = getenv("DV3_TC_CSK");            // cluster split-K: opt-in until its fixed cost is paid down
-    allow_csk = (e && e[0] == '1') ? 1 : 0;
+    e = getenv("DV3_TC_CSK");
+    allow_csk = (e && e[0] == '0') ? 0 : 1;
   }
   pick_shape(M, N, nk_all, (accumulate & 2) != 0, allow_pair && !raw, allow_csk && !raw, &BN,
              &splitk, &pair, &csk);

@@ -132,6 +132,11 @@ umma2x_gemm_kernel(const __grid_constant__ GemmX2Maps mp, GemmX2Args g) {
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&mp.a1h); prefetch_tensormap(&mp.a1l);
+    prefetch_tensormap(&mp.bh); prefetch_tensormap(&mp.bl);
+    if (g.nk1 < g.nk) { prefetch_tensormap(&mp.a2h); prefetch_tensormap(&mp.a2l); }
+  }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
                  ::"r"(smem_u32(tmem_slot)), "n"(Cfg::TMEM_COLS)

@@ -1,6 +1,6 @@
 """Where a single-wave GEMM launch spends its time: globaltimer stamps of CTA 0 (DV3_GEMM_TIMING=1)."""
 import importlib, sys, os, ctypes, numpy as np, torch
-os.environ["DV3_GEMM_TIMING"] = "1"
+os.environ["DV3_GEMM_TIMING"] = "1"; os.environ["DV3_OBSERVE_TIMING"] = "1"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 pkg = importlib.import_module('dreamerv3-torch_b200')
@@ -24,4 +24,4 @@ for (M, N, Kd) in [(1024, 512, 512), (1024, 512, 1536)]:
         rel = {names[i]: int(t[i] - t[0]) for i in range(len(names)) if t[i] >= t[0] and t[i] - t[0] < 10**8}
         print(f"{M}x{N}x{Kd} force={force:8s} eager {e0.elapsed_time(e1)*50:6.1f} us/launch | ns from entry:", rel, flush=True)
         # clear stamps for the next config
-        os.environ["DV3_GEMM_TIMING"] = "1"
+        os.environ["DV3_GEMM_TIMING"] = "1"; os.environ["DV3_OBSERVE_TIMING"] = "1"

@@ -61,9 +61,163 @@ ln_silu_fwd_kernel(const float* __restrict__ pre, int ld, const float* __restric
   }
 }
 
+// ---- bulk rows (M >= BULK_ROWS): one warp per row, the row lives in registers ---------------
+// The block-per-row kernels above are latency-bound (three passes over the row, two block
+// reductions): 35 us for 15360 x 512 where a copy takes 7.  With thousands of rows a warp per row
+// fills the machine; each lane holds NV float4 of the row, reads it once, reduces with shuffles and
+// writes 16-byte vectors.  Needs n % 4 == 0, n <= 128 NV and 16-byte aligned rows.
+constexpr int BULK_ROWS = 4096;
+constexpr int BULK_WARPS = 8;
+
+__device__ __forceinline__ float4 split_hi4(float4 v) {
+  return make_float4(__uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u),
+                     __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u),
+                     __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u),
+                     __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
+}
+__device__ __forceinline__ void put_split4(const SplitOut& so, size_t row, int col, float4 v) {
+  if (so.hi) {
+    const float4 h = split_hi4(v);
+    *reinterpret_cast<float4*>(so.hi + row * so.ld + col) = h;
+    *reinterpret_cast<float4*>(so.lo + row * so.ld + col) =
+        make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+  }
+}
+
+// mean and 1/sqrt(var+eps) of a register-resident row (two-pass, biased variance)
+template <int NV>
+__device__ __forceinline__ void warp_row_stats(const float4 (&x)[NV], const bool (&ok)[NV], int n,
+                                               float eps, float& mean, float& rstd) {
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) s += (x[j].x + x[j].y) + (x[j].z + x[j].w);
+  mean = warp_sum(s) / (float)n;
+  float v = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    if (ok[j]) {
+      const float a = x[j].x - mean, b = x[j].y - mean, c = x[j].z - mean, d = x[j].w - mean;
+      v = fmaf(a, a, v); v = fmaf(b, b, v); v = fmaf(c, c, v); v = fmaf(d, d, v);
+    }
+  }
+  rstd = 1.f / sqrtf(warp_sum(v) / (float)n + eps);
+}
+
+template <int NV>
+__global__ void __launch_bounds__(BULK_WARPS * 32)
+ln_silu_fwd_bulk_kernel(const float* __restrict__ pre, int ld, const float* __restrict__ g,
+                        const float* __restrict__ b, float eps, int M, int n,
+                        float* __restrict__ out, int ldo, SplitOut so) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * BULK_WARPS + (threadIdx.x >> 5);
+  if (r >= M) return;
+  const float* row = pre + (size_t)r * ld;
+  float4 x[NV];
+  bool ok[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int c = 4 * (j * 32 + lane);
+    ok[j] = c < n;
+    x[j] = ok[j] ? *reinterpret_cast<const float4*>(row + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float mean, rstd;
+  warp_row_stats<NV>(x, ok, n, eps, mean, rstd);
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    if (ok[j]) {
+      const int c = 4 * (j * 32 + lane);
+      const float4 gg = __ldg(reinterpret_cast<const float4*>(g + c));
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(b + c));
+      float4 y;
+      y.x = siluf_(fmaf((x[j].x - mean) * rstd, gg.x, bb.x));
+      y.y = siluf_(fmaf((x[j].y - mean) * rstd, gg.y, bb.y));
+      y.z = siluf_(fmaf((x[j].z - mean) * rstd, gg.z, bb.z));
+      y.w = siluf_(fmaf((x[j].w - mean) * rstd, gg.w, bb.w));
+      *reinterpret_cast<float4*>(out + (size_t)r * ldo + c) = y;
+      put_split4(so, r, c, y);
+    }
+  }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(BULK_WARPS * 32)
+ln_silu_bwd_bulk_kernel(const float* __restrict__ pre, int ld, const float* __restrict__ g,
+                        const float* __restrict__ b, float eps, const float* __restrict__ d_out,
+                        int ldd, int M, int n, float* __restrict__ d_pre, int ldp,
+                        float* __restrict__ d_ln, int ldl, SplitOut so) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * BULK_WARPS + (threadIdx.x >> 5);
+  if (r >= M) return;
+  const float* row = pre + (size_t)r * ld;
+  const float* dor = d_out + (size_t)r * ldd;
+  float4 x[NV], dx[NV];
+  bool ok[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int c = 4 * (j * 32 + lane);
+    ok[j] = c < n;
+    x[j] = ok[j] ? *reinterpret_cast<const float4*>(row + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    dx[j] = ok[j] ? *reinterpret_cast<const float4*>(dor + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float mean, rstd;
+  warp_row_stats<NV>(x, ok, n, eps, mean, rstd);
+  float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    if (ok[j]) {
+      const int c = 4 * (j * 32 + lane);
+      const float4 gg = __ldg(reinterpret_cast<const float4*>(g + c));
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(b + c));
+      // x <- xhat, dx <- d_ln * gamma
+      float4 dv;
+      x[j].x = (x[j].x - mean) * rstd; dv.x = dx[j].x * silu_grad(fmaf(x[j].x, gg.x, bb.x));
+      x[j].y = (x[j].y - mean) * rstd; dv.y = dx[j].y * silu_grad(fmaf(x[j].y, gg.y, bb.y));
+      x[j].z = (x[j].z - mean) * rstd; dv.z = dx[j].z * silu_grad(fmaf(x[j].z, gg.z, bb.z));
+      x[j].w = (x[j].w - mean) * rstd; dv.w = dx[j].w * silu_grad(fmaf(x[j].w, gg.w, bb.w));
+      if (d_ln) *reinterpret_cast<float4*>(d_ln + (size_t)r * ldl + c) = dv;
+      dx[j] = make_float4(dv.x * gg.x, dv.y * gg.y, dv.z * gg.z, dv.w * gg.w);
+      a0 += (dx[j].x + dx[j].y) + (dx[j].z + dx[j].w);
+      a1 = fmaf(dx[j].x, x[j].x, a1); a1 = fmaf(dx[j].y, x[j].y, a1);
+      a1 = fmaf(dx[j].z, x[j].z, a1); a1 = fmaf(dx[j].w, x[j].w, a1);
+    }
+  }
+  const float m1 = warp_sum(a0) / (float)n, m2 = warp_sum(a1) / (float)n;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    if (ok[j]) {
+      const int c = 4 * (j * 32 + lane);
+      float4 dp;
+      dp.x = rstd * (dx[j].x - m1 - x[j].x * m2);
+      dp.y = rstd * (dx[j].y - m1 - x[j].y * m2);
+      dp.z = rstd * (dx[j].z - m1 - x[j].z * m2);
+      dp.w = rstd * (dx[j].w - m1 - x[j].w * m2);
+      *reinterpret_cast<float4*>(d_pre + (size_t)r * ldp + c) = dp;
+      put_split4(so, r, c, dp);
+    }
+  }
+}
+
+static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 int ln_silu_fwd(const float* pre, int ld, const float* g, const float* b, float eps, int M, int n,
                 float* out, int ldo, cudaStream_t st, SplitOut so) {
   if (M <= 0) return 0;
+  if (M >= BULK_ROWS && n % 4 == 0 && n <= 1024 && ld % 4 == 0 && ldo % 4 == 0 && al16(pre) &&
+      al16(out) && al16(g) && al16(b) && (!so.hi || (so.ld % 4 == 0 && al16(so.hi) && al16(so.lo)))) {
+    const dim3 grid((M + BULK_WARPS - 1) / BULK_WARPS), block(BULK_WARPS * 32);
+    if (n <= 512)
+      DV3_CHECK_CUDA(launch_pdl(ln_silu_fwd_bulk_kernel<4>, grid, block, 0, st, pre, ld, g, b, eps, M,
+                                n, out, ldo, so));
+    else
+      DV3_CHECK_CUDA(launch_pdl(ln_silu_fwd_bulk_kernel<8>, grid, block, 0, st, pre, ld, g, b, eps, M,
+                                n, out, ldo, so));
+    DV3_CHECK_LAUNCH("ln_silu_fwd_bulk_kernel");
+    return 0;
+  }
   DV3_CHECK_CUDA(launch_pdl(ln_silu_fwd_kernel, dim3(M), dim3(ROW_THREADS), 0, st, pre, ld, g, b, eps,
                             n, out, ldo, so));
   DV3_CHECK_LAUNCH("ln_silu_fwd_kernel");
@@ -110,6 +264,20 @@ int ln_silu_bwd(const float* pre, int ld, const float* g, const float* b, float 
                 const float* d_out, int ldd, int M, int n, float* d_pre, int ldp, float* d_ln,
                 int ldl, cudaStream_t st, SplitOut so) {
   if (M <= 0) return 0;
+  if (M >= BULK_ROWS && n % 4 == 0 && n <= 1024 && ld % 4 == 0 && ldd % 4 == 0 && ldp % 4 == 0 &&
+      al16(pre) && al16(d_out) && al16(d_pre) && al16(g) && al16(b) &&
+      (!d_ln || (ldl % 4 == 0 && al16(d_ln))) &&
+      (!so.hi || (so.ld % 4 == 0 && al16(so.hi) && al16(so.lo)))) {
+    const dim3 grid((M + BULK_WARPS - 1) / BULK_WARPS), block(BULK_WARPS * 32);
+    if (n <= 512)
+      DV3_CHECK_CUDA(launch_pdl(ln_silu_bwd_bulk_kernel<4>, grid, block, 0, st, pre, ld, g, b, eps,
+                                d_out, ldd, M, n, d_pre, ldp, d_ln, ldl, so));
+    else
+      DV3_CHECK_CUDA(launch_pdl(ln_silu_bwd_bulk_kernel<8>, grid, block, 0, st, pre, ld, g, b, eps,
+                                d_out, ldd, M, n, d_pre, ldp, d_ln, ldl, so));
+    DV3_CHECK_LAUNCH("ln_silu_bwd_bulk_kernel");
+    return 0;
+  }
   DV3_CHECK_CUDA(launch_pdl(ln_silu_bwd_kernel, dim3(M), dim3(ROW_THREADS), 0, st, pre, ld, g, b, eps,
                             d_out, ldd, n, d_pre, ldp, d_ln, ldl, so));
   DV3_CHECK_LAUNCH("ln_silu_bwd_kernel");

@@ -1,6 +1,7 @@
 """-m gpu: the CUDA path (through the C ABI) against the CPU oracle on identical seeded inputs.
 Indices bit-exact; floats within 1e-4 relative (BASELINE.json north_star)."""
 import pytest
+import torch
 
 import parity_cases as pc
 
@@ -202,3 +203,49 @@ def test_fused_adam_clip_matches_torch(pkg, device):
                 assert float((pa - pb).abs().max()) <= 2e-6, (clip, step)
         sd = opt.state_dict()
         assert set(sd) == {"state", "param_groups"} and len(sd["state"]) == len(list(a.parameters()))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,n", [(5000, 512), (4100, 1024), (4096, 500), (4097, 72), (6000, 1536), (300, 512)])
+def test_ln_silu_bulk_rows_match_torch(pkg, device, M, n):
+    """LayerNorm+SiLU forward / backward (reference networks.py:657-681 blocks, nn.LayerNorm eps 1e-3)
+    on bulk row counts, where the warp-per-row kernels take over (M >= 4096, n <= 1024; (6000, 1536)
+    and (300, 512) stay on the block-per-row form): against torch fp32 autograd, and the emitted
+    hi/lo planes must be the exact split of the fp32 outputs."""
+    K = pkg.kernels
+    g = torch.Generator().manual_seed(M + n)
+    pre = (torch.randn(M, n, generator=g) * 2 + 0.3).to(device)
+    gam = (1 + 0.1 * torch.randn(n, generator=g)).to(device)
+    bet = (0.1 * torch.randn(n, generator=g)).to(device)
+    dy = torch.randn(M, n, generator=g).to(device)
+    x = pre.clone().requires_grad_(True)
+    ref = torch.nn.functional.silu(torch.nn.functional.layer_norm(x, (n,), gam, bet, 1e-3))
+    ref.backward(dy)
+    out, sp = K.ln_silu_fwd(pre, gam, bet, 1e-3, with_split=True)
+    assert float((out - ref).abs().max()) <= 1e-5 * (1 + float(ref.abs().max()))
+    assert torch.equal(sp.hi[:, :n] + sp.lo[:, :n], out)
+    assert int((sp.hi.view(torch.int32) & 0x1FFF).abs().max()) == 0
+    assert torch.equal(K.ln_silu_fwd(pre, gam, bet, 1e-3), out)
+    d_pre, d_ln, dsp = K.ln_silu_bwd(pre, gam, bet, dy, 1e-3, with_split=True)
+    scale = 1 + float(x.grad.abs().max())
+    assert float((d_pre - x.grad).abs().max()) <= 2e-5 * scale
+    assert torch.equal(dsp.hi[:, :n] + dsp.lo[:, :n], d_pre)
+    v = torch.nn.functional.layer_norm(pre, (n,), gam, bet, 1e-3)
+    sg = torch.sigmoid(v)
+    assert float((d_ln - dy * sg * (1 + v * (1 - sg))).abs().max()) <= 1e-5 * (1 + float(dy.abs().max()))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,K", [(15360, 512), (1024, 1030), (7, 5), (513, 255), (4096, 1536), (64, 4)])
+def test_split_is_exact(pkg, device, M, K):
+    """hi keeps the top 11 mantissa bits (13 low bits zero), hi + lo == x bit for bit, padding is
+    zero -- on the vector path (16-byte aligned pitch) and the scalar one (views, odd pitches)."""
+    g = torch.Generator().manual_seed(M * 3 + K)
+    x = (torch.randn(M, K, generator=g) * 10 ** torch.randint(-3, 4, (M, 1), generator=g).float()).to(device)
+    for src in (x, torch.cat([x, x], 1)[:, 1:1 + K]):
+        sp = pkg.kernels.split(src)
+        assert sp.rows == M and sp.cols == K and sp.ld % 4 == 0
+        assert torch.equal(sp.hi[:, :K] + sp.lo[:, :K], src)
+        assert int((sp.hi.view(torch.int32) & 0x1FFF).abs().max()) == 0
+        if sp.ld > K:
+            assert float(sp.hi[:, K:].abs().max()) == 0.0 and float(sp.lo[:, K:].abs().max()) == 0.0

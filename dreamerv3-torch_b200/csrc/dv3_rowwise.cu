@@ -500,11 +500,111 @@ onehot_sample_kernel(const float* __restrict__ logits, int ldl, const float* __r
   if (onehot && valid) onehot[(size_t)r * ldo + s * C + lane] = (lane == k) ? 1.f : 0.f;
 }
 
+// ---- C == 32: four lanes per (row, group) -------------------------------------------------------
+// The lane-per-class form above spends its time in shuffles (six 5-step butterflies and a 10-shuffle
+// argmax per group, one warp-shuffle per clock and SM): 15 us for 1024 x 32 groups.  Here lane q of
+// a quad keeps classes q, q+4, .., q+28 in registers, so the butterfly's first three steps
+// (i ^ 16, i ^ 8, i ^ 4) are adds between registers and only the last two cross lanes.  The
+// association order is the butterfly's, so every value -- and every sampled index -- is
+// bit-identical to the lane-per-class kernel (tests pin one against the other).
+__device__ __forceinline__ float quad_sum(float (&a)[8]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) a[j] += a[j + 4];       // classes i, i + 16
+  a[0] += a[2]; a[1] += a[3];                           // i, i + 8
+  float v = a[0] + a[1];                                // i, i + 4
+  v += __shfl_xor_sync(FULL, v, 2);
+  v += __shfl_xor_sync(FULL, v, 1);
+  return v;
+}
+__device__ __forceinline__ float quad_max(const float (&a)[8]) {
+  float m = a[0];
+#pragma unroll
+  for (int j = 1; j < 8; ++j) m = fmaxf(m, a[j]);
+  m = fmaxf(m, __shfl_xor_sync(FULL, m, 2));
+  return fmaxf(m, __shfl_xor_sync(FULL, m, 1));
+}
+
+__global__ void __launch_bounds__(256)
+onehot_sample_group_kernel(const float* __restrict__ logits, int ldl, const float* __restrict__ u,
+                           int ldu, int permT, int permB, float unimix, int M, int S,
+                           int32_t* __restrict__ idx, int ldi, float* __restrict__ onehot, int ldo) {
+  pdl_wait();
+  pdl_launch_dependents();
+  constexpr int C = 32;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int q = t & 3;
+  int w = t >> 2;                                       // (row, group)
+  const bool live = w < M * S;                          // dead quads still take part in shuffles
+  if (!live) w = 0;
+  const int r = w / S, s = w - r * S;
+  const float* lrow = logits + (size_t)r * ldl + s * C + q;
+  float l[8], e[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) l[j] = __ldg(lrow + 4 * j);
+  const float m = quad_max(l);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { l[j] = expf(l[j] - m); e[j] = l[j]; }
+  const float s1 = quad_sum(e);
+  if (unimix > 0.f) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) l[j] = logf((l[j] / s1) * (1.f - unimix) + unimix / (float)C);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) l[j] = __ldg(lrow + 4 * j);
+  }
+  const float m2 = quad_max(l);                         // l == lp
+#pragma unroll
+  for (int j = 0; j < 8; ++j) e[j] = expf(l[j] - m2);
+  const float lse = m2 + logf(quad_sum(e));
+#pragma unroll
+  for (int j = 0; j < 8; ++j) l[j] = l[j] - lse;        // l <- norm
+  if (u) {
+    const float m3 = quad_max(l);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { l[j] = expf(l[j] - m3); e[j] = l[j]; }
+    const float s3 = quad_sum(e);
+    const int ur = permT > 0 ? (r % permT) * permB + r / permT : r;
+    const float* urow = u + (size_t)ur * ldu + s * C + q;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) l[j] = (l[j] / s3) / (-logf(__ldg(urow + 4 * j)));   // l <- score
+  }
+  float bv = (l[0] != l[0]) ? -INFINITY : l[0];         // NaN never wins
+  int k = q;
+#pragma unroll
+  for (int j = 1; j < 8; ++j) {
+    const float v = (l[j] != l[j]) ? -INFINITY : l[j];
+    if (v > bv) { bv = v; k = q + 4 * j; }              // first index wins ties
+  }
+#pragma unroll
+  for (int o = 2; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(FULL, bv, o);
+    const int oi = __shfl_xor_sync(FULL, k, o);
+    if (ov > bv || (ov == bv && oi < k)) { bv = ov; k = oi; }
+  }
+  if (!live) return;
+  if (idx && q == 0) idx[(size_t)r * ldi + s] = k;
+  // lane q writes classes [8q, 8q + 8) of the one-hot row
+  float4* o4 = reinterpret_cast<float4*>(onehot + (size_t)r * ldo + s * C + 8 * q);
+  const int k0 = k - 8 * q;
+  o4[0] = make_float4(k0 == 0 ? 1.f : 0.f, k0 == 1 ? 1.f : 0.f, k0 == 2 ? 1.f : 0.f, k0 == 3 ? 1.f : 0.f);
+  o4[1] = make_float4(k0 == 4 ? 1.f : 0.f, k0 == 5 ? 1.f : 0.f, k0 == 6 ? 1.f : 0.f, k0 == 7 ? 1.f : 0.f);
+}
+
 int onehot_sample(const float* logits, int ldl, const float* u, int ldu, int permT, int permB,
                   float unimix, int M, int S, int C, int32_t* idx, int ldi, float* onehot, int ldo,
                   cudaStream_t st) {
   if (M <= 0) return 0;
   DV3_REQUIRE(C >= 1 && C <= 32, DV3_ERR_BAD_SHAPE, "onehot_sample: classes=%d (max 32)", C);
+  const char* gf = getenv("DV3_SAMPLE_GROUP");         // "0": keep the lane-per-class kernel
+  const bool group_form = !(gf && gf[0] == '0');
+  if (group_form && C == 32 && onehot && (long long)M * S >= 4096 && (long long)M * S < (1ll << 28) &&
+      ldl % 4 == 0 && ldo % 4 == 0 && al16(logits) && al16(onehot) && (!u || (ldu % 4 == 0 && al16(u)))) {
+    const long long lanes = 4ll * M * S;
+    DV3_CHECK_CUDA(launch_pdl(onehot_sample_group_kernel, dim3((unsigned)((lanes + 255) / 256)), dim3(256), 0, st,
+                              logits, ldl, u, ldu, permT, permB, unimix, M, S, idx, ldi, onehot, ldo));
+    DV3_CHECK_LAUNCH("onehot_sample_group_kernel");
+    return 0;
+  }
   const long long warps = (long long)M * S;
   const int grid = (int)((warps + 7) / 8);
   DV3_CHECK_CUDA(launch_pdl(onehot_sample_kernel, dim3(grid), dim3(256), 0, st, logits, ldl, u, ldu,

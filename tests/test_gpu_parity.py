@@ -249,3 +249,26 @@ def test_split_is_exact(pkg, device, M, K):
         assert int((sp.hi.view(torch.int32) & 0x1FFF).abs().max()) == 0
         if sp.ld > K:
             assert float(sp.hi[:, K:].abs().max()) == 0.0 and float(sp.lo[:, K:].abs().max()) == 0.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("unimix", [0.01, 0.0])
+@pytest.mark.parametrize("with_u", [True, False])
+def test_onehot_sample_group_form_is_bit_identical(pkg, device, monkeypatch, unimix, with_u):
+    """The thread-per-group sampler (32 classes in registers, sums in the butterfly's association
+    order) must pick exactly the indices of the lane-per-class kernel -- which is the one pinned
+    against the oracle -- for draws (reference tools.py:436-460 + ATen multinomial) and modes."""
+    K = pkg.kernels
+    g = torch.Generator().manual_seed(11)
+    logits = (torch.randn(4096, 32, 32, generator=g) * 3).to(device)
+    logits[5, 3] = 0.0                      # exact ties: first index must win
+    logits[6, 0, 7] = float("nan")
+    u = torch.rand(4096, 32, 32, generator=g).clamp_(1e-30, 1.0).to(device) if with_u else None
+    monkeypatch.setenv("DV3_SAMPLE_GROUP", "0")
+    idx0, hot0 = K.onehot_sample(logits, u, unimix)
+    monkeypatch.setenv("DV3_SAMPLE_GROUP", "1")
+    idx1, hot1 = K.onehot_sample(logits, u, unimix)
+    assert torch.equal(idx0, idx1) and torch.equal(hot0, hot1)
+    if not with_u:
+        assert int(idx1[5, 3]) == 0
+    assert float(hot1.sum()) == 4096 * 32

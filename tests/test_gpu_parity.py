@@ -272,3 +272,36 @@ def test_onehot_sample_group_form_is_bit_identical(pkg, device, monkeypatch, uni
     if not with_u:
         assert int(idx1[5, 3]) == 0
     assert float(hot1.sum()) == 4096 * 32
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,D", [(1024, 512), (600, 1024), (1024, 256)])
+@pytest.mark.parametrize("warp_form", ["1", "0"])
+def test_gru_gates_bwd_matches_autograd(pkg, device, monkeypatch, M, D, warp_form):
+    """Backward of the LayerNorm-GRU gate block (reference networks.py:760-768) through the C ABI,
+    block-per-row and warp-per-row kernels (the latter takes D = 512 / 1024 at M >= 512), against
+    torch autograd of the same expression."""
+    import ctypes as C
+    L = pkg._lib
+    monkeypatch.setenv("DV3_GRU_WARP", warp_form)
+    gen = torch.Generator().manual_seed(M + D)
+    g_pre = torch.randn(M, 3 * D, generator=gen).to(device).requires_grad_(True)
+    gam = (1 + 0.1 * torch.randn(3 * D, generator=gen)).to(device)
+    bet = (0.1 * torch.randn(3 * D, generator=gen)).to(device)
+    h = torch.tanh(torch.randn(M, D, generator=gen)).to(device).requires_grad_(True)
+    d_new = torch.randn(M, D, generator=gen).to(device)
+    parts = torch.nn.functional.layer_norm(g_pre, (3 * D,), gam, bet, 1e-3)
+    parts.retain_grad()
+    r, c, u = parts.split(D, -1)
+    r = torch.sigmoid(r); c = torch.tanh(r * c); u = torch.sigmoid(u - 1)
+    # only the direct (1-u) path of d_h is the kernel's job: detach h inside the candidate terms
+    h_new = u * c + (1 - u) * h
+    h_new.backward(d_new)
+    d_g_pre = torch.empty(M, 3 * D, device=device); d_g_ln = torch.empty(M, 3 * D, device=device)
+    d_h = torch.empty(M, D, device=device)
+    L.check(L.lib().dv3_gru_gates_bwd(L.fptr(g_pre.detach()), 3 * D, L.fptr(gam), L.fptr(bet), 1e-3,
+                                      L.fptr(h.detach()), D, L.fptr(d_new), D, M, D, L.fptr(d_g_pre),
+                                      L.fptr(d_g_ln), 3 * D, L.fptr(d_h), D, L.stream_ptr()), "gru_gates_bwd")
+    torch.cuda.synchronize()
+    for got, want in ((d_g_pre, g_pre.grad), (d_g_ln, parts.grad), (d_h, h.grad)):
+        assert float((got - want).abs().max()) <= 2e-5 * (1 + float(want.abs().max()))

@@ -377,10 +377,90 @@ gru_gates_fwd_kernel(const float* __restrict__ g_pre, int ldg, const float* __re
   }
 }
 
+// warp-per-row form (D = 128 DV <= 1024): row in registers, one read, shuffle reductions
+template <int DV>
+__global__ void __launch_bounds__(8 * 32)
+gru_gates_fwd_warp_kernel(const float* __restrict__ g_pre, int ldg, const float* __restrict__ g,
+                          const float* __restrict__ b, float eps, const float* __restrict__ h,
+                          int ldh, int M, int D, float* __restrict__ h_new, int ldn, SplitOut so) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= M) return;
+  const float* row = g_pre + (size_t)r * ldg;
+  float4 x[3][DV];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int j = 0; j < DV; ++j) {
+      x[k][j] = *reinterpret_cast<const float4*>(row + k * D + 4 * (j * 32 + lane));
+      s += (x[k][j].x + x[k][j].y) + (x[k][j].z + x[k][j].w);
+    }
+  const float n3 = (float)(3 * D);
+  const float mean = warp_sum(s) / n3;
+  float v = 0.f;
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int j = 0; j < DV; ++j) {
+      const float a = x[k][j].x - mean, c = x[k][j].y - mean, d = x[k][j].z - mean,
+                  e = x[k][j].w - mean;
+      v = fmaf(a, a, v); v = fmaf(c, c, v); v = fmaf(d, d, v); v = fmaf(e, e, v);
+    }
+  const float rstd = 1.f / sqrtf(warp_sum(v) / n3 + eps);
+  auto gate = [&](float xr, float xc, float xu, float gr, float gc, float gu, float br, float bc,
+                  float bu, float hp) {
+    const float pr = fmaf((xr - mean) * rstd, gr, br);
+    const float pc = fmaf((xc - mean) * rstd, gc, bc);
+    const float pu = fmaf((xu - mean) * rstd, gu, bu);
+    const float rg = sigmoidf_(pr);
+    const float cc = tanhf(rg * pc);
+    const float u = sigmoidf_(pu - 1.f);
+    return u * cc + (1.f - u) * hp;
+  };
+#pragma unroll
+  for (int j = 0; j < DV; ++j) {
+    const int c = 4 * (j * 32 + lane);
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(g + c));
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(g + D + c));
+    const float4 g2 = __ldg(reinterpret_cast<const float4*>(g + 2 * D + c));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(b + c));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(b + D + c));
+    const float4 b2 = __ldg(reinterpret_cast<const float4*>(b + 2 * D + c));
+    const float4 hp = *reinterpret_cast<const float4*>(h + (size_t)r * ldh + c);
+    float4 hn;
+    hn.x = gate(x[0][j].x, x[1][j].x, x[2][j].x, g0.x, g1.x, g2.x, b0.x, b1.x, b2.x, hp.x);
+    hn.y = gate(x[0][j].y, x[1][j].y, x[2][j].y, g0.y, g1.y, g2.y, b0.y, b1.y, b2.y, hp.y);
+    hn.z = gate(x[0][j].z, x[1][j].z, x[2][j].z, g0.z, g1.z, g2.z, b0.z, b1.z, b2.z, hp.z);
+    hn.w = gate(x[0][j].w, x[1][j].w, x[2][j].w, g0.w, g1.w, g2.w, b0.w, b1.w, b2.w, hp.w);
+    *reinterpret_cast<float4*>(h_new + (size_t)r * ldn + c) = hn;
+    put_split4(so, r, c, hn);
+  }
+}
+
 int gru_gates_fwd(const float* g_pre, int ldg, const float* g, const float* b, float eps,
                   const float* h, int ldh, int M, int D, float* h_new, int ldn, cudaStream_t st,
                   SplitOut so) {
   if (M <= 0) return 0;
+  {
+    const char* wf = getenv("DV3_GRU_WARP_FWD");         // "0": keep the block-per-row kernel
+    const bool ok = !(wf && wf[0] == '0') && M >= 512 && (D == 512 || D == 1024) && ldg % 4 == 0 &&
+                    ldh % 4 == 0 && ldn % 4 == 0 && al16(g_pre) && al16(g) && al16(b) && al16(h) &&
+                    al16(h_new) && (!so.hi || (so.ld % 4 == 0 && al16(so.hi) && al16(so.lo)));
+    if (ok) {
+      const dim3 grid((M + 7) / 8), block(256);
+      if (D == 512)
+        DV3_CHECK_CUDA(launch_pdl(gru_gates_fwd_warp_kernel<4>, grid, block, 0, st, g_pre, ldg, g, b,
+                                  eps, h, ldh, M, D, h_new, ldn, so));
+      else
+        DV3_CHECK_CUDA(launch_pdl(gru_gates_fwd_warp_kernel<8>, grid, block, 0, st, g_pre, ldg, g, b,
+                                  eps, h, ldh, M, D, h_new, ldn, so));
+      DV3_CHECK_LAUNCH("gru_gates_fwd_warp_kernel");
+      return 0;
+    }
+  }
   DV3_CHECK_CUDA(launch_pdl(gru_gates_fwd_kernel, dim3(M), dim3(ROW_THREADS), 0, st, g_pre, ldg, g, b,
                             eps, h, ldh, D, h_new, ldn, so));
   DV3_CHECK_LAUNCH("gru_gates_fwd_kernel");
@@ -786,11 +866,72 @@ onehot_st_bwd_kernel(const float* __restrict__ logits, int ldl, const float* __r
   }
 }
 
+// four lanes per (row, group), as in onehot_sample_group_kernel (C == 32)
+__global__ void __launch_bounds__(256)
+onehot_st_bwd_group_kernel(const float* __restrict__ logits, int ldl, const float* __restrict__ g1,
+                           int ldg1, const float* __restrict__ g2, int ldg2,
+                           const float* __restrict__ ext, int lde, float unimix, int M, int S,
+                           float* __restrict__ d_logits, int ldd, SplitOut so) {
+  pdl_wait();
+  pdl_launch_dependents();
+  constexpr int C = 32;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int q = t & 3;
+  int w = t >> 2;
+  const bool live = w < M * S;
+  if (!live) w = 0;
+  const int r = w / S, s = w - r * S;
+  const int col0 = s * C + q;
+  float l[8], gq[8], tmp[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    l[j] = __ldg(logits + (size_t)r * ldl + col0 + 4 * j);
+    float gg = 0.f;
+    if (g1) gg += __ldg(g1 + (size_t)r * ldg1 + col0 + 4 * j);
+    if (g2) gg += __ldg(g2 + (size_t)r * ldg2 + col0 + 4 * j);
+    gq[j] = gg;
+  }
+  const float m = quad_max(l);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { l[j] = expf(l[j] - m); tmp[j] = l[j]; }
+  const float se = quad_sum(tmp);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    l[j] = l[j] / se;                                             // p
+    tmp[j] = gq[j] * (l[j] * (1.f - unimix) + unimix / (float)C); // g * q
+  }
+  const float gdotq = quad_sum(tmp);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { gq[j] = gq[j] - gdotq; tmp[j] = gq[j] * l[j]; }
+  const float dot = quad_sum(tmp);
+  if (!live) return;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int col = col0 + 4 * j;
+    float d = (1.f - unimix) * l[j] * (gq[j] - dot);
+    if (ext) d += __ldg(ext + (size_t)r * lde + col);
+    d_logits[(size_t)r * ldd + col] = d;
+    put_split(so, r, col, d);
+  }
+}
+
 int onehot_st_bwd(const float* logits, int ldl, const float* g1, int ldg1, const float* g2,
                   int ldg2, const float* ext, int lde, float unimix, int M, int S, int C,
                   float* d_logits, int ldd, cudaStream_t st, SplitOut so) {
   if (M <= 0) return 0;
   DV3_REQUIRE(C >= 1 && C <= 32, DV3_ERR_BAD_SHAPE, "onehot_st_bwd: classes=%d (max 32)", C);
+  {
+    const char* gf = getenv("DV3_STBWD_GROUP");          // "0": keep the lane-per-class kernel
+    if (!(gf && gf[0] == '0') && C == 32 && (long long)M * S >= 4096 &&
+        (long long)M * S < (1ll << 28)) {
+      const long long lanes = 4ll * M * S;
+      DV3_CHECK_CUDA(launch_pdl(onehot_st_bwd_group_kernel, dim3((unsigned)((lanes + 255) / 256)),
+                                dim3(256), 0, st, logits, ldl, g1, ldg1, g2, ldg2, ext, lde, unimix,
+                                M, S, d_logits, ldd, so));
+      DV3_CHECK_LAUNCH("onehot_st_bwd_group_kernel");
+      return 0;
+    }
+  }
   const long long warps = (long long)M * S;
   const int grid = (int)((warps + 7) / 8);
   DV3_CHECK_CUDA(launch_pdl(onehot_st_bwd_kernel, dim3(grid), dim3(256), 0, st, logits, ldl, g1, ldg1,

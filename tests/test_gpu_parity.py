@@ -305,3 +305,27 @@ def test_gru_gates_bwd_matches_autograd(pkg, device, monkeypatch, M, D, warp_for
     torch.cuda.synchronize()
     for got, want in ((d_g_pre, g_pre.grad), (d_g_ln, parts.grad), (d_h, h.grad)):
         assert float((got - want).abs().max()) <= 2e-5 * (1 + float(want.abs().max()))
+
+
+@pytest.mark.gpu
+def test_onehot_st_bwd_group_form_matches(pkg, device, monkeypatch):
+    """Straight-through backward of the unimix categorical (reference tools.py:436-460 through
+    autograd): the four-lanes-per-group kernel against the lane-per-class one and torch autograd."""
+    K = pkg.kernels
+    g = torch.Generator().manual_seed(5)
+    logits = (torch.randn(2048, 32, 32, generator=g) * 2).to(device)
+    gs = torch.randn(2048, 32, 32, generator=g).to(device)
+    ext = torch.randn(2048, 32, 32, generator=g).to(device)
+    monkeypatch.setenv("DV3_STBWD_GROUP", "0")
+    d0 = K.onehot_st_bwd(logits, gs, ext, 0.01)
+    monkeypatch.setenv("DV3_STBWD_GROUP", "1")
+    d1 = K.onehot_st_bwd(logits, gs, ext, 0.01)
+    d0 = d0[0] if isinstance(d0, tuple) else d0
+    d1 = d1[0] if isinstance(d1, tuple) else d1
+    assert float((d0 - d1).abs().max()) <= 1e-6 * (1 + float(d0.abs().max()))
+    x = logits.clone().requires_grad_(True)
+    p = torch.softmax(x, -1) * 0.99 + 0.01 / 32
+    probs = torch.softmax(torch.log(p) - torch.logsumexp(torch.log(p), -1, keepdim=True), -1)
+    (probs * gs).sum().backward()
+    want = x.grad + ext
+    assert float((d1 - want).abs().max()) <= 2e-5 * (1 + float(want.abs().max()))

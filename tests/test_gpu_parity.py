@@ -329,3 +329,36 @@ def test_onehot_st_bwd_group_form_matches(pkg, device, monkeypatch):
     (probs * gs).sum().backward()
     want = x.grad + ext
     assert float((d1 - want).abs().max()) <= 2e-5 * (1 + float(want.abs().max()))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,A,with_add", [(512, 6, False), (1024, 17, True), (500, 0, True)])
+def test_onehot_linear_warp_form_matches(pkg, device, monkeypatch, n, A, with_add):
+    """One-hot Linear + LN + SiLU (reference networks.py:208-221 on cat(one-hot stoch, action)):
+    the warp-per-row kernel accumulates in the block-per-row kernel's order, so `pre` must be
+    bit-identical and `out` equal to fp32 rounding; both against a dense torch product."""
+    L = pkg._lib
+    M, S, Cc = 1024, 32, 32
+    gen = torch.Generator().manual_seed(n + A)
+    idx = torch.randint(0, Cc, (M, S), generator=gen, dtype=torch.int32).to(device)
+    act = torch.randn(M, max(A, 1), generator=gen).to(device)[:, :A].contiguous() if A else None
+    WT = (torch.randn(S * Cc + A, n, generator=gen) / 6).to(device)
+    add = torch.randn(M, n, generator=gen).to(device) if with_add else None
+    gam = (1 + 0.1 * torch.randn(n, generator=gen)).to(device)
+    bet = (0.1 * torch.randn(n, generator=gen)).to(device)
+    res = {}
+    for form in ("0", "1"):
+        monkeypatch.setenv("DV3_GATHER_WARP", form)
+        pre = torch.empty(M, n, device=device); out = torch.empty(M, n, device=device)
+        L.check(L.lib().dv3_onehot_linear_ln_silu(L.iptr(idx), S, Cc, L.fptr(act), A, L.fptr(WT), L.fptr(add),
+                                                  L.fptr(gam), L.fptr(bet), 1e-3, M, n, L.fptr(pre), L.fptr(out),
+                                                  L.stream_ptr()), "onehot_linear")
+        res[form] = (pre, out)
+    assert torch.equal(res["0"][0], res["1"][0])
+    assert float((res["0"][1] - res["1"][1]).abs().max()) <= 2e-6 * (1 + float(res["0"][1].abs().max()))
+    hot = torch.nn.functional.one_hot(idx.long(), Cc).float().reshape(M, S * Cc)
+    x = torch.cat([hot, act], 1) if A else hot
+    ref = x.double() @ WT.double() + (add.double() if with_add else 0)
+    assert float((res["1"][0].double() - ref).abs().max()) <= 1e-5 * (1 + float(ref.abs().max()))
+    want = torch.nn.functional.silu(torch.nn.functional.layer_norm(res["1"][0], (n,), gam, bet, 1e-3))
+    assert float((res["1"][1] - want).abs().max()) <= 1e-5 * (1 + float(want.abs().max()))

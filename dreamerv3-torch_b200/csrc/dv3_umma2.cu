@@ -25,6 +25,11 @@
 // registers.  The cross terms use their own accumulator, double-buffered per tile so the global
 // stores of tile i overlap the MMAs of tile i+1.
 // TMEM columns: [0,BN) hi chunk 0 | [BN,2BN) hi chunk 1 | [2BN,3BN) lo tile even | [3BN,4BN) lo odd.
+// WIDE (the default for BN <= 64 and single-wave BN = 128): two MMAs per k-step -- A_hi x [B_hi;B_lo]
+// at width 2 BN, then A_lo x B_hi -- into two chunk accumulators of 2 BN columns each:
+// [0,BN) hi*hi | [BN,2BN) cross terms | [2BN,4BN) the same for the other chunk.
+// SK > 1: K partitioned over the CTAs of a cluster, partial tiles reduced through distributed
+// shared memory (see the kernel's comment and DESIGN.md section 7 for when it pays).
 #include <cstdlib>
 #include "dv3_tc.cuh"
 
@@ -74,11 +79,7 @@ struct G2Cfg {
 // CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): rows of 32 MN-floats (128 B) per k, 32-byte chunks XORed
 // with (k % 4), i.e. atoms of 4 k-rows = 512 B.  Canonical form ((8,n),(4,k)):((1,LBO),(8,SBO)) in
 // 16-byte units: SBO = 512 B between k-atoms, LBO = 4096 B between the 32-float-wide MN blocks
-// (one TMA box [32 k x 32 mn] each).
-__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr) {
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | (256ull << 16) | (32ull << 32) | (1ull << 46) |
-         (1ull << 61);
-}
+// (one TMA box [32 k x 32 mn] each).  The descriptor itself is umma_desc_units<true> (dv3_tc.cuh).
 
 struct Gemm2Maps {
   CUtensorMap a1h, a1l, a2h, a2l, bh, bl;   // raw mode uses a1h, a2h, bh only

@@ -6,8 +6,10 @@ H=15 imagination from all 1024 posteriors) on N B200s, one process per GPU.
 
 ``--impl ours``       the product: dreamerv3-torch_b200 (CUDA kernels through the C ABI), one
                       whole train step per call of graphs.TrainStepGraph (a captured CUDA graph).
-``--impl reference``  the reference's algorithm on the box's host cores: the CPU oracle port
-                      (oracle/train_step.py), all host threads, same workload / metric / unit.
+``--impl reference``  the reference's OWN code (oracle/_ref = the unmodified tools / networks /
+                      models modules staged by oracle/build_ref.py) on the box's host cores, all
+                      host threads, same workload / metric / unit; the CPU oracle port
+                      (oracle/train_step.py) only if oracle/_ref is missing.
 
 Prints ONE JSON line on rank 0.  ``value`` = whole-job train steps/s with inputs resident in HBM
 (CUDA events, max over ranks); ``e2e`` = the same through ``WorldModel._train`` /
@@ -77,15 +79,38 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.samples)}
 
 
+def workload_string(suite):
+    """One string for both arms (the driver compares ``config`` across them)."""
+    return (f"{suite} (configs.yaml defaults): 16x64 replay batch per GPU, H=15 imagination from 1024 "
+            f"starts, fp32, WM+actor+critic Adam updates")
+
+
+def bench_config(suite, world):
+    """``config`` of the JSON line -- identical in both arms."""
+    return {"workload": workload_string(suite), "suite": suite, "batch": [16, 64], "horizon": 15,
+            "parallelism": f"dp{world}",
+            "why_this_config": "the north star quotes its target at dmc_proprio sizes; dmc_vision / atari100k "
+                               "(--suite, and `other_suites` of the N=1 line) share the RSSM / imagination sizes "
+                               "(embed 4096) and add conv encoder/decoder stacks",
+            "l2": "no explicit flush: one step touches ~75 MB of weights+Adam state x3 and >1 GB of "
+                  "activations, far above the 126 MB L2"}
+
+
 def _oracle_modules():
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import dv3_oracle, synth, train_step    # noqa
     return dv3_oracle, synth, train_step
 
 
+def _ref_harness():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_harness
+    return ref_harness
+
+
 def cpu_oracle_rate(suite, steps, warmup, seed=0, device="cpu"):
-    """Reference algorithm on the host cores (or, device='cuda:N', the same port run eagerly by
-    PyTorch on the GPU): steps/s of oracle Agent.train_step."""
+    """The oracle PORT of the reference algorithm on the host cores (or, device='cuda:N', the same
+    port run eagerly by PyTorch on the GPU): steps/s of oracle Agent.train_step."""
     import torch
     O, synth, TS = _oracle_modules()
     cores = os.cpu_count() or 1
@@ -112,7 +137,72 @@ def cpu_oracle_rate(suite, steps, warmup, seed=0, device="cpu"):
             times.append(dt)
     total = sum(times)
     return dict(value=len(times) / total, ms_per_step=1e3 * total / len(times), cores=cores,
-                steps=len(times))
+                steps=len(times), warmup=warmup, kind="port")
+
+
+def reference_rate(suite, steps, warmup, device="cpu"):
+    """Train steps/s of the reference itself (oracle/_ref: unmodified WorldModel._train ->
+    ImagBehavior._train, reference models.py:108, 327) on ``device``; falls back to the oracle
+    port only when the staged reference is absent (proprio suite only)."""
+    H = _ref_harness()
+    if H.available():
+        r = H.train_rate(suite, device, steps=steps, warmup=warmup)
+        r["kind"] = "reference"
+        return r
+    return cpu_oracle_rate(suite, steps, warmup, device=device)
+
+
+def host_batch(suite, cfg, seed):
+    """Synthetic replay batch as the numpy dict the reference's dataset yields."""
+    import numpy as np
+    B, T, A = cfg.batch_size, cfg.batch_length, cfg.num_actions
+    rs = np.random.RandomState(seed)
+    host = {}
+    if suite == "dmc_proprio":
+        for k, n in (("orientations", 14), ("height", 1), ("velocity", 9)):
+            host[k] = rs.randn(B, T, n).astype(np.float32)
+    else:
+        host["image"] = rs.randint(0, 255, size=(B, T, 64, 64, 3)).astype(np.uint8)
+    if cfg.actor["dist"] == "onehot":
+        host["action"] = np.eye(A, dtype=np.float32)[rs.randint(0, A, size=(B, T))]
+    else:
+        host["action"] = rs.uniform(-1, 1, size=(B, T, A)).astype(np.float32)
+    host["reward"] = rs.randn(B, T).astype(np.float32)
+    host["discount"] = np.ones((B, T), np.float32)
+    host["is_terminal"] = np.zeros((B, T), np.float32)
+    host["is_first"] = np.zeros((B, T), np.float32)
+    host["is_first"][:, 0] = 1.0
+    return host
+
+
+def suite_rate(pkg, suite, device, steps=20):
+    """Train steps/s of another BASELINE suite (configs[1] dmc_vision, configs[2] atari100k) through
+    the same graphs.TrainStepGraph API, batch resident in HBM, CUDA events."""
+    import torch
+    cfgs = pkg.configs
+    torch.manual_seed(0)
+    cfg = cfgs.make_config(suite, device=device, device_metrics=True)
+    shapes = cfgs.PROPRIO_SHAPES if suite == "dmc_proprio" else cfgs.VISION_SHAPES
+    wm = pkg.models.WorldModel(cfgs.ObsSpace(shapes), None, 0, cfg)
+    beh = pkg.models.ImagBehavior(cfg, wm)
+    batch = {k: torch.from_numpy(v).to(device) for k, v in host_batch(suite, cfg, 0).items()}
+    graph = pkg.graphs.TrainStepGraph(wm, beh, warmup=2, device_metrics=True)
+    for _ in range(6):
+        graph(batch)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        graph(batch)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    out = {"train_steps_per_s": 1e3 / ms, "ms_per_step": ms, "steps": steps,
+           "library_launches_per_step": graph.library_launches_per_step,
+           "workload": workload_string(suite)}
+    del graph, wm, beh
+    torch.cuda.empty_cache()
+    return out
 
 
 def large_imagination(pkg, device, iters=3):
@@ -157,19 +247,26 @@ def large_imagination(pkg, device, iters=3):
 
 
 def run_reference(args):
+    """The reference arm: rank 0 alone times the reference's own train step on the host cores.
+    A CPU replica's step already uses every host thread, so the host's rate in per-replica train
+    steps/s does not depend on how many replicas the GPU arm runs (N replicas back to back give
+    the same steps/s); the line therefore carries the same value for every N."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 30))
-    warm = max(1, min(args.warmup, 2))
-    r = cpu_oracle_rate(args.suite, steps, warm)
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    r = reference_rate(args.suite, steps, warm)
+    what = ("unmodified reference modules (oracle/_ref: WorldModel._train -> ImagBehavior._train)"
+            if r["kind"] == "reference" else "oracle port of the reference algorithm (oracle/train_step.py)")
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": r["steps"], "warmup": warm, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.suite} 16x64 replay batch, H=15, fp32, reference algorithm on host CPU"},
-        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-                         "sample": f"{r['steps']} full train steps (WM+AC, 16x64, H=15) after {warm} warm-up"},
+        "config": bench_config(args.suite, args.gpus),
+        "note": f"host CPU, {r['cores']} threads, one replica (rank 0); the host's rate in per-replica "
+                f"steps/s is independent of the number of GPU replicas",
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                         "sample": f"{r['steps']} full train steps (WM+AC, 16x64, H=15) after {warm} warm-up, {what}"},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -206,22 +303,7 @@ def run_ours(args):
 
     # synthetic replay batch of this rank, host copy pinned
     B, T, A = cfg.batch_size, cfg.batch_length, cfg.num_actions
-    rs = np.random.RandomState(rank)
-    host = {}
-    if args.suite == "dmc_proprio":
-        for k, n in (("orientations", 14), ("height", 1), ("velocity", 9)):
-            host[k] = rs.randn(B, T, n).astype(np.float32)
-    else:
-        host["image"] = rs.randint(0, 255, size=(B, T, 64, 64, 3)).astype(np.uint8)
-    if cfg.actor["dist"] == "onehot":
-        host["action"] = np.eye(A, dtype=np.float32)[rs.randint(0, A, size=(B, T))]
-    else:
-        host["action"] = rs.uniform(-1, 1, size=(B, T, A)).astype(np.float32)
-    host["reward"] = rs.randn(B, T).astype(np.float32)
-    host["discount"] = np.ones((B, T), np.float32)
-    host["is_terminal"] = np.zeros((B, T), np.float32)
-    host["is_first"] = np.zeros((B, T), np.float32)
-    host["is_first"][:, 0] = 1.0
+    host = host_batch(args.suite, cfg, rank)
     pinned = {k: torch.from_numpy(v).pin_memory() for k, v in host.items()}
     resident = {k: v.to(device) for k, v in pinned.items()}
     h2d_bytes = sum(v.numel() * v.element_size() for v in pinned.values())
@@ -361,15 +443,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.suite} (configs.yaml defaults): 16x64 replay batch per GPU, "
-                               f"H=15 imagination from 1024 starts, fp32, WM+actor+critic Adam updates",
-                   "suite": args.suite, "batch": [B, T], "horizon": cfg.imag_horizon,
-                   "parallelism": f"dp{world}",
-                   "why_this_config": "the north star quotes its target at dmc_proprio sizes; dmc_vision / atari100k "
-                                      "(--suite) have the same RSSM / imagination sizes (embed 4096) and add conv "
-                                      "encoder/decoder stacks that SURVEY 8f ranks as a later row (cuDNN here)",
-                   "l2": "no explicit flush: one step touches ~75 MB of weights+Adam state x3 and >1 GB of "
-                         "activations, far above the 126 MB L2"},
+        "config": bench_config(args.suite, world),
         "clocks": sampler.summary() if sampler else None,
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),
@@ -401,19 +475,32 @@ def run_ours(args):
             line["large_imagination"] = li
         except Exception as e:      # informational only
             line["large_imagination"] = {"error": str(e)[:160]}
+        line["other_suites"] = {}
+        for other in ("dmc_vision", "atari100k"):
+            if other == args.suite:
+                continue
+            try:
+                line["other_suites"][other] = suite_rate(pkg, other, device)
+            except Exception as e:      # informational only
+                line["other_suites"][other] = {"error": f"{type(e).__name__}: {str(e)[:160]}"}
     if world == 1 and not args.no_cpu_baseline:
-        r = cpu_oracle_rate(args.suite, steps=3, warmup=1)
-        line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-                                "sample": "3 full train steps (WM+AC, 16x64, H=15) after 1 warm-up, "
-                                          "oracle/train_step.py on all host threads"}
+        r = reference_rate(args.suite, steps=5, warmup=1)
+        line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                                "sample": "5 full train steps (WM+AC, 16x64, H=15) after 1 warm-up, "
+                                          + ("unmodified reference modules (oracle/_ref) on all host threads"
+                                             if r["kind"] == "reference" else
+                                             "oracle/train_step.py on all host threads")}
+        # the north star's comparator: the reference's stock eager PyTorch-CUDA step on this same GPU
         try:
-            g = cpu_oracle_rate(args.suite, steps=10, warmup=3, device=device)
-            line["cpu_baseline"]["same_algorithm_eager_torch_on_this_gpu"] = {
-                "value": g["value"], "unit": UNIT, "ms_per_step": g["ms_per_step"],
-                "note": "the oracle port run op by op by PyTorch on cuda:0 (the north star's 'same-box "
-                        "PyTorch-CUDA' comparator; the port issues fewer ops than the reference's own code)"}
+            g = reference_rate(args.suite, steps=50, warmup=10, device=device)
+            line["reference_same_gpu"] = {
+                "value": g["value"], "unit": UNIT, "ms_per_step": g["ms_per_step"], "kind": g["kind"],
+                "steps": g["steps"], "warmup": g["warmup"],
+                "speedup_value": value / g["value"], "speedup_e2e": e2e / g["value"],
+                "note": "unmodified reference WorldModel._train -> ImagBehavior._train on cuda:0, eager "
+                        "PyTorch (models.py:108, 327), same batch shape; target >= 20x"}
         except Exception as e:          # informational only
-            line["cpu_baseline"]["same_algorithm_eager_torch_on_this_gpu"] = {"error": str(e)[:120]}
+            line["reference_same_gpu"] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
     print(json.dumps(line), flush=True)
     leave()
 
@@ -421,7 +508,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--suite", default="dmc_proprio", choices=["dmc_proprio", "dmc_vision", "atari100k"])

@@ -211,7 +211,15 @@ def check(rc: int, what: str):
 
 
 def stream_ptr() -> C.c_void_p:
+    """The current stream of the CURRENT device; ``fptr`` / ``iptr`` refuse tensors that live on
+    another device, so a launch can never land on the wrong GPU's stream."""
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _check_device(t):
+    if t.device.index != torch.cuda.current_device():
+        raise Dv3Error(f"tensor on {t.device} but the current CUDA device is "
+                       f"cuda:{torch.cuda.current_device()}: wrap the call in torch.cuda.device(...)")
 
 
 def fptr(t):
@@ -221,6 +229,7 @@ def fptr(t):
     if t.dtype != torch.float32 or not t.is_contiguous() or not t.is_cuda:
         raise Dv3Error(f"expected contiguous fp32 CUDA tensor, got {t.dtype} "
                        f"{'contig' if t.is_contiguous() else 'strided'} on {t.device}")
+    _check_device(t)
     return C.cast(C.c_void_p(t.data_ptr()), _f)
 
 
@@ -229,6 +238,7 @@ def iptr(t):
         return None
     if t.dtype != torch.int32 or not t.is_contiguous() or not t.is_cuda:
         raise Dv3Error(f"expected contiguous int32 CUDA tensor, got {t.dtype} on {t.device}")
+    _check_device(t)
     return C.cast(C.c_void_p(t.data_ptr()), _i)
 
 

@@ -44,7 +44,9 @@ SUITES = {
     "crafter": dict(dyn_hidden=1024, dyn_deter=4096, units=1024,             # configs.yaml:158-174
                     encoder=dict(mlp_keys="$^", cnn_keys="image", cnn_depth=96),
                     decoder=dict(mlp_keys="$^", cnn_keys="image", cnn_depth=96),
-                    actor=dict(layers=5, dist="onehot", std="none"), critic=dict(layers=5),
+                    # the reference's overlay writes `value: {layers: 5}`, a key nothing reads
+                    # (the critic is built from `critic`, models.py:246-257): its critic keeps 2 layers
+                    actor=dict(layers=5, dist="onehot", std="none"),
                     reward_head=dict(layers=5), cont_head=dict(layers=5),
                     imag_gradient="reinforce", num_actions=17),
 }

@@ -91,13 +91,21 @@ class TrainStepGraph:
         else:
             if self._graph is None:
                 torch.cuda.synchronize()
+                # planes cached by an eager forward since the last optimizer step must not be
+                # reused by the capture: the split kernels have to be recorded in the graph
+                K.invalidate_weight_splits()
                 self._graph = torch.cuda.CUDAGraph()
                 n0 = K.L.lib().dv3_launch_count()
                 with torch.cuda.graph(self._graph, stream=self._stream):
                     self._out = self._run(batch)
                 self.library_launches_per_step = int(K.L.lib().dv3_launch_count() - n0)
-                K.invalidate_weight_splits()     # planes cached during capture live in the pool
             self._graph.replay()
+            # A replay rewrites the flat parameter buffers (fused Adam, slow-critic EMA) without
+            # running any Python: neither the epoch nor a version counter moves, so planes cached
+            # by eager forwards between steps (Dreamer._policy -> actor(feat), the encoder,
+            # video_pred) would go stale -- and planes cached during capture live in the graph's
+            # private pool.  Every replay therefore ends the epoch.
+            K.invalidate_weight_splits()
             out = self._out
         self._calls += 1
         if self.device_metrics:

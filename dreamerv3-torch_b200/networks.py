@@ -138,25 +138,46 @@ class RSSM(nn.Module):
         swap = lambda x: x.permute([1, 0] + list(range(2, x.dim())))
         return dict(stoch=swap(stoch), deter=swap(feat[1:, :, SC:]), logit=swap(logit[1:]))
 
+    def _mode_of(self, logit):
+        """one-hot mode of the unimix categorical (tools.py:448-450), value only."""
+        lead = logit.shape[:-2]
+        lg = logit.detach().reshape(-1, self._stoch, self._discrete).contiguous().float()
+        _, hot = K.onehot_sample(lg, None, float(self._unimix_ratio))
+        return hot.reshape(tuple(lead) + (self._stoch, self._discrete))
+
     def obs_step(self, prev_state, prev_action, embed, is_first, sample=True, noise=None):
-        if not sample:
-            raise NotImplementedError("obs_step(sample=False)")
+        """networks.py:174-206.  ``prev_state is None`` (the acting path's first call,
+        dreamer.py:117-127) starts every row from ``initial()`` with a zero action, exactly like
+        rows whose ``is_first`` is set; ``sample=False`` returns the posterior mode (the prior draw
+        inside ``img_step`` is still a sample, as in the reference).  ``noise`` = (u_prior, u_post)
+        uniforms [n,S,C]."""
         n = embed.shape[0]
+        first = is_first.reshape(n, 1).to(torch.float32)
+        if prev_state is None:
+            prev_action = torch.zeros(n, self._num_actions, device=embed.device)
+        elif prev_action is None:
+            raise L.Dv3Error("obs_step: prev_action is None but prev_state is given")
         if noise is not None:
             noise = (noise[0].reshape(1, n, self._stoch, self._discrete),
                      noise[1].reshape(1, n, self._stoch, self._discrete))
-        post, prior = self.observe(embed[:, None], prev_action[:, None].clone(),
-                                   is_first.reshape(n, 1).float(), prev_state, noise)
-        return {k: v[:, 0] for k, v in post.items()}, {k: v[:, 0] for k, v in prior.items()}
+        post, prior = self.observe(embed[:, None], prev_action[:, None].to(torch.float32).clone(),
+                                   first, prev_state, noise)
+        post = {k: v[:, 0] for k, v in post.items()}
+        prior = {k: v[:, 0] for k, v in prior.items()}
+        if not sample:
+            post["stoch"] = self._mode_of(post["logit"])
+        return post, prior
 
     def img_step(self, prev_state, prev_action, sample=True, noise=None):
-        if not sample:
-            raise NotImplementedError("img_step(sample=False)")
+        """networks.py:208-233; ``noise`` = uniforms [n,S,C] for the prior draw."""
         n = prev_action.shape[0]
         if noise is not None:
             noise = torch.cat([noise.reshape(1, n, self._stoch, self._discrete)] * 2, 0)
         out = self.imagine_with_action(prev_action[:, None], prev_state, noise)
-        return {k: v[:, 0] for k, v in out.items()}
+        out = {k: v[:, 0] for k, v in out.items()}
+        if not sample:
+            out["stoch"] = self._mode_of(out["logit"])
+        return out
 
     def get_feat(self, state):
         """cat(flat(stoch), deter) (reference networks.py:154-159).  The imagination kernel already

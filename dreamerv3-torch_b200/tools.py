@@ -302,7 +302,6 @@ class GradSync:
 
     def __init__(self, group=None):
         import torch.distributed as dist
-        self.dist = dist
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
 
@@ -310,23 +309,55 @@ class GradSync:
         """Average one flat gradient buffer in place (tools.Optimizer's CUDA path)."""
         if self.world == 1:
             return
-        self.dist.all_reduce(flat_grad, op=self.dist.ReduceOp.SUM, group=self.group)
+        import torch.distributed as dist
+        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=self.group)
         flat_grad.div_(self.world)
 
     def __call__(self, params):
         if self.world == 1:
             return
+        import torch.distributed as dist
         grads = [p.grad for p in params if p.grad is not None]
         if not grads:
             return
         flat = torch.cat([g.reshape(-1) for g in grads])
-        self.dist.all_reduce(flat, op=self.dist.ReduceOp.SUM, group=self.group)
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
         flat.div_(self.world)
         off = 0
         for g in grads:
             n = g.numel()
             g.copy_(flat[off:off + n].view_as(g))
             off += n
+
+
+class FlatAdam(torch.optim.Optimizer):
+    """``torch.optim.Optimizer`` face of the flat fused Adam, so that the reference's checkpoint
+    helpers work unchanged on the drop-in path: ``tools.recursively_collect_optim_state_dict``
+    (reference tools.py:975-1002) only collects ``torch.optim.Optimizer`` instances -- found at
+    ``..._model_opt._opt`` -- and ``recursively_load_optim_state_dict`` (1005-1011) calls
+    ``load_state_dict`` on that attribute.  ``state_dict`` / ``load_state_dict`` speak
+    torch.optim.Adam's layout (step, exp_avg, exp_avg_sq per parameter index) and map onto the
+    owner's flat m / v / step buffers; a reference ``latest.pt`` resumes as is."""
+
+    def __init__(self, owner):
+        super().__init__(owner._params, dict(lr=owner._lr, betas=Optimizer.BETAS, eps=owner._eps,
+                                             weight_decay=0, amsgrad=False, maximize=False,
+                                             foreach=None, capturable=True, differentiable=False,
+                                             fused=True))
+        self._owner_ref = [owner]        # in a list: keep nn.Module / recursion helpers out of it
+
+    def state_dict(self):
+        return self._owner_ref[0]._flat_state_dict()
+
+    def load_state_dict(self, sd):
+        self._owner_ref[0]._load_flat_state_dict(sd)
+
+    def step(self, closure=None):
+        raise RuntimeError("FlatAdam is stepped by tools.Optimizer.__call__ (dv3_adam_clip_step)")
+
+    def zero_grad(self, set_to_none=True):
+        for p in self._owner_ref[0]._params:
+            p.grad = None
 
 
 class Optimizer:
@@ -360,7 +391,7 @@ class Optimizer:
                       all(p.is_cuda and p.dtype == torch.float32 for p in self._params))
         if self._flat:
             self._build_flat()
-            self._opt = None
+            self._opt = FlatAdam(self)
         else:
             self._opt = torch.optim.Adam(self._params, lr=lr, eps=eps)
 
@@ -396,8 +427,12 @@ class Optimizer:
 
     def state_dict(self):
         """torch.optim.Adam's layout (what the reference checkpoints, dreamer.py:502-506)."""
-        if not self._flat:
-            return self._opt.state_dict()
+        return self._opt.state_dict()
+
+    def load_state_dict(self, sd):
+        self._opt.load_state_dict(sd)
+
+    def _flat_state_dict(self):
         state = {}
         if float(self._step) > 0:
             ms, vs = self._views(self._fm), self._views(self._fv)
@@ -409,10 +444,7 @@ class Optimizer:
                      fused=True, params=list(range(len(self._params))))
         return {"state": state, "param_groups": [group]}
 
-    def load_state_dict(self, sd):
-        if not self._flat:
-            self._opt.load_state_dict(sd)
-            return
+    def _load_flat_state_dict(self, sd):
         ms, vs = self._views(self._fm), self._views(self._fv)
         with torch.no_grad():
             for i, st in sd.get("state", {}).items():

@@ -1,13 +1,16 @@
-"""Drive the LIVE reference (/root/reference) on CPU -- build-container only, test infrastructure.
+"""Drive the UNMODIFIED reference modules -- test / measurement infrastructure, never product.
 
-Used by ``oracle/pin_against_reference.py`` (pins the oracle) and
-``tests/golden/make_golden.py`` (writes the committed fixtures).  Nothing here is imported
-by the product, by ``-m gpu`` tests, ``smoke()`` or ``bench.py``: /root/reference does not
-exist on the GPU box.
+The reference tree is looked up at ``$DV3_REFERENCE_DIR``, then /root/reference (the build
+container), then ``oracle/_ref`` (the copy staged by ``oracle/build_ref.py``, which travels to the
+GPU box).  Used by ``oracle/pin_against_reference.py`` (pins the oracle), by
+``tests/golden/make_golden.py`` (writes the committed fixtures), by ``tests/test_gpu_reference.py``
+(CUDA path vs the reference itself at the real configs) and by ``bench.py``'s reference arms
+(``--impl reference``, ``cpu_baseline``, the same-GPU eager comparator).  The product package
+never imports this file.
 
-Shims -- applied to the imported modules in memory, the reference tree is
+Shims -- applied to the imported modules in memory, the reference files are
 never edited:
-  1. networks.MLP defaults device="cuda" (networks.py:606) -> patched default "cpu".
+  1. networks.MLP defaults device="cuda" (networks.py:606) -> patched to the device in use.
   2. configs.yaml is read with PyYAML, which leaves ``1e-4`` style scalars as strings.
 Supplied noise: ``torch.multinomial`` and ``torch.distributions.normal._standard_normal``
 are swapped for tape readers for the duration of a call (class NoiseTape).
@@ -19,12 +22,23 @@ import io
 import os
 import re
 import sys
+import time
 import types
 
 import numpy as np
 import torch
 
-REF = os.environ.get("DV3_REFERENCE_DIR", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_reference():
+    for cand in (os.environ.get("DV3_REFERENCE_DIR"), "/root/reference", os.path.join(_HERE, "_ref")):
+        if cand and os.path.isfile(os.path.join(cand, "networks.py")):
+            return cand
+    return os.path.join(_HERE, "_ref")
+
+
+REF = _find_reference()
 
 
 def available() -> bool:
@@ -37,17 +51,26 @@ def quiet():
         yield
 
 
-def load_reference():
-    """-> (tools, networks, models) reference modules, MLP device default patched to cpu."""
-    if REF not in sys.path:
+def load_reference(device="cpu"):
+    """-> (tools, networks, models) reference modules, MLP's device default set to ``device``.
+    The reference's module names are generic (``tools``, ``networks``, ``models``): they are
+    imported with the reference directory first on sys.path and must not be shadowed."""
+    if not available():
+        raise RuntimeError(f"reference modules not found (looked in {REF}); run oracle/build_ref.py "
+                           "in the build container")
+    if sys.path[0] != REF:
         sys.path.insert(0, REF)
+    for name in ("tools", "networks", "models"):
+        mod = sys.modules.get(name)
+        if mod is not None and os.path.dirname(os.path.abspath(getattr(mod, "__file__", "") or "")) != REF:
+            raise RuntimeError(f"module {name!r} already imported from elsewhere: {mod.__file__}")
     with quiet():
         import tools as rtools          # noqa
         import networks as rnetworks    # noqa
         import models as rmodels        # noqa
     dflt = list(rnetworks.MLP.__init__.__defaults__)
     names = rnetworks.MLP.__init__.__code__.co_varnames[1:rnetworks.MLP.__init__.__code__.co_argcount]
-    dflt[len(dflt) - (len(names) - names.index("device"))] = "cpu"
+    dflt[len(dflt) - (len(names) - names.index("device"))] = str(device)
     rnetworks.MLP.__init__.__defaults__ = tuple(dflt)
     return rtools, rnetworks, rmodels
 
@@ -71,6 +94,9 @@ def _merge(base, upd):
             _merge(base[k], v)
         else:
             base[k] = v
+
+
+SUITE_ACTIONS = {"dmc_proprio": 6, "dmc_vision": 6, "atari100k": 18, "crafter": 17}
 
 
 def reference_config(overlays=("dmc_proprio",), num_actions=6, **extra):
@@ -168,8 +194,8 @@ def synthetic_batch(B=16, T=64, A=6, seed=0, onehot_action=False, resets=(), vis
 
 
 def build_agent(cfg, shapes, seed=0):
-    """-> (WorldModel, ImagBehavior) reference modules on CPU."""
-    rtools, rnetworks, rmodels = load_reference()
+    """-> (WorldModel, ImagBehavior) reference modules on ``cfg.device``."""
+    rtools, rnetworks, rmodels = load_reference(cfg.device)
     torch.manual_seed(seed)
     with quiet():
         wm = rmodels.WorldModel(ObsSpace(shapes), None, 0, cfg)
@@ -177,3 +203,50 @@ def build_agent(cfg, shapes, seed=0):
     wm.requires_grad_(False)
     beh.requires_grad_(False)
     return wm, beh
+
+
+def suite_shapes(suite):
+    return PROPRIO_SHAPES if suite == "dmc_proprio" else VISION_SHAPES
+
+
+def suite_batch(suite, B=16, T=64, seed=0, resets=()):
+    """The synthetic replay batch of a suite as the reference's dataset yields it (numpy dict);
+    proprio batches carry a dummy ``image`` because ``preprocess`` divides it unconditionally
+    (models.py:180)."""
+    A = SUITE_ACTIONS[suite]
+    data = synthetic_batch(B, T, A, seed, onehot_action=(suite in ("atari100k", "crafter")),
+                           resets=resets, vision=(suite != "dmc_proprio"))
+    if suite == "dmc_proprio":
+        data["image"] = np.zeros((B, T, 2, 2, 3), np.uint8)
+    return data
+
+
+def train_rate(suite="dmc_proprio", device="cpu", steps=3, warmup=1, seed=0, B=16, T=64):
+    """Train steps/s of the reference's own ``WorldModel._train`` -> ``ImagBehavior._train``
+    (the body of Dreamer._train, dreamer.py:194-200) on ``device``: 'cpu' = all host threads,
+    'cuda:N' = the reference's stock eager PyTorch-CUDA path.  Sampling noise comes from torch's
+    global generator, as in the reference."""
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = reference_config((suite,), num_actions=SUITE_ACTIONS[suite], device=str(device))
+    wm, beh = build_agent(cfg, suite_shapes(suite), seed)
+    data = suite_batch(suite, B, T, seed)
+    reward_fn = lambda f, s, a: wm.heads["reward"](wm.dynamics.get_feat(s)).mode()
+    gpu = str(device).startswith("cuda")
+    times = []
+    for i in range(warmup + steps):
+        feed = {k: v.copy() for k, v in data.items()}
+        if gpu:
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with quiet():
+            post, _, _ = wm._train(feed)
+            beh._train(post, reward_fn)
+        if gpu:
+            torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    total = sum(times)
+    return dict(value=len(times) / total, ms_per_step=1e3 * total / len(times), cores=cores,
+                steps=len(times), warmup=warmup, device=str(device))

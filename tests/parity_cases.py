@@ -3,7 +3,7 @@ oracle (oracle/dv3_oracle.py) and the CUDA path (through the C ABI via the packa
 bindings) on the same seeded inputs and report the differences.
 
 Tolerances (BASELINE.json north_star): categorical indices bit-exact; latents, losses and
-gradients within 1e-4 relative.  "relative" is max|a-b| / max|b| over a tensor.
+gradients within 1e-4 relative, element-wise with an absolute floor (see ``rel``).
 """
 from __future__ import annotations
 
@@ -21,7 +21,24 @@ import synth                # noqa: E402
 RTOL = 1e-4
 
 
+ELEM_FLOOR = 0.05
+
+
 def rel(a, b):
+    """Element-wise relative error with an absolute floor: max_i |a_i - b_i| / max(|b_i|,
+    ELEM_FLOOR * max|b|).  Elements down to 5 % of the tensor's largest magnitude are held to
+    their own 1e-4; smaller ones (whose fp32 rounding error is set by the magnitude of the terms
+    summed, not by the result) to 1e-4 of that floor.  Always >= the tensor-max measure
+    max|a-b| / max|b| that round 1 used."""
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    if b.numel() == 0:
+        return 0.0
+    floor = ELEM_FLOOR * float(b.abs().max()) + 1e-12
+    return float(((a - b).abs() / torch.clamp(b.abs(), min=floor)).max())
+
+
+def rel_max(a, b):
+    """Tensor-max measure (reported next to ``rel`` where useful)."""
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
     return float((a - b).abs().max() / (b.abs().max() + 1e-12))
 
@@ -289,6 +306,79 @@ def imagine_with_action_case(pkg, device, config="dmc_proprio", B=6, T=8, seed=0
                                  != ref["stoch"].argmax(-1)).sum()),
             "deter": rel(feat[1:, :, d.flat:].permute(1, 0, 2), ref["deter"]),
             "logit": rel(logit[1:].permute(1, 0, 2, 3), ref["logit"])}
+
+
+def policy_walk_case(pkg, device, config="dmc_proprio", n=5, steps=5, seed=0):
+    """Dreamer._policy's call order (reference dreamer.py:117-190) through the PUBLIC methods:
+    obs_step(None, None, embed, is_first) on the first call, then obs_step(latent, action, ...)
+    with a mid-episode reset, get_feat, actor(feat).sample() / .mode() / .log_prob(action) --
+    against the oracle fed the same uniforms / normals; the state fed back is the product's own
+    (free-running, as in acting)."""
+    c = synth.CONFIGS[config]
+    d = synth.dims_of(config)
+    p = synth.rssm_params(d, seed)
+    pa = synth.actor_params(config, seed + 1)
+    cfgs = pkg.configs
+    cfg = cfgs.make_config("dmc_proprio", device=device, num_actions=d.actions, dyn_stoch=d.stoch,
+                           dyn_discrete=d.classes, dyn_deter=d.deter, dyn_hidden=d.hidden,
+                           units=c["units"])
+    dyn = pkg.networks.RSSM(cfg.dyn_stoch, cfg.dyn_deter, cfg.dyn_hidden, 1, cfg.dyn_discrete,
+                            cfg.act, cfg.norm, cfg.dyn_mean_act, cfg.dyn_std_act, cfg.dyn_min_std,
+                            cfg.unimix_ratio, cfg.initial, d.actions, d.embed, device).to(device)
+    dyn.load_state_dict({k: v.to(device) for k, v in p.items()}, strict=True)
+    actor = pkg.networks.MLP(d.flat + d.deter, (d.actions,), c["actor_layers"], c["units"], "SiLU",
+                             True, "normal", "learned", 0.1, 1.0, absmax=1.0, name="Actor").to(device)
+    actor.load_state_dict({k: v.to(device) for k, v in pa.items()}, strict=True)
+    g = torch.Generator().manual_seed(seed + 11)
+    res = {"idx_mismatch": 0, "deter": 0.0, "post_logit": 0.0, "prior_logit": 0.0, "feat": 0.0,
+           "action": 0.0, "mode": 0.0, "logprob": 0.0, "mode_state_mismatch": 0}
+    latent = action = None        # product state
+    o_prev = o_act = None         # oracle state
+    with torch.no_grad():
+        for t in range(steps):
+            embed = torch.randn(n, d.embed, generator=g)
+            is_first = torch.zeros(n)
+            if t == 0:
+                is_first[:] = 1.0
+            if t == 2:
+                is_first[1] = 1.0
+            if t == 3:
+                is_first[:] = 1.0               # the all-rows-reset branch (networks.py:176)
+            up, uq = synth.uniforms(g, n, d.stoch, d.classes), synth.uniforms(g, n, d.stoch, d.classes)
+            eps = torch.randn(n, d.actions, generator=g)
+            sample = t != 4                     # last step: obs_step(sample=False) -> mode
+            post_o, prior_o = O.obs_step(p, o_prev, o_act, embed, is_first, up,
+                                         uq if sample else None, d)
+            post, prior = dyn.obs_step(latent, action, embed.to(device), is_first.to(device),
+                                       sample=sample, noise=(up.to(device), uq.to(device)))
+            res["idx_mismatch"] += int((post["stoch"].argmax(-1).cpu() != post_o["stoch"].argmax(-1)).sum())
+            res["idx_mismatch"] += int((prior["stoch"].argmax(-1).cpu() != prior_o["stoch"].argmax(-1)).sum())
+            res["deter"] = max(res["deter"], rel(post["deter"], post_o["deter"]))
+            res["post_logit"] = max(res["post_logit"], rel(post["logit"], post_o["logit"]))
+            res["prior_logit"] = max(res["prior_logit"], rel(prior["logit"], prior_o["logit"]))
+            feat = dyn.get_feat(post)
+            feat_o = O.get_feat(post_o)
+            res["feat"] = max(res["feat"], rel(feat, feat_o))
+            dist = actor(feat)
+            mean_o, std_o = O.actor_normal_stats(pa, feat_o, c["actor_layers"])
+            act = dist.sample(eps=eps.to(device))
+            act_o = O.contdist_sample(mean_o, std_o, eps)
+            res["action"] = max(res["action"], rel(act, act_o))
+            res["mode"] = max(res["mode"], rel(dist.mode(), O.contdist_sample(mean_o, std_o, torch.zeros_like(eps))))
+            res["logprob"] = max(res["logprob"], rel(dist.log_prob(act), O.normal_logprob(mean_o, std_o, act_o)))
+            latent = {k: v.detach() for k, v in post.items()}
+            action = act.detach()
+            o_prev, o_act = post_o, act_o
+        # img_step public method, sample and mode
+        u = synth.uniforms(g, n, d.stoch, d.classes)
+        nxt = dyn.img_step(latent, action, noise=u.to(device))
+        nxt_o = O.img_step(p, o_prev, o_act, u, d)
+        res["idx_mismatch"] += int((nxt["stoch"].argmax(-1).cpu() != nxt_o["stoch"].argmax(-1)).sum())
+        res["img_step_logit"] = rel(nxt["logit"], nxt_o["logit"])
+        nm = dyn.img_step(latent, action, sample=False)
+        nm_o = O.img_step(p, o_prev, o_act, None, d)
+        res["mode_state_mismatch"] = int((nm["stoch"].argmax(-1).cpu() != nm_o["stoch"].argmax(-1)).sum())
+    return res
 
 
 # --------------------------------------------------------------------------------------

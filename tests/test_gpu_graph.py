@@ -63,3 +63,51 @@ def test_graph_step_matches_eager(pkg, device):
         assert float((a - b).abs().max()) <= 2e-6, k
     for (k, a), b in zip(beh_a.state_dict().items(), beh_b.state_dict().values()):
         assert float((a.float() - b.float()).abs().max()) <= 2e-6, k
+
+
+def test_eager_forwards_between_replays_see_updated_weights(pkg, device):
+    """The acting path runs eager forwards (encoder, actor) between graph replays
+    (INTEGRATION.md flow: TrainStepGraph inside Dreamer._train, Dreamer._policy between steps).
+    Their cached tf32 weight planes must follow the weights the replays update: compare against
+    a twin agent trained by eager calls (whose optimizer invalidates the cache itself)."""
+    B, T = 6, 10
+    cfg, wm_a, beh_a = _agent(pkg, device)
+    _, wm_b, beh_b = _agent(pkg, device)
+    wm_b.load_state_dict(wm_a.state_dict())
+    beh_b.load_state_dict(beh_a.state_dict())
+    A, S, C, H = cfg.num_actions, cfg.dyn_stoch, cfg.dyn_discrete, cfg.imag_horizon
+    N = B * T
+    graph = pkg.graphs.TrainStepGraph(wm_b, beh_b, warmup=2)
+    reward = lambda f, s, a: wm_a.heads["reward"](wm_a.dynamics.get_feat(s)).mode()
+    rs = np.random.RandomState(3)
+    gen = torch.Generator().manual_seed(5)
+    feat = torch.randn(64, S * C + cfg.dyn_deter, generator=gen).to(device)
+    obs = {k: torch.randn(64, n, generator=gen).to(device)
+           for k, n in (("orientations", 14), ("height", 1), ("velocity", 9))}
+
+    def policy_outputs(wm, beh):
+        with torch.no_grad():
+            dist = beh.actor(feat)                      # eager MLP forward: caches weight planes
+            return dist.mean.clone(), dist.std.clone(), wm.encoder(obs).clone()
+
+    for step in range(6):
+        data = _batch(rs, B, T, A)
+        noise = dict(u_prior=torch.rand(T, B, S, C, generator=gen).clamp_(1e-30, 1.0),
+                     u_post=torch.rand(T, B, S, C, generator=gen).clamp_(1e-30, 1.0),
+                     act_noise=torch.randn(H, N, A, generator=gen),
+                     u_state=torch.rand(H, N, S, C, generator=gen).clamp_(1e-30, 1.0))
+        nd = {k: v.to(device) for k, v in noise.items()}
+        post, _, _ = wm_a._train(data, noise=(nd["u_prior"], nd["u_post"]))
+        beh_a._train(post, reward, noise=(nd["act_noise"], nd["u_state"]))
+        # eager forwards on the graph agent BEFORE the step (also right before the capture call)
+        policy_outputs(wm_b, beh_b)
+        graph(data, noise=noise)
+        ref = policy_outputs(wm_a, beh_a)
+        got = policy_outputs(wm_b, beh_b)
+        for name, a, b in zip(("mean", "std", "embed"), got, ref):
+            assert float((a - b).abs().max()) <= 2e-5 * float(b.abs().max()) + 1e-6, (step, name)
+    assert graph.captured
+    # and the weights did move, so a stale cache would have been visible
+    with torch.no_grad():
+        fresh = _agent(pkg, device)[2].actor(feat).mean
+    assert float((fresh - got[0]).abs().max()) > 1e-5

@@ -72,6 +72,25 @@ def test_imagine_fwd_bwd(pkg, device, config, N, H):
     _assert(pc.imagine_case(pkg, device, config=config, N=N, H=H))
 
 
+def test_policy_walk_public_methods(pkg, device):
+    """Dreamer._policy (dreamer.py:117-190) through RSSM.obs_step(None, None, ...) / obs_step /
+    img_step / get_feat / actor(feat): the acting path's public-method surface."""
+    _assert(pc.policy_walk_case(pkg, device))
+
+
+def test_imagine_large_config(pkg, device):
+    """BASELINE configs[3] (reference configs.yaml:158-174): 1024 starts x H=15, dyn_deter 4096,
+    dyn_hidden / units 1024, 5-layer one-hot actor, 17 actions -- forward + actor gradients.  The
+    block-per-row GRU gate kernels (D = 4096), the 5-layer actor loop and every GEMM tiling that
+    the `large_imagination` bench numbers come from."""
+    _assert(pc.imagine_case(pkg, device, config="large", N=1024, H=15))
+
+
+def test_observe_large_config(pkg, device):
+    """The same widths through observe (stepwise path; E = 12288), forward + every gradient."""
+    _assert(pc.observe_case(pkg, device, config="large", B=16, T=6))
+
+
 def test_imagine_with_action(pkg, device):
     _assert(pc.imagine_with_action_case(pkg, device))
 

@@ -24,6 +24,23 @@ def test_linear_tc_matches_fp64(pkg, device, M, N, K):
     assert float((out2.double() - ref2).abs().max() / ref2.abs().max()) < 5e-6
 
 
+def test_gemm_config4_gru_product_matches_fp64(pkg, device):
+    """The GRU product of BASELINE configs[3]: [x|h] (1024 x 5120) times W_gru^T (12288 x 5120),
+    two K segments, pre-split planes -- the launch the tensor-pipe figures are quoted on."""
+    g = torch.Generator().manual_seed(4)
+    M, N, K1, K2 = 1024, 12288, 1024, 4096
+    x = torch.randn(M, K1, generator=g).to(device)
+    h = torch.tanh(torch.randn(M, K2, generator=g)).to(device)
+    w = (torch.randn(N, K1 + K2, generator=g) / (K1 + K2) ** 0.5).to(device)
+    out = pkg.kernels.gemm_tc(x, w, A2=h)
+    ref = torch.cat([x, h], 1).double() @ w.double().t()
+    err = float((out.double() - ref).abs().max() / ref.abs().max())
+    assert err < 5e-6, err
+    dx = pkg.kernels.gemm_tc(out, w, b_t=True)                 # dy W, K = 12288
+    refx = out.double() @ w.double()
+    assert float((dx.double() - refx).abs().max() / refx.abs().max()) < 5e-6
+
+
 @pytest.mark.parametrize("M,N,K", [(96, 80, 40), (512, 1536, 1000), (14, 1024, 15)])
 def test_linear_tc_transposed_operands(pkg, device, M, N, K):
     g = torch.Generator().manual_seed(1)

@@ -25,6 +25,13 @@ from . import tools
 
 LN_EPS = 1e-3
 
+# fp32 is the contract of this path (precision: 32, parity to 1e-4 with bit-exact categorical
+# draws).  cuDNN convolutions default to TF32 on sm_80+ (torch.backends.cudnn.allow_tf32 = True),
+# which puts ~1e-3 of error into the conv encoder's embedding -- enough to flip posterior draws
+# against the reference's fp32 CPU path (tests/test_gpu_reference.py found 15 flips per 16x64
+# batch).  Forward and backward convolutions both read this process-wide flag.
+torch.backends.cudnn.allow_tf32 = False
+
 
 class GRUCell(nn.Module):
     """Parameter holder for the LayerNorm GRU (names match reference networks.py:742-758); the

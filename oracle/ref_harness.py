@@ -200,6 +200,10 @@ def build_agent(cfg, shapes, seed=0):
     with quiet():
         wm = rmodels.WorldModel(ObsSpace(shapes), None, 0, cfg)
         beh = rmodels.ImagBehavior(cfg, wm)
+    # the reference's modules do not place themselves: dreamer.py moves the whole agent with
+    # ``Dreamer(...).to(config.device)`` (dreamer.py:~590)
+    wm.to(cfg.device)
+    beh.to(cfg.device)
     wm.requires_grad_(False)
     beh.requires_grad_(False)
     return wm, beh

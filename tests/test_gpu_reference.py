@@ -73,6 +73,10 @@ def _reference_step(suite, seed, B=16, T=64):
 
 
 def _product_step(pkg, device, suite, ref):
+    """WorldModel._train from the reference's initial state_dict; then -- so that the behaviour
+    half is compared on identical weights rather than through the Adam sign noise of the WM update
+    (an element whose gradient is at fp32-noise level moves by +-lr) -- the reference's updated WM
+    weights and posterior are loaded before ImagBehavior._train."""
     cfgs = pkg.configs
     cfg = cfgs.make_config(suite, device=device)
     shapes = cfgs.PROPRIO_SHAPES if suite == "dmc_proprio" else cfgs.VISION_SHAPES
@@ -88,8 +92,11 @@ def _product_step(pkg, device, suite, ref):
     if suite == "dmc_proprio":
         data.pop("image")
     post, _, m1 = wm._train(data, noise=(n["u_prior"], n["u_post"]))
-    _, state, action, _, m2 = beh._train(post, reward_fn, noise=(n["act_noise"], n["u_state"]))
-    return wm, beh, post, state, action, {**m1, **m2}
+    wm_after = {k: v.detach().clone() for k, v in wm.state_dict().items()}
+    wm.load_state_dict(ref["after"]["wm"], strict=True)
+    start = {k: v.to(device) for k, v in ref["post"].items()}
+    _, state, action, _, m2 = beh._train(start, reward_fn, noise=(n["act_noise"], n["u_state"]))
+    return wm_after, beh, post, state, action, {**m1, **m2}
 
 
 METRICS = ("model_loss", "model_grad_norm", "actor_loss", "actor_grad_norm", "value_loss",
@@ -106,7 +113,7 @@ def test_whole_train_step_vs_reference_itself(pkg, device, suite):
     tried = []
     for seed in (0, 1, 2):
         ref = _reference_step(suite, seed)
-        wm, beh, post, state, action, m = _product_step(pkg, device, suite, ref)
+        wm_after, beh, post, state, action, m = _product_step(pkg, device, suite, ref)
         flips = int((post["stoch"].argmax(-1).cpu() != ref["post"]["stoch"].argmax(-1)).sum())
         flips_im = int((state["stoch"].argmax(-1).cpu() != ref["imag_idx"]).sum())
         tried.append((seed, flips, flips_im))
@@ -125,9 +132,9 @@ def test_whole_train_step_vs_reference_itself(pkg, device, suite):
         assert not bad, (suite, seed, bad)
         # Adam turns a gradient into ~lr*sign(g) on the first step: elements whose gradient is at
         # fp32-noise level may move by up to lr in either direction
-        for mod, key, lr in ((wm, "wm", 1e-4), (beh.actor, "actor", 3e-5), (beh.value, "value", 3e-5),
-                             (beh._slow_value, "slow", 3e-5)):
-            sd = mod.state_dict()
+        for sd, key, lr in ((wm_after, "wm", 1e-4), (beh.actor.state_dict(), "actor", 3e-5),
+                            (beh.value.state_dict(), "value", 3e-5),
+                            (beh._slow_value.state_dict(), "slow", 3e-5)):
             for k, r in ref["after"][key].items():
                 diff = (sd[k].cpu() - r).abs()
                 assert float(diff.max()) <= 2 * lr + 1e-6, (suite, key, k, float(diff.max()))

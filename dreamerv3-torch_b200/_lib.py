@@ -170,6 +170,7 @@ SIGNATURES = {
     "dv3_ln_silu_bwd_split": (C.c_int, [_f, _i32, _f, _f, _f32, _f, _i32, _i32, _i32, _f, _f, _i32,
                                         _f, _f, _i32, _v]),
     "dv3_ln_param_grads": (C.c_int, [_f, _i32, _f, _i32, _f32, _i32, _i32, _f, _f, _v]),
+    "dv3_ln_param_grads_acc": (C.c_int, [_f, _i32, _f, _i32, _f32, _i32, _i32, _f, _f, _v]),
     "dv3_gru_gates_fwd": (C.c_int, [_f, _i32, _f, _f, _f32, _f, _i32, _i32, _i32, _f, _i32, _v]),
     "dv3_gru_gates_bwd": (C.c_int, [_f, _i32, _f, _f, _f32, _f, _i32, _f, _i32, _i32, _i32, _f, _f,
                                     _i32, _f, _i32, _v]),
@@ -178,6 +179,24 @@ SIGNATURES = {
     "dv3_onehot_sample": (C.c_int, [_f, _f, _f32, _i32, _i32, _i32, _i, _f, _i32, _v]),
     "dv3_onehot_st_bwd": (C.c_int, [_f, _f, _f, _f32, _i32, _i32, _i32, _f, _v]),
     "dv3_idx_to_onehot": (C.c_int, [_i, _i32, _i32, _i32, _f, _i32, _v]),
+    "dv3_symlog": (C.c_int, [_f, C.c_longlong, _f, _v]),
+    "dv3_sqerr_logprob_fwd": (C.c_int, [_f, _f, _i32, _i32, _i32, _f32, _f, _v]),
+    "dv3_sqerr_logprob_bwd": (C.c_int, [_f, _f, _f, _i32, _i32, _i32, _f32, _f, _v]),
+    "dv3_bernoulli_logprob_fwd": (C.c_int, [_f, _f, C.c_longlong, _f, _v]),
+    "dv3_bernoulli_logprob_bwd": (C.c_int, [_f, _f, _f, C.c_longlong, _f, _v]),
+    "dv3_loss_mean_fwd": (C.c_int, [_pf, _f, _i32, _i32, _f, _f, _v]),
+    "dv3_loss_mean_bwd": (C.c_int, [_f, _f, _i32, _i32, _f, _v]),
+    "dv3_discount_weights_fwd": (C.c_int, [_f, _f32, _i32, _i32, _f, _f, _v]),
+    "dv3_discount_bwd": (C.c_int, [_f, _f, _f32, C.c_longlong, _f, _v]),
+    "dv3_reward_ema": (C.c_int, [_f, _i32, _dbl, _f, _f, _v]),
+    "dv3_actor_loss_fwd": (C.c_int, [_f, _f, _f, _f, _f, _f, _f32, _i32, _i32, _f, _f, _v]),
+    "dv3_actor_loss_bwd": (C.c_int, [_f, _f, _f, _f, _f, _f32, _i32, _i32, _i32, _f, _f, _f, _v]),
+    "dv3_value_loss_fwd": (C.c_int, [_f, _f, _f, _i32, _f, _v]),
+    "dv3_value_loss_bwd": (C.c_int, [_f, _f, _i32, _f, _v]),
+    "dv3_normal_policy_fwd": (C.c_int, [_f, _f, _f, _f32, _f32, _i32, _i32, _f, _f, _v]),
+    "dv3_normal_policy_bwd": (C.c_int, [_f, _f, _f, _f, _f, _f32, _f32, _i32, _i32, _f, _f, _f, _v]),
+    "dv3_tensorstats": (C.c_int, [_f, C.c_longlong, _f, _v]),
+    "dv3_ema_mix": (C.c_int, [_f, _f, C.c_longlong, _dbl, _v]),
 }
 
 _lib = None

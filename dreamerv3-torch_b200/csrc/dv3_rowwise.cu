@@ -1189,15 +1189,17 @@ static int launch_ln_param_grads(const float* pre, int ld, const float* d_ln, in
 
 }  // namespace dv3
 
-extern "C" int dv3_ln_param_grads(const float* pre, int32_t ld, const float* d_ln, int32_t ldl,
-                                  float eps, int32_t M, int32_t n, float* dg, float* db,
-                                  void* stream) {
+static int ln_param_grads_any(const float* pre, int32_t ld, const float* d_ln, int32_t ldl,
+                              float eps, int32_t M, int32_t n, float* dg, float* db, bool zero,
+                              void* stream) {
   using namespace dv3;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   DV3_REQUIRE(M >= 0 && n > 0 && n <= 2048, DV3_ERR_BAD_SHAPE, "ln_param_grads: M=%d n=%d", M, n);
   DV3_REQUIRE(pre && d_ln && dg && db, DV3_ERR_NULL, "ln_param_grads: null pointer");
-  DV3_CHECK_CUDA(cudaMemsetAsync(dg, 0, (size_t)n * 4, st));
-  DV3_CHECK_CUDA(cudaMemsetAsync(db, 0, (size_t)n * 4, st));
+  if (zero) {
+    DV3_CHECK_CUDA(cudaMemsetAsync(dg, 0, (size_t)n * 4, st));
+    DV3_CHECK_CUDA(cudaMemsetAsync(db, 0, (size_t)n * 4, st));
+  }
   if (M == 0) return 0;
   const int npl = (n + 31) / 32;
   if (npl <= 4) return launch_ln_param_grads<4>(pre, ld, d_ln, ldl, eps, M, n, dg, db, st);
@@ -1205,6 +1207,18 @@ extern "C" int dv3_ln_param_grads(const float* pre, int32_t ld, const float* d_l
   if (npl <= 32) return launch_ln_param_grads<32>(pre, ld, d_ln, ldl, eps, M, n, dg, db, st);
   if (npl <= 48) return launch_ln_param_grads<48>(pre, ld, d_ln, ldl, eps, M, n, dg, db, st);
   return launch_ln_param_grads<64>(pre, ld, d_ln, ldl, eps, M, n, dg, db, st);
+}
+
+extern "C" int dv3_ln_param_grads(const float* pre, int32_t ld, const float* d_ln, int32_t ldl,
+                                  float eps, int32_t M, int32_t n, float* dg, float* db,
+                                  void* stream) {
+  return ln_param_grads_any(pre, ld, d_ln, ldl, eps, M, n, dg, db, true, stream);
+}
+
+extern "C" int dv3_ln_param_grads_acc(const float* pre, int32_t ld, const float* d_ln, int32_t ldl,
+                                      float eps, int32_t M, int32_t n, float* dg, float* db,
+                                      void* stream) {
+  return ln_param_grads_any(pre, ld, d_ln, ldl, eps, M, n, dg, db, false, stream);
 }
 
 extern "C" int dv3_ln_silu_fwd(const float* pre, int32_t ld, const float* g, const float* b,

@@ -1,0 +1,553 @@
+// Step-tail kernels: the element-wise / reduction chains around the rollouts that the reference
+// spells as dozens of tiny torch ops per call (and autograd doubles in backward).  Each is one
+// launch here:
+//   symlog                                   tools.py:22-23        (encoder input, networks.py:333)
+//   squared-error log-probs                  tools.MSEDist 520-543, tools.SymlogDist 546-572
+//   Bernoulli log-prob                       tools.py:604-628      (cont head, models.py:137-147)
+//   weighted mean of per-row losses          models.py:140-152     (model_loss)
+//   discount / cumulative weights            models.py:620-638     (_compute_target)
+//   RewardEMA: 5/95 % quantiles + EMA        models.py:11-26
+//   actor loss, value loss                   models.py:640-681, 419-429
+//   normal-policy entropy / log-prob         networks.py:693-700, tools.py:575-601
+//   tensorstats                              tools.py:949-958
+// All are HBM streams over a few hundred KB; what they buy is launch count (the whole step is one
+// CUDA graph whose length is the sum of its kernels' latencies).
+#include "dv3_common.cuh"
+
+namespace dv3 {
+
+constexpr int TL_THREADS = 256;
+
+__device__ __forceinline__ float symlog_(float x) {
+  const float s = (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f);
+  return s * logf(fabsf(x) + 1.f);
+}
+// torch.nn.functional.softplus (beta 1, threshold 20)
+__device__ __forceinline__ float softplus_(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+__device__ __forceinline__ float softplus_grad_(float x) { return x > 20.f ? 1.f : sigmoidf_(x); }
+
+__global__ void symlog_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = symlog_(x[i]);
+}
+
+// logprob[r] = -sum_j d_j,  d_j = (mode - t(value))^2,  t = symlog or identity; symlog form drops
+// d_j < tol (tools.py:558-563).  One warp per row.
+__global__ void __launch_bounds__(TL_THREADS)
+sqerr_logprob_fwd_kernel(const float* __restrict__ mode, const float* __restrict__ value, int R, int n,
+                         int use_symlog, float tol, float* __restrict__ logprob) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (TL_THREADS >> 5) + (threadIdx.x >> 5);
+  if (r >= R) return;
+  const float* m = mode + (size_t)r * n;
+  const float* v = value + (size_t)r * n;
+  float acc = 0.f;
+  for (int j = lane; j < n; j += 32) {
+    const float t = use_symlog ? symlog_(v[j]) : v[j];
+    const float e = m[j] - t;
+    float d = e * e;
+    if (use_symlog && d < tol) d = 0.f;
+    acc += d;
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) logprob[r] = -acc;
+}
+
+__global__ void __launch_bounds__(TL_THREADS)
+sqerr_logprob_bwd_kernel(const float* __restrict__ mode, const float* __restrict__ value,
+                         const float* __restrict__ g, int R, int n, int use_symlog, float tol,
+                         float* __restrict__ d_mode) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (TL_THREADS >> 5) + (threadIdx.x >> 5);
+  if (r >= R) return;
+  const float* m = mode + (size_t)r * n;
+  const float* v = value + (size_t)r * n;
+  const float gr = g[r];
+  for (int j = lane; j < n; j += 32) {
+    const float t = use_symlog ? symlog_(v[j]) : v[j];
+    const float e = m[j] - t;
+    const bool drop = use_symlog && (e * e < tol);
+    d_mode[(size_t)r * n + j] = drop ? 0.f : -2.f * e * gr;
+  }
+}
+
+__global__ void bernoulli_logprob_fwd_kernel(const float* __restrict__ logit,
+                                             const float* __restrict__ x, long long n,
+                                             float* __restrict__ logprob) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float l = logit[i], xv = x[i];
+  logprob[i] = -softplus_(l) * (1.f - xv) - softplus_(-l) * xv;
+}
+
+__global__ void bernoulli_logprob_bwd_kernel(const float* __restrict__ logit,
+                                             const float* __restrict__ x,
+                                             const float* __restrict__ g, long long n,
+                                             float* __restrict__ d_logit) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float l = logit[i], xv = x[i];
+  d_logit[i] = g[i] * (-softplus_grad_(l) * (1.f - xv) + softplus_grad_(-l) * xv);
+}
+
+// out[0] = (1/R) sum_r sum_i scale_i * loss_i[r]; one block, fixed order.
+struct LossPtrs {
+  const float* p[8];
+  float scale[8];
+  int n;
+};
+
+__global__ void __launch_bounds__(1024)
+loss_mean_kernel(LossPtrs lp, int R, float* __restrict__ out, float* __restrict__ neg_out) {
+  __shared__ float red[4 * 32];
+  float acc[1] = {0.f};
+  for (int r = threadIdx.x; r < R; r += blockDim.x) {
+    float s = 0.f;
+    for (int i = 0; i < lp.n; ++i) {
+      const float v = lp.p[i][r];
+      s += lp.scale[i] * v;
+      if (neg_out) neg_out[(size_t)i * R + r] = -v;
+    }
+    acc[0] += s;
+  }
+  block_sum<1>(acc, red);
+  if (threadIdx.x == 0) out[0] = acc[0] / (float)R;
+}
+
+// grads[i][r] = g[0] * scale_i / R   (grads is [n, R])
+__global__ void loss_mean_bwd_kernel(const float* __restrict__ g, LossPtrs lp, int R,
+                                     float* __restrict__ grads) {
+  const int i = blockIdx.y;
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < R) grads[(size_t)i * R + r] = g[0] * lp.scale[i] / (float)R;
+}
+
+// discount[t,n] = gamma * sigmoid(logit[t,n]); weights[0] = 1, weights[t] = prod_{i<t} discount[i]
+__global__ void discount_weights_kernel(const float* __restrict__ logit, float gamma, int H, int N,
+                                        float* __restrict__ discount, float* __restrict__ weights) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float w = 1.f;
+  for (int t = 0; t < H; ++t) {
+    const size_t o = (size_t)t * N + n;
+    const float d = gamma * sigmoidf_(logit[o]);
+    discount[o] = d;
+    weights[o] = w;
+    w = w * d;
+  }
+}
+
+__global__ void discount_bwd_kernel(const float* __restrict__ logit, const float* __restrict__ g,
+                                    float gamma, long long n, float* __restrict__ d_logit) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float s = sigmoidf_(logit[i]);
+  d_logit[i] = g[i] * gamma * s * (1.f - s);
+}
+
+// ---- RewardEMA (models.py:11-26): sort in shared memory, torch.quantile('linear'), EMA ---------
+constexpr int EMA_MAX = 16384;
+
+__global__ void __launch_bounds__(1024)
+reward_ema_kernel(const float* __restrict__ x, int n, int npow2, float alpha, float one_minus_alpha,
+                  float* __restrict__ ema, float* __restrict__ out) {
+  extern __shared__ float sv[];
+  __shared__ float res[2];
+  for (int i = threadIdx.x; i < npow2; i += blockDim.x) sv[i] = (i < n) ? x[i] : INFINITY;
+  __syncthreads();
+  for (int k = 2; k <= npow2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < npow2; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const float a = sv[i], b = sv[ixj];
+          const bool up = (i & k) == 0;
+          if ((a > b) == up) { sv[i] = b; sv[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x < 2) {
+    // torch.quantile: rank = q * (n-1) in fp32, lerp between the neighbours (ATen's lerp form)
+    const float q = threadIdx.x == 0 ? 0.05f : 0.95f;
+    const float rank = __fmul_rn(q, (float)(n - 1));
+    const float lo = floorf(rank);
+    const float w = __fsub_rn(rank, lo);
+    const int i0 = (int)lo, i1 = (int)ceilf(rank);
+    const float a = sv[i0], b = sv[i1];
+    const float diff = __fsub_rn(b, a);
+    const float qv = (w < 0.5f) ? __fadd_rn(a, __fmul_rn(w, diff))
+                                : __fsub_rn(b, __fmul_rn(diff, __fsub_rn(1.f, w)));
+    const float e = __fadd_rn(__fmul_rn(alpha, qv), __fmul_rn(one_minus_alpha, ema[threadIdx.x]));
+    ema[threadIdx.x] = e;
+    res[threadIdx.x] = e;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    out[0] = res[0];                                  // offset
+    out[1] = fmaxf(__fsub_rn(res[1], res[0]), 1.f);   // scale = clip(hi - lo, min=1)
+  }
+}
+
+// ---- actor loss (models.py:640-681 + 393-397) ---------------------------------------------------
+// mode 0 ('dynamics'): term = -w * ((tgt-off)/scale - (base-off)/scale) - c_ent * ent
+// mode 1 ('reinforce'): term = -w * logp * (tgt - base)            - c_ent * ent
+// loss = mean over the Hm*N terms; normed[t,n] = (tgt-off)/scale is written for the metrics.
+// os = {offset, scale} on the device (NULL: offset 0, scale 1 = reward_EMA off).
+__global__ void __launch_bounds__(1024)
+actor_loss_fwd_kernel(const float* __restrict__ tgt, const float* __restrict__ base,
+                      const float* __restrict__ w, const float* __restrict__ ent,
+                      const float* __restrict__ logp, const float* __restrict__ os, float c_ent,
+                      int mode, int cnt, float* __restrict__ normed, float* __restrict__ loss) {
+  __shared__ float red[4 * 32];
+  const float off = os ? os[0] : 0.f, sc = os ? os[1] : 1.f;
+  float acc[1] = {0.f};
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+    const float nt = (tgt[i] - off) / sc;
+    if (normed) normed[i] = nt;
+    float at;
+    if (mode == 0) at = nt - (base[i] - off) / sc;
+    else at = logp[i] * (tgt[i] - base[i]);
+    acc[0] += -w[i] * at - c_ent * ent[i];
+  }
+  block_sum<1>(acc, red);
+  if (threadIdx.x == 0) loss[0] = acc[0] / (float)cnt;
+}
+
+__global__ void actor_loss_bwd_kernel(const float* __restrict__ g, const float* __restrict__ tgt,
+                                      const float* __restrict__ base, const float* __restrict__ w,
+                                      const float* __restrict__ os, float c_ent, int mode, int cnt,
+                                      int total, float* __restrict__ d_tgt, float* __restrict__ d_ent,
+                                      float* __restrict__ d_logp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;                    // total = H*N >= cnt = (H-1)*N
+  const float gs = g[0] / (float)cnt;
+  const bool in = i < cnt;
+  d_ent[i] = in ? -c_ent * gs : 0.f;
+  if (mode == 0) {
+    const float sc = os ? os[1] : 1.f;
+    if (in) d_tgt[i] = -w[i] * gs / sc;
+  } else {
+    d_logp[i] = in ? -w[i] * (tgt[i] - base[i]) * gs : 0.f;
+  }
+}
+
+// value loss (models.py:419-429): mean_i w_i * (-(lp_target_i) - lp_slow_i)
+__global__ void __launch_bounds__(1024)
+value_loss_fwd_kernel(const float* __restrict__ lp1, const float* __restrict__ lp2,
+                      const float* __restrict__ w, int cnt, float* __restrict__ loss) {
+  __shared__ float red[4 * 32];
+  float acc[1] = {0.f};
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+    float v = -lp1[i];
+    if (lp2) v -= lp2[i];
+    acc[0] += w[i] * v;
+  }
+  block_sum<1>(acc, red);
+  if (threadIdx.x == 0) loss[0] = acc[0] / (float)cnt;
+}
+
+__global__ void value_loss_bwd_kernel(const float* __restrict__ g, const float* __restrict__ w,
+                                      int cnt, float* __restrict__ d_lp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < cnt) d_lp[i] = -w[i] * g[0] / (float)cnt;
+}
+
+// ---- 'normal' actor distribution (networks.py:693-700 + tools.ContDist) -------------------------
+// mean = tanh(mr); std = (max-min) sigmoid(sr + 2) + min
+// ent[r]  = sum_a 0.5 + 0.5 log(2 pi) + log std
+// logp[r] = sum_a -(x-mean)^2 / (2 std^2) - log std - log sqrt(2 pi)
+__global__ void normal_policy_fwd_kernel(const float* __restrict__ mr, const float* __restrict__ sr,
+                                         const float* __restrict__ x, float min_std, float max_std,
+                                         int R, int A, float* __restrict__ ent,
+                                         float* __restrict__ logp) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  float e = 0.f, lp = 0.f;
+  for (int a = 0; a < A; ++a) {
+    const size_t o = (size_t)r * A + a;
+    const float mean = tanhf(mr[o]);
+    const float std = (max_std - min_std) * sigmoidf_(sr[o] + 2.f) + min_std;
+    const float ls = logf(std);
+    e += 0.5f + 0.9189385332046727f + ls;             // 0.5 log(2 pi)
+    const float dx = x[o] - mean;
+    lp += -(dx * dx) / (2.f * std * std) - ls - 0.9189385332046727f;
+  }
+  ent[r] = e;
+  if (logp) logp[r] = lp;
+}
+
+__global__ void normal_policy_bwd_kernel(const float* __restrict__ mr, const float* __restrict__ sr,
+                                         const float* __restrict__ x, const float* __restrict__ g_ent,
+                                         const float* __restrict__ g_logp, float min_std,
+                                         float max_std, int R, int A, float* __restrict__ d_mr,
+                                         float* __restrict__ d_sr, float* __restrict__ d_x) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)R * A) return;
+  const int r = (int)(i / A);
+  const float mean = tanhf(mr[i]);
+  const float sg = sigmoidf_(sr[i] + 2.f);
+  const float std = (max_std - min_std) * sg + min_std;
+  const float ge = g_ent ? g_ent[r] : 0.f, gl = g_logp ? g_logp[r] : 0.f;
+  const float dx = x[i] - mean;
+  const float var = std * std;
+  const float d_mean = gl * dx / var;
+  const float d_std = ge / std + gl * (dx * dx / (var * std) - 1.f / std);
+  d_mr[i] = d_mean * (1.f - mean * mean);
+  d_sr[i] = d_std * (max_std - min_std) * sg * (1.f - sg);
+  if (d_x) d_x[i] = -gl * dx / var;
+}
+
+// ---- tensorstats (tools.py:949-958): mean, std (unbiased), min, max; one block ------------------
+__global__ void __launch_bounds__(1024)
+tensorstats_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
+  __shared__ float red[4 * 32];
+  __shared__ float smin[32], smax[32];
+  float acc[1] = {0.f};
+  float mn = INFINITY, mx = -INFINITY;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = x[i];
+    acc[0] += v;
+    mn = fminf(mn, v);
+    mx = fmaxf(mx, v);
+  }
+  block_sum<1>(acc, red);
+  const float mean = acc[0] / (float)n;
+  float q[1] = {0.f};
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const float d = x[i] - mean;
+    q[0] = fmaf(d, d, q[0]);
+  }
+  block_sum<1>(q, red);
+  mn = -warp_max(-mn);
+  mx = warp_max(mx);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) { smin[wid] = mn; smax[wid] = mx; }
+  __syncthreads();
+  if (wid == 0) {
+    const int nw = blockDim.x >> 5;
+    mn = lane < nw ? smin[lane] : INFINITY;
+    mx = lane < nw ? smax[lane] : -INFINITY;
+    mn = -warp_max(-mn);
+    mx = warp_max(mx);
+    if (lane == 0) {
+      out[0] = mean;
+      out[1] = sqrtf(q[0] / (float)(n > 1 ? n - 1 : 1));
+      out[2] = mn;
+      out[3] = mx;
+    }
+  }
+}
+
+// param = (1 - mix) * param + mix * src  over a flat buffer (slow critic, models.py:683-689)
+__global__ void ema_mix_kernel(float* __restrict__ dst, const float* __restrict__ src, long long n,
+                               float mix, float one_minus_mix) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = __fadd_rn(__fmul_rn(mix, src[i]), __fmul_rn(one_minus_mix, dst[i]));
+}
+
+static inline int nblk(long long n, int t) { return (int)((n + t - 1) / t); }
+
+}  // namespace dv3
+
+using namespace dv3;
+#define ST static_cast<cudaStream_t>(stream)
+
+extern "C" int dv3_symlog(const float* x, long long n, float* out, void* stream) {
+  if (n <= 0) return 0;
+  DV3_REQUIRE(x && out, DV3_ERR_NULL, "symlog: null pointer");
+  symlog_kernel<<<nblk(n, 256), 256, 0, ST>>>(x, n, out);
+  DV3_CHECK_LAUNCH("symlog_kernel");
+  return 0;
+}
+
+extern "C" int dv3_sqerr_logprob_fwd(const float* mode, const float* value, int32_t R, int32_t n,
+                                     int32_t use_symlog, float tol, float* logprob, void* stream) {
+  if (R <= 0) return 0;
+  DV3_REQUIRE(mode && value && logprob && n > 0, DV3_ERR_NULL, "sqerr_logprob_fwd: null / n=%d", n);
+  sqerr_logprob_fwd_kernel<<<nblk(R, TL_THREADS / 32), TL_THREADS, 0, ST>>>(mode, value, R, n,
+                                                                             use_symlog, tol, logprob);
+  DV3_CHECK_LAUNCH("sqerr_logprob_fwd_kernel");
+  return 0;
+}
+
+extern "C" int dv3_sqerr_logprob_bwd(const float* mode, const float* value, const float* g_logprob,
+                                     int32_t R, int32_t n, int32_t use_symlog, float tol,
+                                     float* d_mode, void* stream) {
+  if (R <= 0) return 0;
+  DV3_REQUIRE(mode && value && g_logprob && d_mode && n > 0, DV3_ERR_NULL, "sqerr_logprob_bwd: null");
+  sqerr_logprob_bwd_kernel<<<nblk(R, TL_THREADS / 32), TL_THREADS, 0, ST>>>(
+      mode, value, g_logprob, R, n, use_symlog, tol, d_mode);
+  DV3_CHECK_LAUNCH("sqerr_logprob_bwd_kernel");
+  return 0;
+}
+
+extern "C" int dv3_bernoulli_logprob_fwd(const float* logit, const float* x, long long n,
+                                         float* logprob, void* stream) {
+  if (n <= 0) return 0;
+  DV3_REQUIRE(logit && x && logprob, DV3_ERR_NULL, "bernoulli_logprob_fwd: null pointer");
+  bernoulli_logprob_fwd_kernel<<<nblk(n, 256), 256, 0, ST>>>(logit, x, n, logprob);
+  DV3_CHECK_LAUNCH("bernoulli_logprob_fwd_kernel");
+  return 0;
+}
+
+extern "C" int dv3_bernoulli_logprob_bwd(const float* logit, const float* x, const float* g,
+                                         long long n, float* d_logit, void* stream) {
+  if (n <= 0) return 0;
+  DV3_REQUIRE(logit && x && g && d_logit, DV3_ERR_NULL, "bernoulli_logprob_bwd: null pointer");
+  bernoulli_logprob_bwd_kernel<<<nblk(n, 256), 256, 0, ST>>>(logit, x, g, n, d_logit);
+  DV3_CHECK_LAUNCH("bernoulli_logprob_bwd_kernel");
+  return 0;
+}
+
+extern "C" int dv3_loss_mean_fwd(const float* const* losses, const float* scales, int32_t n_losses,
+                                 int32_t R, float* out, float* neg_out, void* stream) {
+  DV3_REQUIRE(losses && scales && out && n_losses >= 1 && n_losses <= 8 && R > 0, DV3_ERR_BAD_SHAPE,
+              "loss_mean_fwd: n_losses=%d R=%d", n_losses, R);
+  LossPtrs lp{};
+  lp.n = n_losses;
+  for (int i = 0; i < n_losses; ++i) {
+    DV3_REQUIRE(losses[i], DV3_ERR_NULL, "loss_mean_fwd: loss %d is NULL", i);
+    lp.p[i] = losses[i];
+    lp.scale[i] = scales[i];
+  }
+  loss_mean_kernel<<<1, 1024, 0, ST>>>(lp, R, out, neg_out);
+  DV3_CHECK_LAUNCH("loss_mean_kernel");
+  return 0;
+}
+
+extern "C" int dv3_loss_mean_bwd(const float* g, const float* scales, int32_t n_losses, int32_t R,
+                                 float* grads, void* stream) {
+  DV3_REQUIRE(g && scales && grads && n_losses >= 1 && n_losses <= 8 && R > 0, DV3_ERR_BAD_SHAPE,
+              "loss_mean_bwd: n_losses=%d R=%d", n_losses, R);
+  LossPtrs lp{};
+  lp.n = n_losses;
+  for (int i = 0; i < n_losses; ++i) lp.scale[i] = scales[i];
+  loss_mean_bwd_kernel<<<dim3(nblk(R, 256), n_losses), 256, 0, ST>>>(g, lp, R, grads);
+  DV3_CHECK_LAUNCH("loss_mean_bwd_kernel");
+  return 0;
+}
+
+extern "C" int dv3_discount_weights_fwd(const float* cont_logit, float gamma, int32_t H, int32_t N,
+                                        float* discount, float* weights, void* stream) {
+  if (H <= 0 || N <= 0) return 0;
+  DV3_REQUIRE(cont_logit && discount && weights, DV3_ERR_NULL, "discount_weights_fwd: null pointer");
+  discount_weights_kernel<<<nblk(N, 128), 128, 0, ST>>>(cont_logit, gamma, H, N, discount, weights);
+  DV3_CHECK_LAUNCH("discount_weights_kernel");
+  return 0;
+}
+
+extern "C" int dv3_discount_bwd(const float* cont_logit, const float* g_discount, float gamma,
+                                long long n, float* d_logit, void* stream) {
+  if (n <= 0) return 0;
+  DV3_REQUIRE(cont_logit && g_discount && d_logit, DV3_ERR_NULL, "discount_bwd: null pointer");
+  discount_bwd_kernel<<<nblk(n, 256), 256, 0, ST>>>(cont_logit, g_discount, gamma, n, d_logit);
+  DV3_CHECK_LAUNCH("discount_bwd_kernel");
+  return 0;
+}
+
+extern "C" int dv3_reward_ema(const float* x, int32_t n, double alpha, float* ema_vals,
+                              float* offset_scale, void* stream) {
+  DV3_REQUIRE(x && ema_vals && offset_scale, DV3_ERR_NULL, "reward_ema: null pointer");
+  DV3_REQUIRE(n >= 1 && n <= EMA_MAX, DV3_ERR_BAD_SHAPE,
+              "reward_ema: n=%d outside [1, %d] (single-CTA sort)", n, EMA_MAX);
+  int np2 = 2;
+  while (np2 < n) np2 <<= 1;
+  static bool attr = false;
+  if (!attr) {
+    DV3_CHECK_CUDA(cudaFuncSetAttribute(reward_ema_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        EMA_MAX * 4));
+    attr = true;
+  }
+  // alpha * q and (1 - alpha) * ema with the python scalars rounded to fp32 once, like torch
+  reward_ema_kernel<<<1, 1024, (size_t)np2 * 4, ST>>>(x, n, np2, (float)alpha, (float)(1.0 - alpha),
+                                                     ema_vals, offset_scale);
+  DV3_CHECK_LAUNCH("reward_ema_kernel");
+  return 0;
+}
+
+extern "C" int dv3_actor_loss_fwd(const float* target, const float* base, const float* weights,
+                                  const float* entropy, const float* logp, const float* offset_scale,
+                                  float entropy_coef, int32_t mode, int32_t count, float* normed,
+                                  float* loss, void* stream) {
+  DV3_REQUIRE(target && base && weights && entropy && loss && count > 0 && (mode == 0 || mode == 1),
+              DV3_ERR_NULL, "actor_loss_fwd: null pointer / count=%d mode=%d", count, mode);
+  DV3_REQUIRE(mode == 0 || logp, DV3_ERR_NULL, "actor_loss_fwd: reinforce needs logp");
+  actor_loss_fwd_kernel<<<1, 1024, 0, ST>>>(target, base, weights, entropy, logp, offset_scale,
+                                             entropy_coef, mode, count, normed, loss);
+  DV3_CHECK_LAUNCH("actor_loss_fwd_kernel");
+  return 0;
+}
+
+extern "C" int dv3_actor_loss_bwd(const float* g_loss, const float* target, const float* base,
+                                  const float* weights, const float* offset_scale, float entropy_coef,
+                                  int32_t mode, int32_t count, int32_t total, float* d_target,
+                                  float* d_entropy, float* d_logp, void* stream) {
+  DV3_REQUIRE(g_loss && target && base && weights && d_entropy && count > 0 && total >= count,
+              DV3_ERR_NULL, "actor_loss_bwd: null pointer / count=%d total=%d", count, total);
+  DV3_REQUIRE(mode == 0 ? d_target != nullptr : d_logp != nullptr, DV3_ERR_NULL,
+              "actor_loss_bwd: missing output for mode %d", mode);
+  actor_loss_bwd_kernel<<<nblk(total, 256), 256, 0, ST>>>(g_loss, target, base, weights, offset_scale,
+                                                          entropy_coef, mode, count, total, d_target,
+                                                          d_entropy, d_logp);
+  DV3_CHECK_LAUNCH("actor_loss_bwd_kernel");
+  return 0;
+}
+
+extern "C" int dv3_value_loss_fwd(const float* lp_target, const float* lp_slow, const float* weights,
+                                  int32_t count, float* loss, void* stream) {
+  DV3_REQUIRE(lp_target && weights && loss && count > 0, DV3_ERR_NULL, "value_loss_fwd: null pointer");
+  value_loss_fwd_kernel<<<1, 1024, 0, ST>>>(lp_target, lp_slow, weights, count, loss);
+  DV3_CHECK_LAUNCH("value_loss_fwd_kernel");
+  return 0;
+}
+
+extern "C" int dv3_value_loss_bwd(const float* g_loss, const float* weights, int32_t count,
+                                  float* d_lp, void* stream) {
+  DV3_REQUIRE(g_loss && weights && d_lp && count > 0, DV3_ERR_NULL, "value_loss_bwd: null pointer");
+  value_loss_bwd_kernel<<<nblk(count, 256), 256, 0, ST>>>(g_loss, weights, count, d_lp);
+  DV3_CHECK_LAUNCH("value_loss_bwd_kernel");
+  return 0;
+}
+
+extern "C" int dv3_normal_policy_fwd(const float* mean_raw, const float* std_raw, const float* action,
+                                     float min_std, float max_std, int32_t R, int32_t A,
+                                     float* entropy, float* logp, void* stream) {
+  if (R <= 0) return 0;
+  DV3_REQUIRE(mean_raw && std_raw && action && entropy && A > 0, DV3_ERR_NULL,
+              "normal_policy_fwd: null pointer");
+  normal_policy_fwd_kernel<<<nblk(R, 128), 128, 0, ST>>>(mean_raw, std_raw, action, min_std, max_std,
+                                                         R, A, entropy, logp);
+  DV3_CHECK_LAUNCH("normal_policy_fwd_kernel");
+  return 0;
+}
+
+extern "C" int dv3_normal_policy_bwd(const float* mean_raw, const float* std_raw, const float* action,
+                                     const float* g_entropy, const float* g_logp, float min_std,
+                                     float max_std, int32_t R, int32_t A, float* d_mean_raw,
+                                     float* d_std_raw, float* d_action, void* stream) {
+  if (R <= 0) return 0;
+  DV3_REQUIRE(mean_raw && std_raw && action && d_mean_raw && d_std_raw && A > 0, DV3_ERR_NULL,
+              "normal_policy_bwd: null pointer");
+  normal_policy_bwd_kernel<<<nblk((long long)R * A, 256), 256, 0, ST>>>(
+      mean_raw, std_raw, action, g_entropy, g_logp, min_std, max_std, R, A, d_mean_raw, d_std_raw,
+      d_action);
+  DV3_CHECK_LAUNCH("normal_policy_bwd_kernel");
+  return 0;
+}
+
+extern "C" int dv3_tensorstats(const float* x, long long n, float* out4, void* stream) {
+  DV3_REQUIRE(x && out4 && n > 0, DV3_ERR_NULL, "tensorstats: null pointer / n=%lld", n);
+  tensorstats_kernel<<<1, 1024, 0, ST>>>(x, n, out4);
+  DV3_CHECK_LAUNCH("tensorstats_kernel");
+  return 0;
+}
+
+extern "C" int dv3_ema_mix(float* dst, const float* src, long long n, double mix, void* stream) {
+  if (n <= 0) return 0;
+  DV3_REQUIRE(dst && src, DV3_ERR_NULL, "ema_mix: null pointer");
+  ema_mix_kernel<<<nblk(n, 256), 256, 0, ST>>>(dst, src, n, (float)mix, (float)(1.0 - mix));
+  DV3_CHECK_LAUNCH("ema_mix_kernel");
+  return 0;
+}

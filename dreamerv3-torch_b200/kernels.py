@@ -270,6 +270,64 @@ def split(x):
     return Split(hi, lo, rows, cols)
 
 
+# --------------------------------------------------------------------------------------
+# gradient sink: while tools.Optimizer runs a backward pass, the parameter gradients computed by
+# the Functions below (dW = delta^T x split-K products, LayerNorm affine sums, bias column sums)
+# are ACCUMULATED STRAIGHT INTO views of the optimizer's flat, pre-zeroed gradient buffer instead
+# of being returned to autograd -- no per-product memset, no gather of ~100 gradient tensors
+# afterwards (reference tools.py:760-776 has clip_grad_norm_ / Adam walk the per-parameter grads).
+# --------------------------------------------------------------------------------------
+_SINK = {}          # id(parameter) -> view of the flat gradient buffer (armed optimizers only)
+_SINK_DIRTY = set() # ids whose view has been written in this backward pass
+
+
+def arm_grad_sink(params, views):
+    for p, v in zip(params, views):
+        _SINK[id(p)] = v
+
+
+def disarm_grad_sink(params):
+    written = []
+    for p in params:
+        written.append(id(p) in _SINK_DIRTY)
+        _SINK.pop(id(p), None)
+        _SINK_DIRTY.discard(id(p))
+    return written
+
+
+_SUNK = object()     # marker: this gradient went into the sink (autograd gets None)
+
+
+def _sink_of(pid):
+    return _SINK.get(pid) if pid is not None else None
+
+
+def _sink_gemm(pid, d, inp, cols=None):
+    """dW = d^T inp accumulated into the sink view of parameter ``pid`` (optionally into a column
+    block of it); returns None when there is no armed sink (caller computes a fresh tensor)."""
+    view = _sink_of(pid)
+    if view is None:
+        return None
+    out = view if cols is None else view[:, cols[0]:cols[1]]
+    gemm_tc(d, inp, a_t=True, b_t=True, out=out, accumulate=True, split_k=True)
+    _SINK_DIRTY.add(pid)
+    return view
+
+
+def _sink_add(pid, fn_out, fresh):
+    """Vector gradients (bias / LayerNorm sums).  ``fn_out(out)`` writes the gradient into ``out``
+    (overwriting); ``fresh()`` returns it as a new tensor.  -> None if sunk, else the tensor."""
+    view = _sink_of(pid)
+    if view is None:
+        return fresh()
+    if pid in _SINK_DIRTY:
+        view.add_(fresh().reshape(view.shape))
+    else:
+        fn_out(view)
+        _SINK_DIRTY.add(pid)
+    return None
+
+
 _WEIGHT_EPOCH = [0]
 
 
@@ -293,6 +351,11 @@ def split_param(w):
     sp = split(w.detach())
     w._dv3_split = (tag, sp)
     return sp
+
+
+def split_param_like(w):
+    """Split of a detached weight tensor (saved for backward): no parameter object to cache on."""
+    return split(w)
 
 
 def gemm_tc(A, B, a_t=False, b_t=False, A2=None, bias=None, addend=None, out=None,
@@ -409,21 +472,23 @@ class _DenseLnSilu(torch.autograd.Function):
         _LAST_OUT_SPLIT[0] = osp
         ctx.save_for_backward(g.detach(), b.detach(), pre, xs.hi, xs.lo, Ws.hi, Ws.lo)
         ctx.shapes = (xs.rows, xs.cols, Ws.rows, Ws.cols)
+        ctx.pids = (id(W), id(g), id(b))
         return out
 
     @staticmethod
     def backward(ctx, d_out):
         g, b, pre, xh, xl, Wh, Wl = ctx.saved_tensors
         M, Kd, U, _ = ctx.shapes
+        wid, gid, bid = ctx.pids
         xs, Ws = Split(xh, xl, M, Kd), Split(Wh, Wl, U, Kd)
         d_pre, d_ln, ds = ln_silu_bwd(pre, _c(g), _c(b), _f32(d_out), with_split=True)
         dx = dW = dg = db = None
         if ctx.needs_input_grad[0]:
             dx = gemm_tc(ds, Ws, b_t=True)                    # dy W
-        if ctx.needs_input_grad[1]:
+        if ctx.needs_input_grad[1] and _sink_gemm(wid, ds, xs) is None:
             dW = gemm_tc(ds, xs, a_t=True, b_t=True, split_k=True)   # dy^T x
         if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
-            dg, db = _ln_grads(pre, d_ln)
+            dg, db = _ln_grads(pre, d_ln, gid, bid)
         return dx, dW, dg, db, None
 
 
@@ -435,22 +500,24 @@ class _LinearBias(torch.autograd.Function):
         Ws = split_param(W)
         ctx.save_for_backward(xs.hi, xs.lo, Ws.hi, Ws.lo)
         ctx.shapes = (xs.rows, xs.cols, Ws.rows, Ws.cols)
+        ctx.pids = (id(W), id(bias) if bias is not None else None)
         return gemm_tc(xs, Ws, bias=None if bias is None else _c(bias.detach()))
 
     @staticmethod
     def backward(ctx, d_out):
         xh, xl, Wh, Wl = ctx.saved_tensors
         M, Kd, N, _ = ctx.shapes
+        wid, bid = ctx.pids
         xs, Ws = Split(xh, xl, M, Kd), Split(Wh, Wl, N, Kd)
         d_out = _f32(d_out)
         ds = split(d_out)
         dx = dW = db = None
         if ctx.needs_input_grad[0]:
             dx = gemm_tc(ds, Ws, b_t=True)
-        if ctx.needs_input_grad[1]:
+        if ctx.needs_input_grad[1] and _sink_gemm(wid, ds, xs) is None:
             dW = gemm_tc(ds, xs, a_t=True, b_t=True, split_k=True)
         if ctx.needs_input_grad[2]:
-            db = d_out.sum(0)
+            db = _bias_grad(d_out, bid)
         return dx, dW, db, None
 
 
@@ -496,17 +563,41 @@ def _xhat(pre):
     return F.layer_norm(pre, (pre.shape[-1],), None, None, LN_EPS)
 
 
-def _ln_grads(pre2d, d_ln2d):
-    """LayerNorm weight / bias gradients from the saved pre-LN rows and d(LN output)."""
+def _ln_grads_into(pre2d, d_ln2d, dg, db, accumulate=False):
     M, n = pre2d.shape
-    if n > 2048 or pre2d.stride(1) != 1 or d_ln2d.stride(1) != 1:
-        return (d_ln2d * _xhat(pre2d)).sum(0), d_ln2d.sum(0)
-    dg = torch.empty(n, dtype=torch.float32, device=pre2d.device)
-    db = torch.empty(n, dtype=torch.float32, device=pre2d.device)
-    L.check(L.lib().dv3_ln_param_grads(_raw(pre2d), pre2d.stride(0), _raw(d_ln2d), d_ln2d.stride(0),
-                                       LN_EPS, M, n, L.fptr(dg), L.fptr(db), L.stream_ptr()),
-            "ln_param_grads")
+    fn = L.lib().dv3_ln_param_grads_acc if accumulate else L.lib().dv3_ln_param_grads
+    L.check(fn(_raw(pre2d), pre2d.stride(0), _raw(d_ln2d), d_ln2d.stride(0), LN_EPS, M, n,
+               L.fptr(dg), L.fptr(db), L.stream_ptr()), "ln_param_grads")
+
+
+def _ln_grads(pre2d, d_ln2d, gid=None, bid=None):
+    """LayerNorm weight / bias gradients from the saved pre-LN rows and d(LN output).  With armed
+    sinks for both parameters (ids ``gid`` / ``bid``) the kernel writes into the flat gradient
+    buffer and (None, None) is returned."""
+    M, n = pre2d.shape
+    kernel_ok = n <= 2048 and pre2d.stride(1) == 1 and d_ln2d.stride(1) == 1
+    vg, vb = _sink_of(gid), _sink_of(bid)
+    if vg is not None and vb is not None and kernel_ok:
+        _ln_grads_into(pre2d, d_ln2d, vg, vb, accumulate=True)   # the sink is pre-zeroed
+        _SINK_DIRTY.update((gid, bid))
+        return None, None
+    if not kernel_ok:
+        dg, db = (d_ln2d * _xhat(pre2d)).sum(0), d_ln2d.sum(0)
+    else:
+        dg = torch.empty(n, dtype=torch.float32, device=pre2d.device)
+        db = torch.empty(n, dtype=torch.float32, device=pre2d.device)
+        _ln_grads_into(pre2d, d_ln2d, dg, db)
+    if vg is not None and vb is not None:
+        vg.add_(dg)
+        vb.add_(db)
+        _SINK_DIRTY.update((gid, bid))
+        return None, None
     return dg, db
+
+
+def _bias_grad(d2d, pid=None):
+    """Column sums of a delta [M,n] = the gradient of a Linear bias."""
+    return _sink_add(pid, lambda out: torch.sum(d2d, 0, out=out), lambda: d2d.sum(0))
 
 
 # --------------------------------------------------------------------------------------
@@ -565,6 +656,7 @@ class _Observe(torch.autograd.Function):
                 "observe_fwd")
         ctx.dims = dims
         ctx.BT = (B, T)
+        ctx.pids = [id(q) for q in params]
         ctx.has_state = state_idx is not None
         ctx.save_for_backward(embed, o["first_eff"], o["post_logit"], o["prior_logit"],
                               o["hprev"], o["x_pre"], o["g_pre"], o["y_pre"], o["z_pre"],
@@ -601,6 +693,7 @@ class _Observe(torch.autograd.Function):
         L.check(L.lib().dv3_observe_bwd(C.byref(d), C.byref(pst), C.byref(io), L.stream_ptr()),
                 "observe_bwd")
         P = dict(zip(L.RSSM_PARAM_FIELDS, params))
+        pid = dict(zip(L.RSSM_PARAM_FIELDS, ctx.pids))
         need = dict(zip(L.RSSM_PARAM_FIELDS, ctx.needs_input_grad[8:]))
         G = {k: None for k in L.RSSM_PARAM_FIELDS}
         if any(need.values()):
@@ -612,28 +705,44 @@ class _Observe(torch.autograd.Function):
             dpo, dpr = r2(o["d_post_logit"]), r2(o["d_prior_logit"])
             dpos, dprs = split(dpo), split(dpr)
             deters = split(r2(deter))
+
             # dW = delta^T @ input over all B*T rows: transposed-operand tcgen05 products with the
-            # rows (K = B*T) partitioned over the SMs; column blocks of one weight are written
-            # through strided output views
-            dw = lambda d, inp, out=None: gemm_tc(d, inp, a_t=True, b_t=True, out=out, split_k=True)
-            G["w_in"] = torch.empty(Hd, SC + A, dtype=torch.float32, device=dev)
-            dw(dx, hot, G["w_in"][:, :SC])
-            dw(dx, r2(aprev), G["w_in"][:, SC:])
-            G["ln_in_g"], G["ln_in_b"] = _ln_grads(r2(x_pre), r2(o["d_x_ln"]))
-            G["w_gru"] = torch.empty(3 * D, Hd + D, dtype=torch.float32, device=dev)
-            dw(dg, r2(x), G["w_gru"][:, :Hd])
-            dw(dg, r2(hprev), G["w_gru"][:, Hd:])
-            G["ln_gru_g"], G["ln_gru_b"] = _ln_grads(r2(g_pre), r2(o["d_g_ln"]))
-            G["w_out"] = dw(dy, deters)
-            G["ln_out_g"], G["ln_out_b"] = _ln_grads(r2(y_pre), r2(o["d_y_ln"]))
-            G["w_ims"] = dw(dprs, r2(y))
-            G["b_ims"] = dpr.sum(0)
-            G["w_obs"] = torch.empty(Hd, D + E, dtype=torch.float32, device=dev)
-            dw(dz, deters, G["w_obs"][:, :D])
-            dw(dz, r2(embed), G["w_obs"][:, D:])
-            G["ln_obs_g"], G["ln_obs_b"] = _ln_grads(r2(z_pre), r2(o["d_z_ln"]))
-            G["w_os"] = dw(dpos, r2(z))
-            G["b_os"] = dpo.sum(0)
+            # rows (K = B*T) partitioned over the SMs, accumulated into the optimizer's flat
+            # gradient buffer when it is armed (else into fresh tensors); column blocks of one
+            # weight are written through strided output views
+            def dw(name, d, inp, cols=None):
+                if _sink_gemm(pid[name], d, inp, cols) is not None:
+                    G[name] = _SUNK
+                elif cols is None:
+                    G[name] = gemm_tc(d, inp, a_t=True, b_t=True, split_k=True)
+                else:
+                    if G[name] is None:
+                        G[name] = torch.empty(P[name].shape, dtype=torch.float32, device=dev)
+                    gemm_tc(d, inp, a_t=True, b_t=True, out=G[name][:, cols[0]:cols[1]], split_k=True)
+
+            def ln(gname, bname, pre, dln):
+                a, b_ = _ln_grads(r2(pre), r2(dln), pid[gname], pid[bname])
+                G[gname], G[bname] = (_SUNK, _SUNK) if a is None else (a, b_)
+
+            def bias(name, d2d):
+                r = _bias_grad(d2d, pid[name])
+                G[name] = _SUNK if r is None else r
+
+            dw("w_in", dx, hot, (0, SC))
+            dw("w_in", dx, r2(aprev), (SC, SC + A))
+            ln("ln_in_g", "ln_in_b", x_pre, o["d_x_ln"])
+            dw("w_gru", dg, r2(x), (0, Hd))
+            dw("w_gru", dg, r2(hprev), (Hd, Hd + D))
+            ln("ln_gru_g", "ln_gru_b", g_pre, o["d_g_ln"])
+            dw("w_out", dy, deters)
+            ln("ln_out_g", "ln_out_b", y_pre, o["d_y_ln"])
+            dw("w_ims", dprs, r2(y))
+            bias("b_ims", dpr)
+            dw("w_obs", dz, deters, (0, D))
+            dw("w_obs", dz, r2(embed), (D, D + E))
+            ln("ln_obs_g", "ln_obs_b", z_pre, o["d_z_ln"])
+            dw("w_os", dpos, r2(z))
+            bias("b_os", dpo)
             # RSSM.initial (networks.py:99-125): tanh(W) -> prior head -> mode (straight-through
             # on the normalised log-probs).  One row; differentiated with autograd.
             names = ["w_init", "w_out", "ln_out_g", "ln_out_b", "w_ims", "b_ims"]
@@ -650,8 +759,14 @@ class _Observe(torch.autograd.Function):
                                          [leaf[k] for k in names],
                                          [o["d_init_stoch"], o["d_init_deter"]])
             for k, g in zip(names, gi):
-                G[k] = g if G[k] is None else G[k] + g
-        grads = [G[k] if need[k] else None for k in L.RSSM_PARAM_FIELDS]
+                view = _sink_of(pid[k])
+                if view is not None:
+                    view.add_(g.reshape(view.shape))
+                    _SINK_DIRTY.add(pid[k])
+                    G[k] = _SUNK
+                else:
+                    G[k] = g if G[k] is None else G[k] + g
+        grads = [G[k] if need[k] and G[k] is not _SUNK else None for k in L.RSSM_PARAM_FIELDS]
         d_embed = o["d_embed"] if ctx.needs_input_grad[0] else None
         return (d_embed, None, None, None, None, None, d_state_deter, None, *grads)
 
@@ -735,11 +850,18 @@ class _Imagine(torch.autograd.Function):
                                         L.stream_ptr()), "imagine_fwd")
         ctx.dims, ctx.spec, ctx.NH = dims, spec, (N, H)
         ctx.n_actor = len(actor_params)
+        ctx.pids_actor = [id(q) for q in actor_params]
         saved = [o["logit"], o["feat"], o["x_pre"], o["g_pre"], o["y_pre"], act_noise]
         if spec is not None:
             saved += [o["a_pre"], o["a_act"], o["a_mean_raw"]]
             if spec.dist == "normal":
                 saved.append(o["a_std_raw"])
+        # tf32 planes of the feature buffer: the A operand of every head that reads the rollout
+        # (reward, cont, critic, slow critic) and of the actor's first-layer dW in backward
+        fsp = split(o["feat"].reshape(H * N, Fw)) if (spec is not None and H * N >= 64) else None
+        ctx.has_fsp = fsp is not None
+        if fsp is not None:
+            saved += [fsp.hi, fsp.lo]
         ctx.n_saved = len(saved)
         ctx.save_for_backward(*saved, *[p.detach() for p in params])
         ctx.mark_non_differentiable(o["idx"])
@@ -749,10 +871,12 @@ class _Imagine(torch.autograd.Function):
         empty = o["action"].new_zeros(0)
         mean_raw = o["a_mean_raw"] if spec is not None else empty
         std_raw = o["a_std_raw"] if spec is not None and spec.dist == "normal" else empty
-        return o["feat"], o["logit"], o["action"], o["idx"], mean_raw, std_raw
+        fh, fl = (fsp.hi, fsp.lo) if fsp is not None else (empty, empty)
+        ctx.mark_non_differentiable(fh, fl)
+        return o["feat"], o["logit"], o["action"], o["idx"], mean_raw, std_raw, fh, fl
 
     @staticmethod
-    def backward(ctx, g_feat, g_logit, g_action, _g_idx, g_mean_raw=None, g_std_raw=None):
+    def backward(ctx, g_feat, g_logit, g_action, _g_idx, g_mean_raw=None, g_std_raw=None, *_):
         S, Cc, D, Hd, A, E, unimix = ctx.dims
         spec = ctx.spec
         N, H = ctx.NH
@@ -767,6 +891,9 @@ class _Imagine(torch.autograd.Function):
                              "video prediction (models.py:196-204)")
         a_pre, a_act, a_mean_raw = saved[6:9]
         a_std_raw = saved[9] if spec.dist == "normal" else None
+        feat_sp = None
+        if ctx.has_fsp:
+            feat_sp = Split(saved[ctx.n_saved - 2], saved[ctx.n_saved - 1], H * N, SC + D)
         dev = feat.device
         d = make_dims(S, Cc, D, Hd, A, E, unimix)
         pst, keep_r = pack_rssm(rssm_params)
@@ -803,23 +930,36 @@ class _Imagine(torch.autograd.Function):
             dm = dm + _f32(g_mean_raw).reshape(HN, A)
         top = a_act[Lr - 1].reshape(HN, U)
         ga = [None] * len(actor_params)
-        dw = lambda d, inp: gemm_tc(d, inp, a_t=True, b_t=True, split_k=True)
+        pids = ctx.pids_actor
+
+        def dw(i, d, inp):
+            if _sink_gemm(pids[i], d, inp) is None:
+                ga[i] = gemm_tc(d, inp, a_t=True, b_t=True, split_k=True)
+
         tops = split(top)
-        ga[3 * Lr], ga[3 * Lr + 1] = dw(dm, tops), dm.sum(0)
-        d_act = dm @ actor_params[3 * Lr]
+        dms = split(dm)
+        dw(3 * Lr, dms, tops)
+        ga[3 * Lr + 1] = _bias_grad(dm, pids[3 * Lr + 1])
+        d_act = gemm_tc(dms, split_param_like(actor_params[3 * Lr]), b_t=True)      # dm W_mean
         if spec.dist == "normal":
             ds = o["d_std_raw"].reshape(HN, A)
             if g_std_raw is not None and g_std_raw.numel():
                 ds = ds + _f32(g_std_raw).reshape(HN, A)
-            ga[3 * Lr + 2], ga[3 * Lr + 3] = dw(ds, tops), ds.sum(0)
-            d_act = d_act + ds @ actor_params[3 * Lr + 2]
+            dss = split(ds)
+            dw(3 * Lr + 2, dss, tops)
+            ga[3 * Lr + 3] = _bias_grad(ds, pids[3 * Lr + 3])
+            gemm_tc(dss, split_param_like(actor_params[3 * Lr + 2]), b_t=True, out=d_act,
+                    accumulate=True)                                                # + ds W_std
         for i in range(Lr - 1, -1, -1):
             pre = a_pre[i].reshape(HN, U)
             d_pre, d_ln, dps = ln_silu_bwd(pre, actor_params[3 * i + 1], actor_params[3 * i + 2],
                                            _c(d_act), with_split=True)
-            inp = feat.reshape(HN, -1) if i == 0 else a_act[i - 1].reshape(HN, U)
-            ga[3 * i] = dw(dps, inp)
-            ga[3 * i + 1], ga[3 * i + 2] = _ln_grads(pre, d_ln)
+            if i == 0:
+                inp = feat_sp if feat_sp is not None else feat.reshape(HN, -1)
+            else:
+                inp = a_act[i - 1].reshape(HN, U)
+            dw(3 * i, dps, inp)
+            ga[3 * i + 1], ga[3 * i + 2] = _ln_grads(pre, d_ln, pids[3 * i + 1], pids[3 * i + 2])
             if i > 0:
                 d_act = gemm_tc(dps, split(actor_params[3 * i]), b_t=True)
         need = ctx.needs_input_grad[9 + 17:]
@@ -830,9 +970,15 @@ class _Imagine(torch.autograd.Function):
 def imagine_full(start_idx, start_deter, act_noise, u_state, given_action, H, dims, spec,
                  rssm_params, actor_params, start_logit=None):
     """-> feat, logit, action, idx, actor mean_raw [H,N,A], actor std_raw [H,N,A] (empty for a
-    one-hot actor / no actor); the last two are differentiable w.r.t. the actor parameters."""
-    return _Imagine.apply(start_idx, start_deter, act_noise, u_state, given_action, start_logit, H,
-                          dims, spec, *rssm_params, *actor_params)
+    one-hot actor / no actor; both differentiable w.r.t. the actor parameters), Split of feat
+    viewed [H*N, F] (None for fewer than 64 rows / no actor)."""
+    out = _Imagine.apply(start_idx, start_deter, act_noise, u_state, given_action, start_logit, H,
+                         dims, spec, *rssm_params, *actor_params)
+    feat = out[0]
+    sp = None
+    if out[6].numel():
+        sp = Split(out[6], out[7], feat.shape[0] * feat.shape[1], feat.shape[2])
+    return out[:6] + (sp,)
 
 
 def imagine(start_idx, start_deter, act_noise, u_state, given_action, H, dims, spec, rssm_params,
@@ -840,3 +986,290 @@ def imagine(start_idx, start_deter, act_noise, u_state, given_action, H, dims, s
     """-> feat [H,N,F], logit [H,N,S,C], action [H,N,A], idx int32 [H,N,S]."""
     return imagine_full(start_idx, start_deter, act_noise, u_state, given_action, H, dims, spec,
                         rssm_params, actor_params, start_logit)[:4]
+
+
+# --------------------------------------------------------------------------------------
+# step tail (dv3_tail.cu): fused element-wise / reduction chains around the rollouts
+# --------------------------------------------------------------------------------------
+def symlog(x):
+    """tools.symlog (reference tools.py:22-23) as one kernel; no gradient (observation inputs)."""
+    x = _f32(x)
+    out = torch.empty_like(x)
+    L.check(L.lib().dv3_symlog(L.fptr(x), x.numel(), L.fptr(out), L.stream_ptr()), "symlog")
+    return out
+
+
+class _SqerrLogprob(torch.autograd.Function):
+    """log_prob of the squared-error heads: tools.SymlogDist (reference tools.py:546-572) when
+    ``use_symlog`` else tools.MSEDist (520-543).  mode / value [..., *event]; the event axes
+    (everything after the first two) are summed."""
+
+    @staticmethod
+    def forward(ctx, mode, value, use_symlog, tol):
+        lead = tuple(mode.shape[:2])
+        R = lead[0] * lead[1]
+        m2, v2 = _f32(mode).reshape(R, -1), _f32(value).reshape(R, -1)
+        n = m2.shape[1]
+        out = _empty(R, like=m2)
+        L.check(L.lib().dv3_sqerr_logprob_fwd(L.fptr(m2), L.fptr(v2), R, n, int(use_symlog), tol,
+                                              L.fptr(out), L.stream_ptr()), "sqerr_logprob_fwd")
+        ctx.save_for_backward(m2, v2)
+        ctx.cfg = (int(use_symlog), tol, mode.shape)
+        return out.reshape(lead)
+
+    @staticmethod
+    def backward(ctx, g):
+        m2, v2 = ctx.saved_tensors
+        use_symlog, tol, shape = ctx.cfg
+        R, n = m2.shape
+        d = torch.empty_like(m2)
+        L.check(L.lib().dv3_sqerr_logprob_bwd(L.fptr(m2), L.fptr(v2), L.fptr(_f32(g).reshape(R)), R, n,
+                                              use_symlog, tol, L.fptr(d), L.stream_ptr()),
+                "sqerr_logprob_bwd")
+        return d.reshape(shape), None, None, None
+
+
+def sqerr_logprob(mode, value, use_symlog, tol=1e-8):
+    return _SqerrLogprob.apply(mode, value, bool(use_symlog), float(tol))
+
+
+class _BernoulliLogprob(torch.autograd.Function):
+    """tools.Bernoulli.log_prob (reference tools.py:604-628), element-wise."""
+
+    @staticmethod
+    def forward(ctx, logits, x):
+        lg, xv = _f32(logits).reshape(-1), _f32(x).reshape(-1)
+        out = torch.empty_like(lg)
+        L.check(L.lib().dv3_bernoulli_logprob_fwd(L.fptr(lg), L.fptr(xv), lg.numel(), L.fptr(out),
+                                                  L.stream_ptr()), "bernoulli_logprob_fwd")
+        ctx.save_for_backward(lg, xv)
+        ctx.shape = logits.shape
+        return out.reshape(logits.shape)
+
+    @staticmethod
+    def backward(ctx, g):
+        lg, xv = ctx.saved_tensors
+        d = torch.empty_like(lg)
+        L.check(L.lib().dv3_bernoulli_logprob_bwd(L.fptr(lg), L.fptr(xv), L.fptr(_f32(g).reshape(-1)),
+                                                  lg.numel(), L.fptr(d), L.stream_ptr()),
+                "bernoulli_logprob_bwd")
+        return d.reshape(ctx.shape), None
+
+
+def bernoulli_logprob(logits, x):
+    return _BernoulliLogprob.apply(logits, x)
+
+
+class _LossMean(torch.autograd.Function):
+    """mean_r sum_i scales[i] * terms[i][r] -> 0-dim tensor (reference models.py:140-152: the
+    scaled per-head losses plus the KL loss, averaged over the batch)."""
+
+    @staticmethod
+    def forward(ctx, scales, *terms):
+        ts = [_f32(t).reshape(-1) for t in terms]
+        R = ts[0].numel()
+        if any(t.numel() != R for t in ts):
+            raise L.Dv3Error("loss_mean: terms differ in size")
+        out = _empty(1, like=ts[0])
+        neg = torch.empty(len(ts), R, dtype=torch.float32, device=ts[0].device)
+        sc = (C.c_float * len(ts))(*scales)
+        ptrs = L.float_ptr_array(ts)
+        L.check(L.lib().dv3_loss_mean_fwd(ptrs, sc, len(ts), R, L.fptr(out), L.fptr(neg),
+                                          L.stream_ptr()), "loss_mean_fwd")
+        ctx.cfg = (tuple(scales), R, [t.shape for t in terms])
+        ctx.like = ts[0]
+        ctx.mark_non_differentiable(neg)
+        return out.reshape(()), neg
+
+    @staticmethod
+    def backward(ctx, g, _gneg):
+        scales, R, shapes = ctx.cfg
+        grads = torch.empty(len(scales), R, dtype=torch.float32, device=ctx.like.device)
+        sc = (C.c_float * len(scales))(*scales)
+        L.check(L.lib().dv3_loss_mean_bwd(L.fptr(_f32(g).reshape(1)), sc, len(scales), R, L.fptr(grads),
+                                          L.stream_ptr()), "loss_mean_bwd")
+        return (None, *[grads[i].reshape(s) for i, s in enumerate(shapes)])
+
+
+def loss_mean(terms, scales):
+    """-> (mean 0-dim, neg [n_terms, R] = -terms, no gradient)."""
+    return _LossMean.apply(tuple(float(s) for s in scales), *terms)
+
+
+class _DiscountWeights(torch.autograd.Function):
+    """discount = gamma * sigmoid(cont_logit), weights = cumprod([1, discount[:-1]]) over the time
+    axis (reference models.py:620-638); weights carry no gradient."""
+
+    @staticmethod
+    def forward(ctx, cont_logit, gamma):
+        H = cont_logit.shape[0]
+        lg = _f32(cont_logit).reshape(H, -1)
+        N = lg.shape[1]
+        disc, w = torch.empty_like(lg), torch.empty_like(lg)
+        L.check(L.lib().dv3_discount_weights_fwd(L.fptr(lg), gamma, H, N, L.fptr(disc), L.fptr(w),
+                                                 L.stream_ptr()), "discount_weights_fwd")
+        ctx.save_for_backward(lg)
+        ctx.cfg = (gamma, cont_logit.shape)
+        ctx.mark_non_differentiable(w)
+        return disc.reshape(cont_logit.shape), w.reshape(cont_logit.shape)
+
+    @staticmethod
+    def backward(ctx, g_disc, _gw):
+        (lg,) = ctx.saved_tensors
+        gamma, shape = ctx.cfg
+        d = torch.empty_like(lg)
+        L.check(L.lib().dv3_discount_bwd(L.fptr(lg), L.fptr(_f32(g_disc).reshape(lg.shape)), gamma,
+                                         lg.numel(), L.fptr(d), L.stream_ptr()), "discount_bwd")
+        return d.reshape(shape), None
+
+
+def discount_weights(cont_logit, gamma):
+    return _DiscountWeights.apply(cont_logit, float(gamma))
+
+
+REWARD_EMA_MAX = 16384
+
+
+def reward_ema(x, ema_vals, alpha):
+    """RewardEMA.__call__ (reference models.py:11-26): updates ``ema_vals`` [2] in place and returns
+    a [2] tensor (offset, scale).  x: any shape, at most REWARD_EMA_MAX elements."""
+    xf = _f32(x.detach()).reshape(-1)
+    out = _empty(2, like=xf)
+    L.check(L.lib().dv3_reward_ema(L.fptr(xf), xf.numel(), float(alpha), L.fptr(ema_vals), L.fptr(out),
+                                   L.stream_ptr()), "reward_ema")
+    return out
+
+
+class _ActorLoss(torch.autograd.Function):
+    """mean over the (H-1)*N leading elements of -w * actor_target - c_ent * entropy, with
+    actor_target = normed_target - normed_base ('dynamics', mode 0) or logp * (target - base)
+    ('reinforce', mode 1); reference models.py:393-397, 640-681.  Also returns normed_target."""
+
+    @staticmethod
+    def forward(ctx, target, base, weights, entropy, logp, offset_scale, c_ent, mode):
+        Hm = target.shape[0]
+        H = weights.shape[0]
+        tg, bs = _f32(target).reshape(Hm, -1), _f32(base).reshape(Hm, -1)
+        N = tg.shape[1]
+        w, en = _f32(weights).reshape(H, N), _f32(entropy).reshape(H, N)
+        lp = _f32(logp).reshape(H, N) if logp is not None else None
+        loss = _empty(1, like=tg)
+        normed = torch.empty_like(tg)
+        L.check(L.lib().dv3_actor_loss_fwd(L.fptr(tg), L.fptr(bs), L.fptr(w), L.fptr(en), L.fptr(lp),
+                                           L.fptr(offset_scale), c_ent, mode, Hm * N, L.fptr(normed),
+                                           L.fptr(loss), L.stream_ptr()), "actor_loss_fwd")
+        ctx.save_for_backward(tg, bs, w, offset_scale if offset_scale is not None else loss)
+        ctx.cfg = (c_ent, mode, Hm, H, N, target.shape, entropy.shape,
+                   logp.shape if logp is not None else None, offset_scale is not None)
+        ctx.mark_non_differentiable(normed)
+        return loss.reshape(()), normed.reshape(target.shape)
+
+    @staticmethod
+    def backward(ctx, g, _gn):
+        tg, bs, w, os_ = ctx.saved_tensors
+        c_ent, mode, Hm, H, N, tshape, eshape, lshape, has_os = ctx.cfg
+        d_t = torch.empty_like(tg) if mode == 0 else None
+        d_e = torch.empty(H, N, dtype=torch.float32, device=tg.device)
+        d_l = torch.empty(H, N, dtype=torch.float32, device=tg.device) if mode == 1 else None
+        L.check(L.lib().dv3_actor_loss_bwd(L.fptr(_f32(g).reshape(1)), L.fptr(tg), L.fptr(bs), L.fptr(w),
+                                           L.fptr(os_) if has_os else None, c_ent, mode, Hm * N, H * N,
+                                           L.fptr(d_t), L.fptr(d_e), L.fptr(d_l), L.stream_ptr()),
+                "actor_loss_bwd")
+        return (d_t.reshape(tshape) if d_t is not None else None, None, None, d_e.reshape(eshape),
+                d_l.reshape(lshape) if d_l is not None else None, None, None, None)
+
+
+def actor_loss(target, base, weights, entropy, logp, offset_scale, c_ent, mode):
+    """-> (loss 0-dim, normed_target like target).  mode: 'dynamics' | 'reinforce'."""
+    return _ActorLoss.apply(target, base, weights, entropy, logp, offset_scale, float(c_ent),
+                            {"dynamics": 0, "reinforce": 1}[mode])
+
+
+class _ValueLoss(torch.autograd.Function):
+    """mean_i w_i * (-lp_target_i - lp_slow_i) over [H-1,N] (reference models.py:419-429)."""
+
+    @staticmethod
+    def forward(ctx, lp_target, lp_slow, weights):
+        a = _f32(lp_target).reshape(-1)
+        b = _f32(lp_slow).reshape(-1) if lp_slow is not None else None
+        cnt = a.numel()
+        w = _f32(weights).reshape(-1)
+        if w.numel() < cnt:
+            raise L.Dv3Error("value_loss: weights shorter than the log-probs")
+        loss = _empty(1, like=a)
+        L.check(L.lib().dv3_value_loss_fwd(L.fptr(a), L.fptr(b), L.fptr(w), cnt, L.fptr(loss),
+                                           L.stream_ptr()), "value_loss_fwd")
+        ctx.save_for_backward(w)
+        ctx.cfg = (cnt, lp_target.shape, lp_slow.shape if lp_slow is not None else None)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (w,) = ctx.saved_tensors
+        cnt, s1, s2 = ctx.cfg
+        d = torch.empty(cnt, dtype=torch.float32, device=w.device)
+        L.check(L.lib().dv3_value_loss_bwd(L.fptr(_f32(g).reshape(1)), L.fptr(w), cnt, L.fptr(d),
+                                           L.stream_ptr()), "value_loss_bwd")
+        return d.reshape(s1), (d.reshape(s2) if s2 is not None else None), None
+
+
+def value_loss(lp_target, lp_slow, weights):
+    return _ValueLoss.apply(lp_target, lp_slow, weights)
+
+
+class _NormalPolicy(torch.autograd.Function):
+    """Entropy and log_prob(action) of the 'normal' actor distribution from its raw head outputs
+    (reference networks.py:693-700, tools.py:575-601): -> entropy [lead], logp [lead]."""
+
+    @staticmethod
+    def forward(ctx, mean_raw, std_raw, action, min_std, max_std, want_logp):
+        A = mean_raw.shape[-1]
+        lead = mean_raw.shape[:-1]
+        mr, sr, ac = (_f32(t).reshape(-1, A) for t in (mean_raw, std_raw, action))
+        R = mr.shape[0]
+        ent = _empty(R, like=mr)
+        lp = _empty(R, like=mr) if want_logp else None
+        L.check(L.lib().dv3_normal_policy_fwd(L.fptr(mr), L.fptr(sr), L.fptr(ac), min_std, max_std, R, A,
+                                              L.fptr(ent), L.fptr(lp), L.stream_ptr()), "normal_policy_fwd")
+        ctx.save_for_backward(mr, sr, ac)
+        ctx.cfg = (min_std, max_std, want_logp, mean_raw.shape)
+        if lp is None:
+            lp = ent.new_zeros(0)
+            ctx.mark_non_differentiable(lp)
+            return ent.reshape(lead), lp
+        return ent.reshape(lead), lp.reshape(lead)
+
+    @staticmethod
+    def backward(ctx, g_ent, g_lp):
+        mr, sr, ac = ctx.saved_tensors
+        min_std, max_std, want_logp, shape = ctx.cfg
+        R, A = mr.shape
+        d_m, d_s = torch.empty_like(mr), torch.empty_like(mr)
+        use_lp = want_logp and g_lp is not None
+        d_a = torch.empty_like(mr) if (use_lp and ctx.needs_input_grad[2]) else None
+        L.check(L.lib().dv3_normal_policy_bwd(
+            L.fptr(mr), L.fptr(sr), L.fptr(ac), L.fptr(_f32(g_ent).reshape(R)) if g_ent is not None else None,
+            L.fptr(_f32(g_lp).reshape(R)) if use_lp else None, min_std, max_std, R, A, L.fptr(d_m),
+            L.fptr(d_s), L.fptr(d_a), L.stream_ptr()), "normal_policy_bwd")
+        return (d_m.reshape(shape), d_s.reshape(shape), d_a.reshape(shape) if d_a is not None else None,
+                None, None, None)
+
+
+def normal_policy(mean_raw, std_raw, action, min_std, max_std, want_logp):
+    ent, lp = _NormalPolicy.apply(mean_raw, std_raw, action, float(min_std), float(max_std),
+                                  bool(want_logp))
+    return ent, (lp if want_logp else None)
+
+
+def tensorstats4(x):
+    """-> [4] tensor: mean, unbiased std, min, max (reference tools.py:949-958)."""
+    xf = _f32(x.detach()).reshape(-1)
+    out = _empty(4, like=xf)
+    L.check(L.lib().dv3_tensorstats(L.fptr(xf), xf.numel(), L.fptr(out), L.stream_ptr()), "tensorstats")
+    return out
+
+
+def ema_mix(dst_flat, src_flat, mix):
+    """dst = mix * src + (1 - mix) * dst over flat fp32 buffers (slow critic, models.py:683-689)."""
+    L.check(L.lib().dv3_ema_mix(L.fptr(dst_flat), L.fptr(src_flat), dst_flat.numel(), float(mix),
+                                L.stream_ptr()), "ema_mix")

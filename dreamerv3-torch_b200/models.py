@@ -27,10 +27,17 @@ class RewardEMA:
         self.range = torch.tensor([0.05, 0.95], device=device)
 
     def __call__(self, x, ema_vals):
+        if x.is_cuda and 0 < x.numel() <= K.REWARD_EMA_MAX and ema_vals.is_contiguous():
+            os_ = self.offset_scale(x, ema_vals)
+            return os_[0], os_[1]
         q = torch.quantile(x.detach().flatten(), self.range)
         ema_vals[:] = self.alpha * q + (1 - self.alpha) * ema_vals
         scale = torch.clip(ema_vals[1] - ema_vals[0], min=1.0)
         return ema_vals[0].detach(), scale.detach()
+
+    def offset_scale(self, x, ema_vals):
+        """One kernel: sort + 5/95 % quantiles + EMA (in place on ``ema_vals``) -> [offset, scale]."""
+        return K.reward_ema(x, ema_vals, self.alpha)
 
 
 class WorldModel(nn.Module):
@@ -105,16 +112,25 @@ class WorldModel(nn.Module):
                 preds.update(pred)
             else:
                 preds[name] = pred
-        losses = {}
+        logps = {}
         for name, pred in preds.items():
-            loss = -pred.log_prob(data[name])
-            if loss.shape != embed.shape[:2]:
-                raise AssertionError((name, loss.shape))
-            losses[name] = loss
-        model_loss = sum(v * self._scales.get(k, 1.0) for k, v in losses.items()) + kl_loss
+            lp = pred.log_prob(data[name])
+            if lp.shape != embed.shape[:2]:
+                raise AssertionError((name, lp.shape))
+            logps[name] = lp
+        # model_loss = mean(sum_k scale_k * (-log_prob_k) + kl_loss) (reference models.py:140-152)
+        names = list(logps)
+        if embed.is_cuda and len(names) < 8:
+            mean_loss, neg = K.loss_mean([logps[k] for k in names] + [kl_loss],
+                                         [-self._scales.get(k, 1.0) for k in names] + [1.0])
+            losses = {k: neg[i].reshape(lp.shape) for i, k in enumerate(names)}
+        else:
+            losses = {k: -v for k, v in logps.items()}
+            mean_loss = torch.mean(sum(v * self._scales.get(k, 1.0) for k, v in losses.items())
+                                   + kl_loss)
         aux = dict(embed=embed, feat=feat, prior=prior, losses=losses, kl_value=kl_value,
                    dyn_loss=dyn_loss, rep_loss=rep_loss, post_ent=post_ent, prior_ent=prior_ent)
-        return torch.mean(model_loss), post, aux
+        return mean_loss, post, aux
 
     def _train(self, data, noise=None):
         cfg = self._config
@@ -133,7 +149,9 @@ class WorldModel(nn.Module):
         metrics["post_ent"] = torch.mean(aux["post_ent"])
         context = dict(embed=aux["embed"], feat=aux["feat"], kl=aux["kl_value"],
                        postent=aux["post_ent"])
+        idx = self.dynamics._to_idx(post["stoch"])
         post = {k: v.detach() for k, v in post.items()}
+        self.dynamics.tag_idx(post["stoch"], idx)        # _imagine starts from these indices
         if not getattr(cfg, "device_metrics", False):
             metrics = tools.to_host(metrics)
         return post, context, metrics
@@ -183,8 +201,24 @@ class ImagBehavior(nn.Module):
                                           config.critic["eps"], config.critic["grad_clip"], **kw)
         self.actor.requires_grad_(False)
         self.value.requires_grad_(False)
+        self._slow_flat = None
         if config.critic["slow_target"]:
             self._slow_value.requires_grad_(False)
+            self._rehome_slow()
+
+    def _rehome_slow(self):
+        """Give the slow critic the flat layout of the critic's parameter buffer, so that the EMA
+        update (reference models.py:683-689) is one kernel over two flat buffers."""
+        opt = self._value_opt
+        if not getattr(opt, "_flat", False):
+            return
+        flat = torch.zeros_like(opt._fp)
+        with torch.no_grad():
+            for p, off in zip(self._slow_value.parameters(), opt._offsets):
+                view = flat[off:off + p.numel()].view(p.shape)
+                view.copy_(p.data)
+                p.data = view
+        self._slow_flat = flat
 
     # ---- rollout -------------------------------------------------------------------------
     def _imagine(self, start, policy, horizon, noise=None):
@@ -194,6 +228,7 @@ class ImagBehavior(nn.Module):
         dyn = self._world_model.dynamics
         S, Cc = dyn._stoch, dyn._discrete
         flat = {k: v.reshape([-1] + list(v.shape[2:])) for k, v in start.items()}
+        start_idx = dyn._to_idx(start["stoch"]).reshape(-1, S)
         N = flat["deter"].shape[0]
         dev = flat["deter"].device
         spec = policy.actor_spec()
@@ -202,8 +237,8 @@ class ImagBehavior(nn.Module):
             an = (torch.randn(horizon, N, A, device=dev) if spec.dist == "normal"
                   else torch.rand(horizon, N, A, device=dev))
             noise = (an, torch.rand(horizon, N, S, Cc, device=dev))
-        feat, logit, action, _, mean_raw, std_raw = K.imagine_full(
-            dyn._to_idx(flat["stoch"]), flat["deter"].detach(), noise[0], noise[1], None, horizon,
+        feat, logit, action, idx, mean_raw, std_raw, sp = K.imagine_full(
+            start_idx, flat["deter"].detach(), noise[0], noise[1], None, horizon,
             dyn.dims, spec, dyn.kernel_params(), policy.actor_params(),
             start_logit=flat.get("logit"))
         SC = S * Cc
@@ -218,8 +253,7 @@ class ImagBehavior(nn.Module):
         # raw head outputs of the in-loop actor (differentiable w.r.t. the actor parameters):
         # losses() builds the policy distribution from them instead of re-running the actor
         action._dv3_policy_raw = (policy, mean_raw, std_raw if std_raw.numel() else None)
-        if horizon * N >= 64:
-            sp = K.split(imag_feat.reshape(horizon * N, -1))
+        if sp is not None:
             K.attach_split(feat, sp)
             K.attach_split(imag_feat, sp)
         return imag_feat, states, action
@@ -241,21 +275,44 @@ class ImagBehavior(nn.Module):
             v_mode = v_all.mode().detach() if isinstance(v_all, tools.DiscDist) else None
             reward = objective(imag_feat, imag_state, imag_action)
             raw = getattr(imag_action, "_dv3_policy_raw", None)
-            if raw is not None and raw[0] is self.actor:
-                # same numbers the reference gets from self.actor(imag_feat) (models.py:349): the
-                # rollout already evaluated the actor on these very features
-                std = raw[2] if raw[2] is not None else self.actor._std
-                policy = self.actor.dist(self.actor._dist, raw[1], std, self.actor._shape)
+            reuse = raw is not None and raw[0] is self.actor
+            grad_mode = cfg.imag_gradient
+            fused = (imag_feat.is_cuda and v_mode is not None and grad_mode in ("dynamics", "reinforce")
+                     and (not cfg.reward_EMA or (imag_feat.shape[0] - 1) * imag_feat.shape[1]
+                          <= K.REWARD_EMA_MAX))
+            policy = logp = None
+            if reuse and self.actor._dist == "normal" and raw[2] is not None and fused:
+                # entropy / log-prob straight from the in-loop actor's raw head outputs: the same
+                # numbers the reference gets from self.actor(imag_feat) (models.py:349), one kernel
+                actor_ent, logp = K.normal_policy(raw[1], raw[2], imag_action, self.actor._min_std,
+                                                  self.actor._max_std, grad_mode == "reinforce")
             else:
-                policy = self.actor(imag_feat)
-            actor_ent = policy.entropy()
+                if reuse:
+                    std = raw[2] if raw[2] is not None else self.actor._std
+                    policy = self.actor.dist(self.actor._dist, raw[1], std, self.actor._shape)
+                else:
+                    policy = self.actor(imag_feat)
+                actor_ent = policy.entropy()
+                if fused and grad_mode == "reinforce":
+                    logp = policy.log_prob(imag_action)
             target, weights, base = self._compute_target(imag_feat, imag_state, reward,
                                                          value_mode=v_mode)
-            actor_loss, mets = self._compute_actor_loss(imag_feat, imag_action, target, weights,
-                                                        base, policy, value_mode=v_mode)
-            actor_loss = actor_loss - cfg.actor["entropy"] * actor_ent[:-1, ..., None]
-            actor_loss = torch.mean(actor_loss)
-            metrics.update(mets)
+            if fused:
+                os_ = None
+                if cfg.reward_EMA:
+                    os_ = self.reward_ema.offset_scale(target, self.ema_vals)
+                    metrics["EMA_005"] = self.ema_vals[0].detach()   # valid until the next step
+                    metrics["EMA_095"] = self.ema_vals[1].detach()
+                actor_loss, normed = K.actor_loss(target, base, weights, actor_ent, logp, os_,
+                                                  cfg.actor["entropy"], grad_mode)
+                if cfg.reward_EMA:
+                    metrics.update(tools.tensorstats(normed, "normed_target"))
+            else:
+                actor_loss, mets = self._compute_actor_loss(imag_feat, imag_action, target, weights,
+                                                            base, policy, value_mode=v_mode)
+                actor_loss = actor_loss - cfg.actor["entropy"] * actor_ent[:-1, ..., None]
+                actor_loss = torch.mean(actor_loss)
+                metrics.update(mets)
         with tools.RequiresGrad(self.value):
             feat_m1 = imag_feat[:-1].detach()
             sp = K.split_of_attached(imag_feat)
@@ -263,11 +320,18 @@ class ImagBehavior(nn.Module):
                 K.attach_split(feat_m1, sp.prefix(feat_m1.shape[0] * feat_m1.shape[1]))
             value = (tools.DiscDist(logits=v_all.logits[:-1]) if v_mode is not None
                      else self.value(feat_m1))
-            value_loss = -value.log_prob(target.detach())
+            lp_target = value.log_prob(target.detach())
+            lp_slow = None
             if cfg.critic["slow_target"]:
                 slow = self._slow_value(feat_m1)
-                value_loss = value_loss - value.log_prob(slow.mode().detach())
-            value_loss = torch.mean(weights[:-1] * value_loss[:, :, None])
+                lp_slow = value.log_prob(slow.mode().detach())
+            if imag_feat.is_cuda:
+                value_loss = K.value_loss(lp_target, lp_slow, weights)
+            else:
+                value_loss = -lp_target
+                if lp_slow is not None:
+                    value_loss = value_loss - lp_slow
+                value_loss = torch.mean(weights[:-1] * value_loss[:, :, None])
         metrics.update(tools.tensorstats(v_mode[:-1] if v_mode is not None else value.mode(), "value"))
         metrics.update(tools.tensorstats(target, "target"))
         metrics.update(tools.tensorstats(reward, "imag_reward"))
@@ -297,16 +361,22 @@ class ImagBehavior(nn.Module):
         the critic's mode over all H steps when the caller already evaluated it."""
         cfg = self._config
         wm = self._world_model
+        weights = None
         if "cont" in wm.heads:
             inp = wm.dynamics.get_feat(imag_state)
-            discount = cfg.discount * wm.heads["cont"](inp).mean
+            cont = wm.heads["cont"](inp)
+            if inp.is_cuda and isinstance(cont, tools.Bernoulli):
+                discount, weights = K.discount_weights(cont.logits, cfg.discount)
+            else:
+                discount = cfg.discount * cont.mean
         else:
             discount = cfg.discount * torch.ones_like(reward)
         value = value_mode if value_mode is not None else self.value(imag_feat).mode()
         target = tools.lambda_return_stacked(reward[1:], value[:-1], discount[1:], value[-1],
                                              cfg.discount_lambda)
-        weights = torch.cumprod(torch.cat([torch.ones_like(discount[:1]), discount[:-1]], 0),
-                                0).detach()
+        if weights is None:
+            weights = torch.cumprod(torch.cat([torch.ones_like(discount[:1]), discount[:-1]], 0),
+                                    0).detach()
         return target, weights, value[:-1]
 
     def _compute_actor_loss(self, imag_feat, imag_action, target, weights, base, policy=None,
@@ -347,9 +417,12 @@ class ImagBehavior(nn.Module):
             if self._updates % cfg.critic["slow_target_update"] == 0:
                 mix = cfg.critic["slow_target_fraction"]
                 with torch.no_grad():
-                    src = list(self.value.parameters())
-                    dst = list(self._slow_value.parameters())
-                    torch._foreach_mul_(dst, 1 - mix)
-                    torch._foreach_add_(dst, src, alpha=mix)
+                    if self._slow_flat is not None:
+                        K.ema_mix(self._slow_flat, self._value_opt._fp, mix)
+                    else:
+                        src = list(self.value.parameters())
+                        dst = list(self._slow_value.parameters())
+                        torch._foreach_mul_(dst, 1 - mix)
+                        torch._foreach_add_(dst, src, alpha=mix)
                 K.invalidate_weight_splits()
             self._updates += 1

@@ -96,7 +96,17 @@ class RSSM(nn.Module):
 
     @staticmethod
     def _to_idx(stoch):
+        """Class indices of a one-hot stoch tensor.  Tensors produced by ``observe`` carry the
+        int32 indices the kernel sampled (``tag_idx``), so no argmax pass is needed for them."""
+        hit = getattr(stoch, "_dv3_idx", None)
+        if hit is not None and hit[0] == stoch._version and hit[1].shape == stoch.shape[:-1]:
+            return hit[1]
         return torch.argmax(stoch, -1).to(torch.int32).contiguous()
+
+    @staticmethod
+    def tag_idx(stoch, idx):
+        stoch._dv3_idx = (stoch._version, idx)
+        return stoch
 
     # ---- reference API ---------------------------------------------------------------
     def initial(self, batch_size):
@@ -122,9 +132,11 @@ class RSSM(nn.Module):
         sidx = sdet = None
         if state is not None:
             sidx, sdet = self._to_idx(state["stoch"]), state["deter"]
-        (post_stoch, post_logit, prior_stoch, prior_logit, deter, aprev, _, _) = K.observe(
-            embed, action, is_first, noise[0], noise[1], sidx, sdet, self.dims,
-            self.kernel_params())
+        (post_stoch, post_logit, prior_stoch, prior_logit, deter, aprev, post_idx, prior_idx) = \
+            K.observe(embed, action, is_first, noise[0], noise[1], sidx, sdet, self.dims,
+                      self.kernel_params())
+        self.tag_idx(post_stoch, post_idx)
+        self.tag_idx(prior_stoch, prior_idx)
         if action.shape == aprev.shape and not action.requires_grad:
             action.copy_(aprev)
         post = dict(stoch=post_stoch, deter=deter, logit=post_logit)
@@ -255,9 +267,11 @@ class MLP(nn.Module):
     def trunk(self, features):
         """[Linear(no bias) -> LayerNorm -> SiLU] x layers (networks.py:657-661) on the tensor-core
         GEMM + LN/SiLU row kernels."""
-        x = tools.symlog(features) if self._symlog_inputs else features
-        if not x.is_cuda:
+        if not features.is_cuda:
             raise L.Dv3Error("MLP forward needs CUDA tensors: the B200 path has no CPU fallback")
+        x = features
+        if self._symlog_inputs:
+            x = tools.symlog(features) if features.requires_grad else K.symlog(features)
         for i in range(self._layers):
             lin = getattr(self.layers, f"{self._name}_linear{i}")
             nrm = getattr(self.layers, f"{self._name}_norm{i}")

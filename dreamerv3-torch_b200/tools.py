@@ -205,13 +205,19 @@ class Bernoulli:
 
     def __init__(self, logits):
         self.logits = logits
-        self.mean = torch.sigmoid(logits)
+
+    @property
+    def mean(self):
+        return torch.sigmoid(self.logits)
 
     def mode(self):
-        m = torch.round(self.mean)
-        return m.detach() + self.mean - self.mean.detach()
+        mean = self.mean
+        m = torch.round(mean)
+        return m.detach() + mean - mean.detach()
 
     def log_prob(self, x):
+        if self.logits.is_cuda and self.logits.shape[-1] == 1 and x.shape == self.logits.shape:
+            return K.bernoulli_logprob(self.logits, x)[..., 0]      # the sum runs over one element
         return torch.sum(-F.softplus(self.logits) * (1 - x) - F.softplus(-self.logits) * x, -1)
 
     def entropy(self):
@@ -234,6 +240,8 @@ class MSEDist:
     def log_prob(self, value):
         if self._mode.shape != value.shape:
             raise AssertionError((self._mode.shape, value.shape))
+        if self._mode.is_cuda and self._mode.dim() >= 3:
+            return K.sqerr_logprob(self._mode, value, False)
         return -((self._mode - value) ** 2).flatten(2).sum(-1)
 
 
@@ -253,6 +261,8 @@ class SymlogDist:
     def log_prob(self, value):
         if self._mode.shape != value.shape:
             raise AssertionError((self._mode.shape, value.shape))
+        if self._mode.is_cuda and self._mode.dim() >= 3:
+            return K.sqerr_logprob(self._mode, value, True, self._tol)
         dist = (self._mode - symlog(value)) ** 2.0
         dist = torch.where(dist < self._tol, torch.zeros_like(dist), dist)
         return -dist.flatten(2).sum(-1)
@@ -276,7 +286,11 @@ def tensorstats(tensor, prefix=None):
     """mean/std/min/max as device scalars (the reference syncs four times here,
     tools.py:949-958; the host copy happens once per step in ``to_host``)."""
     t = tensor.detach().float()
-    out = {"mean": t.mean(), "std": t.std(), "min": t.min(), "max": t.max()}
+    if t.is_cuda and t.numel() > 0:
+        s4 = K.tensorstats4(t)                      # one kernel; the entries are views
+        out = {"mean": s4[0], "std": s4[1], "min": s4[2], "max": s4[3]}
+    else:
+        out = {"mean": t.mean(), "std": t.std(), "min": t.min(), "max": t.max()}
     return {f"{prefix}_{k}" if prefix else k: v for k, v in out.items()}
 
 
@@ -407,7 +421,6 @@ class Optimizer:
         self._step = torch.zeros(1, dtype=torch.float32, device=dev)
         self._ctl = torch.zeros(4, dtype=torch.float32, device=dev)
         self._scratch = torch.empty(1024, dtype=torch.float32, device=dev)
-        self._zero_like, self._pads = [], []
         with torch.no_grad():
             for p, off in zip(self._params, self._offsets):
                 n = p.numel()
@@ -415,9 +428,7 @@ class Optimizer:
                 view.copy_(p.data)
                 p.data = view
                 p.grad = None
-                gap = ((n + 3) & ~3) - n
-                self._zero_like.append(torch.zeros(n, dtype=torch.float32, device=dev))
-                self._pads.append(torch.zeros(gap, dtype=torch.float32, device=dev) if gap else None)
+        self._gviews = self._views(self._fg)
 
     def _views(self, flat):
         return [flat[off:off + p.numel()].view(p.shape) for p, off in zip(self._params, self._offsets)]
@@ -476,20 +487,37 @@ class Optimizer:
             self._opt.zero_grad(set_to_none=True)
             metrics[f"{self._name}_grad_norm"] = norm.detach()
             return metrics
-        # Gradients are produced as fresh tensors (autograd hands the first gradient of a leaf over
-        # without a kernel; accumulating into persistent views would cost one add launch per
-        # parameter) and gathered into the flat buffer by one batched copy.
+        # The flat gradient buffer is zeroed once and armed as the gradient sink: the library's
+        # backward Functions accumulate dW / LayerNorm / bias gradients straight into its views
+        # (kernels.arm_grad_sink); gradients that still arrive through autograd (torch modules:
+        # the conv stacks) are copied in per parameter afterwards.
         for p in params:
             p.grad = None
-        loss.backward(retain_graph=retain_graph)
-        pieces = []
-        for p, z, pad in zip(params, self._zero_like, self._pads):
-            pieces.append(p.grad.reshape(-1) if p.grad is not None else z)
-            if pad is not None:
-                pieces.append(pad)
-        torch.cat(pieces, out=self._fg)
-        for p in params:
-            p.grad = None
+        self._fg.zero_()
+        K.arm_grad_sink(params, self._gviews)
+        try:
+            loss.backward(retain_graph=retain_graph)
+        finally:
+            written = K.disarm_grad_sink(params)
+        skipped = []
+        with torch.no_grad():
+            for i, (p, view, w) in enumerate(zip(params, self._gviews, written)):
+                if p.grad is not None:
+                    if w:
+                        view.add_(p.grad)
+                    else:
+                        view.copy_(p.grad)
+                    p.grad = None
+                elif not w:
+                    skipped.append(i)
+        # torch.optim.Adam leaves a parameter that received no gradient untouched (no moment
+        # decay, no move on stale momentum): keep that by restoring it after the fused update.
+        # (The step counter stays global: a parameter that is skipped in some steps gets the
+        # optimizer's bias correction, not a private one.)
+        keep = None
+        if skipped:
+            pv, mv, vv = self._views(self._fp), self._views(self._fm), self._views(self._fv)
+            keep = [(pv[i], pv[i].clone(), mv[i], mv[i].clone(), vv[i], vv[i].clone()) for i in skipped]
         if self._sync is not None:
             self._sync.flat(self._fg)
         L_ = K.L
@@ -499,6 +527,12 @@ class Optimizer:
             float(self._clip) if self._clip else 0.0, 1.0 - float(self._wd) if self._wd else 1.0,
             L_.fptr(self._step), L_.fptr(self._ctl), L_.fptr(self._scratch), L_.stream_ptr()),
             "adam_clip_step")
+        if keep is not None:
+            with torch.no_grad():
+                for p_, p0, m_, m0, v_, v0 in keep:
+                    p_.copy_(p0)
+                    m_.copy_(m0)
+                    v_.copy_(v0)
         K.invalidate_weight_splits()
         metrics[f"{self._name}_grad_norm"] = self._ctl[0].clone()
         return metrics

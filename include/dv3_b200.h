@@ -400,6 +400,9 @@ int dv3_ln_silu_bwd_split(const float* pre, int32_t ld, const float* g, const fl
  * (autograd of nn.LayerNorm's weight / bias, networks.py:56, 628, 758) */
 int dv3_ln_param_grads(const float* pre, int32_t ld, const float* d_ln, int32_t ldl, float eps,
                        int32_t M, int32_t n, float* dg, float* db, void* stream);
+/* the same sums ADDED onto dg / db (no zeroing): accumulation into a pre-zeroed flat gradient */
+int dv3_ln_param_grads_acc(const float* pre, int32_t ld, const float* d_ln, int32_t ldl, float eps,
+                           int32_t M, int32_t n, float* dg, float* db, void* stream);
 /* LayerNorm-GRU gate block (networks.py:760-768): parts = LN_3D(g_pre); r = sig(p0);
  * c = tanh(r*p1); u = sig(p2 - 1); h_new = u*c + (1-u)*h.  bwd also returns d_g_ln (gradient
  * w.r.t. the LayerNorm affine output) and d_h = the direct (1-u) path only. */
@@ -437,6 +440,79 @@ int dv3_idx_to_onehot(const int32_t* idx, int32_t M, int32_t S, int32_t C, float
 int dv3_adam_clip_step(float* p, const float* g, float* m, float* v, long long n, float lr,
                        float beta1, float beta2, float eps, float clip, float decay_mul,
                        float* step, float* ctl, float* scratch, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Step tail: the element-wise / reduction chains around the rollouts, one launch each
+ * (dv3_tail.cu).  Every array is contiguous fp32; "rows" R are the B*T or H*N samples.
+ * ---------------------------------------------------------------------------------------- */
+/* tools.symlog (tools.py:22-23), element-wise: the MLP encoder's input transform (networks.py:333) */
+int dv3_symlog(const float* x, long long n, float* out, void* stream);
+/* Squared-error heads: logprob[r] = -sum_j (mode[r,j] - t(value[r,j]))^2.
+ * use_symlog != 0: t = symlog and terms below tol are dropped -- tools.SymlogDist.log_prob
+ * (tools.py:546-572, dist 'mse', agg 'sum', tol 1e-8); use_symlog == 0: t = identity --
+ * tools.MSEDist.log_prob (tools.py:520-543).  bwd: d_mode = g_logprob[r] * d logprob / d mode. */
+int dv3_sqerr_logprob_fwd(const float* mode, const float* value, int32_t R, int32_t n,
+                          int32_t use_symlog, float tol, float* logprob, void* stream);
+int dv3_sqerr_logprob_bwd(const float* mode, const float* value, const float* g_logprob, int32_t R,
+                          int32_t n, int32_t use_symlog, float tol, float* d_mode, void* stream);
+/* tools.Bernoulli.log_prob (tools.py:604-628): -softplus(l)(1-x) - softplus(-l)x, element-wise */
+int dv3_bernoulli_logprob_fwd(const float* logit, const float* x, long long n, float* logprob,
+                              void* stream);
+int dv3_bernoulli_logprob_bwd(const float* logit, const float* x, const float* g, long long n,
+                              float* d_logit, void* stream);
+/* model_loss = mean_r sum_i scales[i] * terms[i][r]  (models.py:140-152; a term is a head's
+ * log_prob with scale -loss_scale, or the KL loss with scale 1): out is one float; neg_out
+ * (optional, [n_terms, R]) receives -terms[i][r], the per-head losses the metrics report.
+ * bwd fills grads [n_terms, R] with g[0] * scales[i] / R.  terms / scales are HOST arrays. */
+int dv3_loss_mean_fwd(const float* const* losses, const float* scales, int32_t n_losses, int32_t R,
+                      float* out, float* neg_out, void* stream);
+int dv3_loss_mean_bwd(const float* g, const float* scales, int32_t n_losses, int32_t R, float* grads,
+                      void* stream);
+/* ImagBehavior._compute_target (models.py:620-638), time-major [H,N]:
+ * discount = gamma * sigmoid(cont_logit); weights[t] = prod_{i<t} discount[i] (weights[0] = 1) */
+int dv3_discount_weights_fwd(const float* cont_logit, float gamma, int32_t H, int32_t N,
+                             float* discount, float* weights, void* stream);
+int dv3_discount_bwd(const float* cont_logit, const float* g_discount, float gamma, long long n,
+                     float* d_logit, void* stream);
+/* RewardEMA.__call__ (models.py:11-26): 5 % / 95 % torch.quantile ('linear') of x[n] (n <= 16384,
+ * sorted in one CTA's shared memory), ema_vals = alpha q + (1-alpha) ema_vals in place,
+ * offset_scale = {ema_vals[0], max(ema_vals[1] - ema_vals[0], 1)}. */
+int dv3_reward_ema(const float* x, int32_t n, double alpha, float* ema_vals, float* offset_scale,
+                   void* stream);
+/* ImagBehavior._compute_actor_loss + the entropy term (models.py:393-397, 640-681) over
+ * count = (H-1)*N leading elements of time-major [H,N] arrays.  mode 0 'dynamics':
+ * -w ((target-off)/scale - (base-off)/scale) - c_ent ent; mode 1 'reinforce':
+ * -w logp (target - base) - c_ent ent.  loss = mean; normed (optional) = (target-off)/scale.
+ * offset_scale NULL = reward_EMA off.  bwd writes d_target [count] (mode 0), d_logp [total]
+ * (mode 1) and d_entropy [total], total = H*N. */
+int dv3_actor_loss_fwd(const float* target, const float* base, const float* weights,
+                       const float* entropy, const float* logp, const float* offset_scale,
+                       float entropy_coef, int32_t mode, int32_t count, float* normed, float* loss,
+                       void* stream);
+int dv3_actor_loss_bwd(const float* g_loss, const float* target, const float* base,
+                       const float* weights, const float* offset_scale, float entropy_coef,
+                       int32_t mode, int32_t count, int32_t total, float* d_target, float* d_entropy,
+                       float* d_logp, void* stream);
+/* value loss (models.py:419-429): mean_i weights[i] * (-lp_target[i] - lp_slow[i]) (lp_slow may be
+ * NULL); bwd: d_lp[i] = -weights[i] g / count for both log-prob inputs */
+int dv3_value_loss_fwd(const float* lp_target, const float* lp_slow, const float* weights,
+                       int32_t count, float* loss, void* stream);
+int dv3_value_loss_bwd(const float* g_loss, const float* weights, int32_t count, float* d_lp,
+                       void* stream);
+/* 'normal' actor distribution (networks.py:693-700, tools.py:575-601) from the raw head outputs
+ * [R,A]: mean = tanh(mean_raw), std = (max-min) sigmoid(std_raw + 2) + min; entropy [R] and (logp
+ * != NULL) log_prob(action) [R].  bwd takes g_entropy / g_logp (either may be NULL). */
+int dv3_normal_policy_fwd(const float* mean_raw, const float* std_raw, const float* action,
+                          float min_std, float max_std, int32_t R, int32_t A, float* entropy,
+                          float* logp, void* stream);
+int dv3_normal_policy_bwd(const float* mean_raw, const float* std_raw, const float* action,
+                          const float* g_entropy, const float* g_logp, float min_std, float max_std,
+                          int32_t R, int32_t A, float* d_mean_raw, float* d_std_raw, float* d_action,
+                          void* stream);
+/* tools.tensorstats (tools.py:949-958): out4 = {mean, unbiased std, min, max} of x[n] */
+int dv3_tensorstats(const float* x, long long n, float* out4, void* stream);
+/* slow-critic update (models.py:683-689) over flat buffers: dst = mix * src + (1 - mix) * dst */
+int dv3_ema_mix(float* dst, const float* src, long long n, double mix, void* stream);
 
 /* Debug aid: with DV3_OBSERVE_TIMING=1 in the environment the persistent observe kernel stamps
  * %globaltimer (ns) at its 8 phase boundaries per step on CTA 0; this copies [T][8] stamps out. */

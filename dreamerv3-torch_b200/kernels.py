@@ -1110,8 +1110,9 @@ class _DiscountWeights(torch.autograd.Function):
                                                  L.stream_ptr()), "discount_weights_fwd")
         ctx.save_for_backward(lg)
         ctx.cfg = (gamma, cont_logit.shape)
-        ctx.mark_non_differentiable(w)
-        return disc.reshape(cont_logit.shape), w.reshape(cont_logit.shape)
+        disc, w = disc.reshape(cont_logit.shape), w.reshape(cont_logit.shape)
+        ctx.mark_non_differentiable(w)          # the very tensor object that is returned
+        return disc, w
 
     @staticmethod
     def backward(ctx, g_disc, _gw):
@@ -1161,8 +1162,9 @@ class _ActorLoss(torch.autograd.Function):
         ctx.save_for_backward(tg, bs, w, offset_scale if offset_scale is not None else loss)
         ctx.cfg = (c_ent, mode, Hm, H, N, target.shape, entropy.shape,
                    logp.shape if logp is not None else None, offset_scale is not None)
+        normed = normed.reshape(target.shape)
         ctx.mark_non_differentiable(normed)
-        return loss.reshape(()), normed.reshape(target.shape)
+        return loss.reshape(()), normed
 
     @staticmethod
     def backward(ctx, g, _gn):

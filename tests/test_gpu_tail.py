@@ -179,7 +179,7 @@ def test_normal_policy(pkg, device, want_logp):
         assert pc.rel(lp, lp_r) < TOL
     for a, b in zip(grads, rg):
         if b is None:
-            assert a is None
+            assert a is None or float(a.abs().max()) == 0.0
         elif not want_logp and a is None:
             assert float(b.abs().max()) == 0.0
         else:

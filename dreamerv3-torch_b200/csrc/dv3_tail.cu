@@ -145,46 +145,137 @@ __global__ void discount_bwd_kernel(const float* __restrict__ logit, const float
   d_logit[i] = g[i] * gamma * s * (1.f - s);
 }
 
-// ---- RewardEMA (models.py:11-26): sort in shared memory, torch.quantile('linear'), EMA ---------
-constexpr int EMA_MAX = 16384;
+// ---- RewardEMA (models.py:11-26): torch.quantile('linear') at 5 % / 95 % + EMA -------------------
+// torch sorts all n values (several radix-sort launches) and gathers two neighbours per quantile.
+// Only four order statistics are needed, so one CTA selects them by three-level radix select on
+// the monotonic integer image of the floats (11 + 11 + 10 bits): a histogram pass over the values
+// per level (they sit in L2), a warp-parallel prefix scan per wanted rank.  Exact, like a sort.
+constexpr int EMA_MAX = 1 << 20;
+constexpr int EMA_BINS = 2048;
 
-__global__ void __launch_bounds__(1024)
-reward_ema_kernel(const float* __restrict__ x, int n, int npow2, float alpha, float one_minus_alpha,
-                  float* __restrict__ ema, float* __restrict__ out) {
-  extern __shared__ float sv[];
-  __shared__ float res[2];
-  for (int i = threadIdx.x; i < npow2; i += blockDim.x) sv[i] = (i < n) ? x[i] : INFINITY;
-  __syncthreads();
-  for (int k = 2; k <= npow2; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < npow2; i += blockDim.x) {
-        const int ixj = i ^ j;
-        if (ixj > i) {
-          const float a = sv[i], b = sv[ixj];
-          const bool up = (i & k) == 0;
-          if ((a > b) == up) { sv[i] = b; sv[ixj] = a; }
-        }
-      }
-      __syncthreads();
+__device__ __forceinline__ unsigned ema_key(float f) {
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ema_unkey(unsigned k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
+}
+
+// warp w finds, in hist[w * stride .. + nbins), the bin holding the element of (0-based) rank
+// rk[w] and the rank left inside that bin
+__device__ __forceinline__ void ema_pick(const unsigned* hist, int nbins, unsigned rank, int lane,
+                                         unsigned* bin_out, unsigned* rank_out) {
+  const int per = nbins / 32;
+  unsigned mine = 0;
+  for (int i = 0; i < per; ++i) mine += hist[lane * per + i];
+  unsigned incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned v = __shfl_up_sync(FULL, incl, o);
+    if (lane >= o) incl += v;
+  }
+  const unsigned excl = incl - mine;
+  const bool here = rank >= excl && rank < incl;
+  const unsigned who = __ballot_sync(FULL, here);
+  const int src = __ffs(who) - 1;                    // exactly one lane (rank < n)
+  unsigned bin = 0, left = 0;
+  if (lane == src) {
+    unsigned acc = excl;
+    for (int i = 0; i < per; ++i) {
+      const unsigned c = hist[lane * per + i];
+      if (rank < acc + c) { bin = lane * per + i; left = rank - acc; break; }
+      acc += c;
     }
   }
-  if (threadIdx.x < 2) {
-    // torch.quantile: rank = q * (n-1) in fp32, lerp between the neighbours (ATen's lerp form)
-    const float q = threadIdx.x == 0 ? 0.05f : 0.95f;
+  *bin_out = __shfl_sync(FULL, bin, src);
+  *rank_out = __shfl_sync(FULL, left, src);
+}
+
+__global__ void __launch_bounds__(1024)
+reward_ema_kernel(const float* __restrict__ x, int n, float alpha, float one_minus_alpha,
+                  float* __restrict__ ema, float* __restrict__ out) {
+  __shared__ unsigned hist[4 * EMA_BINS];
+  __shared__ unsigned pref[4], left[4];
+  __shared__ float val[4], res[2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // wanted ranks: floor / ceil of q (n-1) for q = 0.05, 0.95 (rank computed in fp32 like torch)
+  unsigned want[4];
+  float wgt[2];
+#pragma unroll
+  for (int qi = 0; qi < 2; ++qi) {
+    const float q = qi == 0 ? 0.05f : 0.95f;
     const float rank = __fmul_rn(q, (float)(n - 1));
     const float lo = floorf(rank);
-    const float w = __fsub_rn(rank, lo);
-    const int i0 = (int)lo, i1 = (int)ceilf(rank);
-    const float a = sv[i0], b = sv[i1];
+    want[2 * qi] = (unsigned)lo;
+    want[2 * qi + 1] = (unsigned)ceilf(rank);
+    wgt[qi] = __fsub_rn(rank, lo);
+  }
+  // level 0: one histogram of the top 11 bits serves all four ranks
+  for (int i = tid; i < EMA_BINS; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  for (int i = tid; i < n; i += blockDim.x) atomicAdd(&hist[ema_key(x[i]) >> 21], 1u);
+  __syncthreads();
+  if (warp < 4) {
+    unsigned b, l;
+    ema_pick(hist, EMA_BINS, want[warp], lane, &b, &l);
+    if (lane == 0) { pref[warp] = b; left[warp] = l; }
+  }
+  __syncthreads();
+  // level 1: next 11 bits among the values sharing each rank's top bits
+  for (int i = tid; i < 4 * EMA_BINS; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  {
+    const unsigned p0 = pref[0], p1 = pref[1], p2 = pref[2], p3 = pref[3];
+    for (int i = tid; i < n; i += blockDim.x) {
+      const unsigned k = ema_key(x[i]);
+      const unsigned top = k >> 21, mid = (k >> 10) & 2047u;
+      if (top == p0) atomicAdd(&hist[mid], 1u);
+      if (top == p1) atomicAdd(&hist[EMA_BINS + mid], 1u);
+      if (top == p2) atomicAdd(&hist[2 * EMA_BINS + mid], 1u);
+      if (top == p3) atomicAdd(&hist[3 * EMA_BINS + mid], 1u);
+    }
+  }
+  __syncthreads();
+  if (warp < 4) {
+    unsigned b, l;
+    ema_pick(hist + warp * EMA_BINS, EMA_BINS, left[warp], lane, &b, &l);
+    __syncwarp();
+    if (lane == 0) { pref[warp] = (pref[warp] << 11) | b; left[warp] = l; }
+  }
+  __syncthreads();
+  // level 2: the last 10 bits
+  for (int i = tid; i < 4 * EMA_BINS; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  {
+    const unsigned p0 = pref[0], p1 = pref[1], p2 = pref[2], p3 = pref[3];
+    for (int i = tid; i < n; i += blockDim.x) {
+      const unsigned k = ema_key(x[i]);
+      const unsigned top = k >> 10, low = k & 1023u;
+      if (top == p0) atomicAdd(&hist[low], 1u);
+      if (top == p1) atomicAdd(&hist[EMA_BINS + low], 1u);
+      if (top == p2) atomicAdd(&hist[2 * EMA_BINS + low], 1u);
+      if (top == p3) atomicAdd(&hist[3 * EMA_BINS + low], 1u);
+    }
+  }
+  __syncthreads();
+  if (warp < 4) {
+    unsigned b, l;
+    ema_pick(hist + warp * EMA_BINS, 1024, left[warp], lane, &b, &l);
+    if (lane == 0) val[warp] = ema_unkey((pref[warp] << 10) | b);
+  }
+  __syncthreads();
+  if (tid < 2) {
+    // ATen's lerp: a + w (b - a) for w < 0.5, else b - (b - a)(1 - w)
+    const float a = val[2 * tid], b = val[2 * tid + 1], w = wgt[tid];
     const float diff = __fsub_rn(b, a);
     const float qv = (w < 0.5f) ? __fadd_rn(a, __fmul_rn(w, diff))
                                 : __fsub_rn(b, __fmul_rn(diff, __fsub_rn(1.f, w)));
-    const float e = __fadd_rn(__fmul_rn(alpha, qv), __fmul_rn(one_minus_alpha, ema[threadIdx.x]));
-    ema[threadIdx.x] = e;
-    res[threadIdx.x] = e;
+    const float e = __fadd_rn(__fmul_rn(alpha, qv), __fmul_rn(one_minus_alpha, ema[tid]));
+    ema[tid] = e;
+    res[tid] = e;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (tid == 0) {
     out[0] = res[0];                                  // offset
     out[1] = fmaxf(__fsub_rn(res[1], res[0]), 1.f);   // scale = clip(hi - lo, min=1)
   }
@@ -450,19 +541,11 @@ extern "C" int dv3_discount_bwd(const float* cont_logit, const float* g_discount
 extern "C" int dv3_reward_ema(const float* x, int32_t n, double alpha, float* ema_vals,
                               float* offset_scale, void* stream) {
   DV3_REQUIRE(x && ema_vals && offset_scale, DV3_ERR_NULL, "reward_ema: null pointer");
-  DV3_REQUIRE(n >= 1 && n <= EMA_MAX, DV3_ERR_BAD_SHAPE,
-              "reward_ema: n=%d outside [1, %d] (single-CTA sort)", n, EMA_MAX);
-  int np2 = 2;
-  while (np2 < n) np2 <<= 1;
-  static bool attr = false;
-  if (!attr) {
-    DV3_CHECK_CUDA(cudaFuncSetAttribute(reward_ema_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        EMA_MAX * 4));
-    attr = true;
-  }
+  DV3_REQUIRE(n >= 1 && n <= EMA_MAX, DV3_ERR_BAD_SHAPE, "reward_ema: n=%d outside [1, %d]", n,
+              EMA_MAX);
   // alpha * q and (1 - alpha) * ema with the python scalars rounded to fp32 once, like torch
-  reward_ema_kernel<<<1, 1024, (size_t)np2 * 4, ST>>>(x, n, np2, (float)alpha, (float)(1.0 - alpha),
-                                                     ema_vals, offset_scale);
+  reward_ema_kernel<<<1, 1024, 0, ST>>>(x, n, (float)alpha, (float)(1.0 - alpha), ema_vals,
+                                        offset_scale);
   DV3_CHECK_LAUNCH("reward_ema_kernel");
   return 0;
 }

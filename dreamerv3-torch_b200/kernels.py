@@ -1128,7 +1128,7 @@ def discount_weights(cont_logit, gamma):
     return _DiscountWeights.apply(cont_logit, float(gamma))
 
 
-REWARD_EMA_MAX = 16384
+REWARD_EMA_MAX = 1 << 20
 
 
 def reward_ema(x, ema_vals, alpha):

@@ -9,7 +9,9 @@ tests); without it they are drawn from torch's generator.
 """
 from __future__ import annotations
 
+import contextlib
 import copy
+import os
 
 import torch
 from torch import nn
@@ -202,9 +204,18 @@ class ImagBehavior(nn.Module):
         self.actor.requires_grad_(False)
         self.value.requires_grad_(False)
         self._slow_flat = None
+        self._side_stream = None
         if config.critic["slow_target"]:
             self._slow_value.requires_grad_(False)
             self._rehome_slow()
+
+    def _side(self, ref):
+        """Side stream of the critic branch (None on CPU tensors or with DV3_SIDE_STREAM=0)."""
+        if not ref.is_cuda or os.environ.get("DV3_SIDE_STREAM", "1") == "0":
+            return None
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream(device=ref.device)
+        return self._side_stream
 
     def _rehome_slow(self):
         """Give the slow critic the flat layout of the critic's parameter buffer, so that the EMA
@@ -270,10 +281,28 @@ class ImagBehavior(nn.Module):
             # One critic forward over all H steps serves the lambda-return target, the baseline
             # and the value loss: the reference evaluates self.value three times on the same
             # (detached) features with unchanged weights (models.py:629, 421, 662).
-            with tools.RequiresGrad(self.value):
+            # The critic branch (critic + slow-critic forward, value loss, and -- because autograd
+            # replays a node on the stream of its forward -- the critic's whole backward) lives on
+            # a side stream: in the captured step graph it is a parallel branch that fills the SMs
+            # the latency-bound imagination backward leaves idle.
+            main = torch.cuda.current_stream() if imag_feat.is_cuda else None
+            side = self._side(imag_feat)
+            on_side = (lambda: torch.cuda.stream(side)) if side is not None else contextlib.nullcontext
+            if side is not None:
+                side.wait_stream(main)
+            slow_mode = None
+            with tools.RequiresGrad(self.value), on_side():
                 v_all = self.value(imag_feat)
-            v_mode = v_all.mode().detach() if isinstance(v_all, tools.DiscDist) else None
+                v_mode = v_all.mode().detach() if isinstance(v_all, tools.DiscDist) else None
+                feat_m1 = imag_feat[:-1].detach()
+                sp = K.split_of_attached(imag_feat)
+                if sp is not None:
+                    K.attach_split(feat_m1, sp.prefix(feat_m1.shape[0] * feat_m1.shape[1]))
+                if cfg.critic["slow_target"]:
+                    slow_mode = self._slow_value(feat_m1).mode().detach()
             reward = objective(imag_feat, imag_state, imag_action)
+            if side is not None:
+                main.wait_stream(side)              # v_mode feeds the lambda-return target
             raw = getattr(imag_action, "_dv3_policy_raw", None)
             reuse = raw is not None and raw[0] is self.actor
             grad_mode = cfg.imag_gradient
@@ -313,18 +342,13 @@ class ImagBehavior(nn.Module):
                 actor_loss = actor_loss - cfg.actor["entropy"] * actor_ent[:-1, ..., None]
                 actor_loss = torch.mean(actor_loss)
                 metrics.update(mets)
-        with tools.RequiresGrad(self.value):
-            feat_m1 = imag_feat[:-1].detach()
-            sp = K.split_of_attached(imag_feat)
-            if sp is not None:
-                K.attach_split(feat_m1, sp.prefix(feat_m1.shape[0] * feat_m1.shape[1]))
+        if side is not None:
+            side.wait_stream(main)                  # target, weights, reward, actions
+        with tools.RequiresGrad(self.value), on_side():
             value = (tools.DiscDist(logits=v_all.logits[:-1]) if v_mode is not None
                      else self.value(feat_m1))
             lp_target = value.log_prob(target.detach())
-            lp_slow = None
-            if cfg.critic["slow_target"]:
-                slow = self._slow_value(feat_m1)
-                lp_slow = value.log_prob(slow.mode().detach())
+            lp_slow = value.log_prob(slow_mode) if slow_mode is not None else None
             if imag_feat.is_cuda:
                 value_loss = K.value_loss(lp_target, lp_slow, weights)
             else:
@@ -332,15 +356,17 @@ class ImagBehavior(nn.Module):
                 if lp_slow is not None:
                     value_loss = value_loss - lp_slow
                 value_loss = torch.mean(weights[:-1] * value_loss[:, :, None])
-        metrics.update(tools.tensorstats(v_mode[:-1] if v_mode is not None else value.mode(), "value"))
-        metrics.update(tools.tensorstats(target, "target"))
-        metrics.update(tools.tensorstats(reward, "imag_reward"))
-        if cfg.actor["dist"] in ["onehot"]:
-            metrics.update(tools.tensorstats(torch.argmax(imag_action, dim=-1).float(),
-                                             "imag_action"))
-        else:
-            metrics.update(tools.tensorstats(imag_action, "imag_action"))
-        metrics["actor_entropy"] = torch.mean(actor_ent.detach())
+            metrics.update(tools.tensorstats(v_mode[:-1] if v_mode is not None else value.mode(), "value"))
+            metrics.update(tools.tensorstats(target, "target"))
+            metrics.update(tools.tensorstats(reward, "imag_reward"))
+            if cfg.actor["dist"] in ["onehot"]:
+                metrics.update(tools.tensorstats(torch.argmax(imag_action, dim=-1).float(),
+                                                 "imag_action"))
+            else:
+                metrics.update(tools.tensorstats(imag_action, "imag_action"))
+            metrics["actor_entropy"] = torch.mean(actor_ent.detach())
+        if side is not None:
+            main.wait_stream(side)                  # callers continue on the current stream
         aux = dict(reward=reward, target=target, value=value)
         return actor_loss, value_loss, (imag_feat, imag_state, imag_action, weights), metrics, aux
 
@@ -348,10 +374,22 @@ class ImagBehavior(nn.Module):
         cfg = self._config
         self._update_slow_target()
         actor_loss, value_loss, roll, metrics, _ = self.losses(start, objective, noise)
-        with tools.RequiresGrad(self):
-            metrics.update(self._actor_opt(actor_loss, self.actor.parameters()))
-            metrics.update(self._value_opt(value_loss, self.value.parameters()))
         imag_feat, imag_state, imag_action, weights = roll
+        side = self._side(imag_feat)
+        with tools.RequiresGrad(self):
+            if side is None:
+                metrics.update(self._actor_opt(actor_loss, self.actor.parameters()))
+                metrics.update(self._value_opt(value_loss, self.value.parameters()))
+            else:
+                # critic backward + Adam on the side stream, concurrently with the actor's
+                # (imagination) backward on the current one
+                main = torch.cuda.current_stream()
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    m_v = self._value_opt(value_loss, self.value.parameters())
+                metrics.update(self._actor_opt(actor_loss, self.actor.parameters()))
+                metrics.update(m_v)
+                main.wait_stream(side)
         if not getattr(cfg, "device_metrics", False):
             metrics = tools.to_host(metrics)
         return imag_feat, imag_state, imag_action, weights, metrics

@@ -474,8 +474,8 @@ int dv3_discount_weights_fwd(const float* cont_logit, float gamma, int32_t H, in
                              float* discount, float* weights, void* stream);
 int dv3_discount_bwd(const float* cont_logit, const float* g_discount, float gamma, long long n,
                      float* d_logit, void* stream);
-/* RewardEMA.__call__ (models.py:11-26): 5 % / 95 % torch.quantile ('linear') of x[n] (n <= 16384,
- * sorted in one CTA's shared memory), ema_vals = alpha q + (1-alpha) ema_vals in place,
+/* RewardEMA.__call__ (models.py:11-26): 5 % / 95 % torch.quantile ('linear') of x[n] (n <= 2^20;
+ * the four order statistics by exact radix select in one CTA), ema_vals = alpha q + (1-alpha) ema_vals in place,
  * offset_scale = {ema_vals[0], max(ema_vals[1] - ema_vals[0], 1)}. */
 int dv3_reward_ema(const float* x, int32_t n, double alpha, float* ema_vals, float* offset_scale,
                    void* stream);

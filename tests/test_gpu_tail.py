@@ -93,7 +93,7 @@ def test_discount_weights(pkg, device):
     assert pc.rel(disc, dr_) < TOL and pc.rel(w, wr) < TOL and pc.rel(d, dr) < TOL
 
 
-@pytest.mark.parametrize("n", [1, 2, 60, 1000, 14336, 16384])
+@pytest.mark.parametrize("n", [1, 2, 60, 1000, 14336, 16384, 200000])
 def test_reward_ema(pkg, device, n):
     g = _g(5 + n)
     ema = torch.tensor([-0.3, 0.9]).to(device)

@@ -79,6 +79,16 @@ class WorldModel(nn.Module):
                             cont=config.cont_head["loss_scale"])
         self.requires_grad_(False)
 
+    def _head_streams(self, ref, n):
+        """One CUDA stream per head (none on CPU tensors or with DV3_SIDE_STREAM=0)."""
+        if not ref.is_cuda or os.environ.get("DV3_SIDE_STREAM", "1") == "0":
+            return []
+        pool = getattr(self, "_hstreams", None)
+        if pool is None or len(pool) < n:
+            pool = [torch.cuda.Stream(device=ref.device) for _ in range(n)]
+            object.__setattr__(self, "_hstreams", pool)
+        return pool[:n]
+
     def preprocess(self, obs):
         """numpy / CPU tensors -> fp32 device tensors (reference models.py:174-190); pinned host
         tensors are copied asynchronously."""
@@ -107,19 +117,32 @@ class WorldModel(nn.Module):
         if kl_loss.shape != embed.shape[:2]:
             raise AssertionError(kl_loss.shape)
         feat = self.dynamics.get_feat(post)
-        preds = {}
-        for name, head in self.heads.items():
-            pred = head(feat if name in cfg.grad_heads else feat.detach())
-            if isinstance(pred, dict):
-                preds.update(pred)
-            else:
-                preds[name] = pred
+        # The heads (decoder, reward, cont) are independent chains of 1024-row products that each
+        # fill less than half of the SMs: every head runs -- forward here, and therefore its
+        # backward too (autograd replays a node on its forward stream) -- on its own stream, a
+        # parallel branch of the captured step graph.
+        streams = self._head_streams(feat, len(self.heads))
+        main = torch.cuda.current_stream() if streams else None
+        if streams:
+            feat2 = feat.reshape(-1, feat.shape[-1])
+            if feat2.shape[0] >= 64:
+                K.split_of(feat2, feat)          # shared tf32 planes are made before the fork
         logps = {}
-        for name, pred in preds.items():
-            lp = pred.log_prob(data[name])
-            if lp.shape != embed.shape[:2]:
-                raise AssertionError((name, lp.shape))
-            logps[name] = lp
+        for i, (name, head) in enumerate(self.heads.items()):
+            ctx = contextlib.nullcontext()
+            if streams:
+                streams[i].wait_stream(main)
+                ctx = torch.cuda.stream(streams[i])
+            with ctx:
+                pred = head(feat if name in cfg.grad_heads else feat.detach())
+                preds = pred if isinstance(pred, dict) else {name: pred}
+                for key, dist in preds.items():
+                    lp = dist.log_prob(data[key])
+                    if lp.shape != embed.shape[:2]:
+                        raise AssertionError((key, lp.shape))
+                    logps[key] = lp
+        for st in streams:
+            main.wait_stream(st)
         # model_loss = mean(sum_k scale_k * (-log_prob_k) + kl_loss) (reference models.py:140-152)
         names = list(logps)
         if embed.is_cuda and len(names) < 8:

@@ -57,7 +57,8 @@ __global__ void adam_prepare_kernel(const float* __restrict__ partials, int np, 
 __global__ void __launch_bounds__(OP_THREADS)
 adam_update_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                    float* __restrict__ v, long long n4, float beta1, float beta2, float eps,
-                   float decay_mul, const float* __restrict__ ctl) {
+                   float decay_mul, const float* __restrict__ ctl, float* __restrict__ hi,
+                   float* __restrict__ lo) {
   const float coef = ctl[1], step_size = ctl[2], bc2s = ctl[3];
   const float omb1 = 1.f - beta1, omb2 = 1.f - beta2;
   float4* p4 = reinterpret_cast<float4*>(p);
@@ -81,15 +82,27 @@ adam_update_kernel(float* __restrict__ p, const float* __restrict__ g, float* __
     upd(pp.z, mm.z, vv.z, gg.z);
     upd(pp.w, mm.w, vv.w, gg.w);
     p4[i] = pp; m4[i] = mm; v4[i] = vv;
+    if (hi) {
+      // tf32 operand planes of the updated parameters (hi + lo == p exactly): the GEMMs of the
+      // next step read them, no per-weight split pass
+      float4 h, l;
+      h.x = __uint_as_float(__float_as_uint(pp.x) & 0xFFFFE000u);
+      h.y = __uint_as_float(__float_as_uint(pp.y) & 0xFFFFE000u);
+      h.z = __uint_as_float(__float_as_uint(pp.z) & 0xFFFFE000u);
+      h.w = __uint_as_float(__float_as_uint(pp.w) & 0xFFFFE000u);
+      l.x = pp.x - h.x; l.y = pp.y - h.y; l.z = pp.z - h.z; l.w = pp.w - h.w;
+      reinterpret_cast<float4*>(hi)[i] = h;
+      reinterpret_cast<float4*>(lo)[i] = l;
+    }
   }
 }
 
 }  // namespace dv3
 
-extern "C" int dv3_adam_clip_step(float* p, const float* g, float* m, float* v, long long n,
-                                  float lr, float beta1, float beta2, float eps, float clip,
-                                  float decay_mul, float* step, float* ctl, float* scratch,
-                                  void* stream) {
+static int adam_clip_step_any(float* p, const float* g, float* m, float* v, long long n, float lr,
+                              float beta1, float beta2, float eps, float clip, float decay_mul,
+                              float* step, float* ctl, float* scratch, float* hi, float* lo,
+                              void* stream) {
   using namespace dv3;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   DV3_REQUIRE(n >= 0 && n % 4 == 0, DV3_ERR_BAD_SHAPE, "adam_clip_step: n=%lld must be a multiple of 4", n);
@@ -103,7 +116,24 @@ extern "C" int dv3_adam_clip_step(float* p, const float* g, float* m, float* v, 
   adam_prepare_kernel<<<1, 256, 0, st>>>(scratch, blocks, clip, lr, beta1, beta2, step, ctl);
   DV3_CHECK_LAUNCH("adam_prepare_kernel");
   adam_update_kernel<<<blocks, OP_THREADS, 0, st>>>(p, g, m, v, n4, beta1, beta2, eps, decay_mul,
-                                                    ctl);
+                                                    ctl, hi, lo);
   DV3_CHECK_LAUNCH("adam_update_kernel");
   return 0;
+}
+
+extern "C" int dv3_adam_clip_step(float* p, const float* g, float* m, float* v, long long n,
+                                  float lr, float beta1, float beta2, float eps, float clip,
+                                  float decay_mul, float* step, float* ctl, float* scratch,
+                                  void* stream) {
+  return adam_clip_step_any(p, g, m, v, n, lr, beta1, beta2, eps, clip, decay_mul, step, ctl,
+                            scratch, nullptr, nullptr, stream);
+}
+
+extern "C" int dv3_adam_clip_step_planes(float* p, const float* g, float* m, float* v, long long n,
+                                         float lr, float beta1, float beta2, float eps, float clip,
+                                         float decay_mul, float* step, float* ctl, float* scratch,
+                                         float* hi, float* lo, void* stream) {
+  DV3_REQUIRE(hi && lo, DV3_ERR_NULL, "adam_clip_step_planes: null plane buffer");
+  return adam_clip_step_any(p, g, m, v, n, lr, beta1, beta2, eps, clip, decay_mul, step, ctl,
+                            scratch, hi, lo, stream);
 }

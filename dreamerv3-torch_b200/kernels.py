@@ -344,6 +344,9 @@ def split_param(w):
     counter / storage pointer catch load_state_dict and re-assignment."""
     if not isinstance(w, torch.nn.Parameter):
         return split(w.detach())
+    flat = getattr(w, "_dv3_flat_split", None)
+    if flat is not None and flat[0] == (w._version, w.data_ptr()):
+        return flat[1]          # planes written by the fused Adam step that wrote the weight
     tag = (_WEIGHT_EPOCH[0], w._version, w.data_ptr(), tuple(w.shape))
     hit = getattr(w, "_dv3_split", None)
     if hit is not None and hit[0] == tag:

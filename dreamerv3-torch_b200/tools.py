@@ -429,6 +429,13 @@ class Optimizer:
                 p.data = view
                 p.grad = None
         self._gviews = self._views(self._fg)
+        # tf32 operand planes of the parameters, written by the Adam kernel itself: matrices whose
+        # row length is a multiple of 4 read them directly as GEMM operands (kernels.split_param)
+        self._fhi, self._flo = z(), z()
+        self._plane_views = []
+        for p, h, l in zip(self._params, self._views(self._fhi), self._views(self._flo)):
+            ok = p.dim() == 2 and p.shape[1] % 4 == 0 and p.shape[0] * p.shape[1] >= 4096
+            self._plane_views.append(K.Split(h, l, p.shape[0], p.shape[1]) if ok else None)
 
     def _views(self, flat):
         return [flat[off:off + p.numel()].view(p.shape) for p, off in zip(self._params, self._offsets)]
@@ -521,18 +528,22 @@ class Optimizer:
         if self._sync is not None:
             self._sync.flat(self._fg)
         L_ = K.L
-        L_.check(L_.lib().dv3_adam_clip_step(
+        L_.check(L_.lib().dv3_adam_clip_step_planes(
             L_.fptr(self._fp), L_.fptr(self._fg), L_.fptr(self._fm), L_.fptr(self._fv),
             self._fp.numel(), self._lr, self.BETAS[0], self.BETAS[1], self._eps,
             float(self._clip) if self._clip else 0.0, 1.0 - float(self._wd) if self._wd else 1.0,
-            L_.fptr(self._step), L_.fptr(self._ctl), L_.fptr(self._scratch), L_.stream_ptr()),
-            "adam_clip_step")
+            L_.fptr(self._step), L_.fptr(self._ctl), L_.fptr(self._scratch), L_.fptr(self._fhi),
+            L_.fptr(self._flo), L_.stream_ptr()), "adam_clip_step_planes")
         if keep is not None:
             with torch.no_grad():
                 for p_, p0, m_, m0, v_, v0 in keep:
                     p_.copy_(p0)
                     m_.copy_(m0)
                     v_.copy_(v0)
+        skip = set(skipped)
+        for i, (p, sp) in enumerate(zip(params, self._plane_views)):
+            if sp is not None:
+                p._dv3_flat_split = None if i in skip else ((p._version, p.data_ptr()), sp)
         K.invalidate_weight_splits()
         metrics[f"{self._name}_grad_norm"] = self._ctl[0].clone()
         return metrics

@@ -440,6 +440,13 @@ int dv3_idx_to_onehot(const int32_t* idx, int32_t M, int32_t S, int32_t C, float
 int dv3_adam_clip_step(float* p, const float* g, float* m, float* v, long long n, float lr,
                        float beta1, float beta2, float eps, float clip, float decay_mul,
                        float* step, float* ctl, float* scratch, void* stream);
+/* The same update, also writing the tf32 hi / lo planes of the updated parameters into flat
+ * buffers of the same layout (hi + lo == p exactly): the operand planes dv3_gemm_tc reads for
+ * every weight of the next step, produced by the pass that writes the weights. */
+int dv3_adam_clip_step_planes(float* p, const float* g, float* m, float* v, long long n, float lr,
+                              float beta1, float beta2, float eps, float clip, float decay_mul,
+                              float* step, float* ctl, float* scratch, float* hi, float* lo,
+                              void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Step tail: the element-wise / reduction chains around the rollouts, one launch each

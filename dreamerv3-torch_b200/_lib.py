@@ -166,6 +166,8 @@ SIGNATURES = {
                                      _f, _f, _f, _v]),
     "dv3_adam_clip_step_planes": (C.c_int, [_f, _f, _f, _f, C.c_longlong, _f32, _f32, _f32, _f32, _f32,
                                             _f32, _f, _f, _f, _f, _f, _v]),
+    "dv3_im2col_s2k4": (C.c_int, [_f, _i32, _i32, _i32, _i32, _f, _f, _f, _v]),
+    "dv3_col2im_s2k4": (C.c_int, [_f, _i32, _i32, _i32, _i32, _f, _f32, _f, _v]),
     "dv3_debug_observe_timing": (C.c_int, [_P(C.c_ulonglong), _i32]),
     "dv3_ln_silu_fwd_split": (C.c_int, [_f, _i32, _f, _f, _f32, _i32, _i32, _f, _i32, _f, _f, _i32,
                                         _v]),

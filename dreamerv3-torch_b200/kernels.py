@@ -1278,3 +1278,159 @@ def ema_mix(dst_flat, src_flat, mix):
     """dst = mix * src + (1 - mix) * dst over flat fp32 buffers (slow critic, models.py:683-689)."""
     L.check(L.lib().dv3_ema_mix(L.fptr(dst_flat), L.fptr(src_flat), dst_flat.numel(), float(mix),
                                 L.stream_ptr()), "ema_mix")
+
+
+# --------------------------------------------------------------------------------------
+# 4x4 stride-2 conv / transposed conv blocks of the image encoder / decoder (dv3_conv.cu)
+# --------------------------------------------------------------------------------------
+def im2col_split(x2d, n, H, W, Cc):
+    """x2d: [n*H*W, C] channels-last -> Split of the patch matrix [n*H/2*W/2, 16*C]."""
+    rows, cols = n * (H // 2) * (W // 2), 16 * Cc
+    hi = torch.empty(rows, cols, dtype=torch.float32, device=x2d.device)
+    lo = torch.empty(rows, cols, dtype=torch.float32, device=x2d.device)
+    L.check(L.lib().dv3_im2col_s2k4(L.fptr(x2d), n, H, W, Cc, None, L.fptr(hi), L.fptr(lo),
+                                    L.stream_ptr()), "im2col_s2k4")
+    return Split(hi, lo, rows, cols)
+
+
+def col2im(cols2d, n, H, W, Cc, bias=None, shift=0.0):
+    """cols2d [n*H/2*W/2, 16*C] -> [n*H*W, C] (adjoint of the patch gather) + bias + shift."""
+    out = torch.empty(n * H * W, Cc, dtype=torch.float32, device=cols2d.device)
+    L.check(L.lib().dv3_col2im_s2k4(L.fptr(cols2d), n, H, W, Cc, L.fptr(bias), float(shift),
+                                    L.fptr(out), L.stream_ptr()), "col2im_s2k4")
+    return out
+
+
+def _conv_w2(W):
+    """Conv2d weight [Cout,Cin,4,4] -> [Cout, (ky,kx,ci)]; ConvTranspose2d weight [Cin,Cout,4,4] ->
+    [Cin, (ky,kx,co)]: the same permutation.  Cached per weight epoch like split_param."""
+    tag = (_WEIGHT_EPOCH[0], W._version, W.data_ptr(), tuple(W.shape))
+    hit = getattr(W, "_dv3_w2", None)
+    if hit is not None and hit[0] == tag:
+        return hit[1]
+    w2 = W.detach().permute(0, 2, 3, 1).reshape(W.shape[0], 16 * W.shape[1]).contiguous()
+    sp = split(w2)
+    W._dv3_w2 = (tag, sp)
+    return sp
+
+
+def _w2_grad_to_param(dW2, shape):
+    """[A, (ky,kx,b)] -> [A, b, 4, 4] (view)."""
+    return dW2.view(shape[0], 4, 4, shape[1]).permute(0, 3, 1, 2)
+
+
+def _sink_w2(pid, dW2, shape):
+    """Add a permuted conv-weight gradient into the armed sink; False if there is none."""
+    view = _sink_of(pid)
+    if view is None:
+        return False
+    view.add_(_w2_grad_to_param(dW2, shape))
+    _SINK_DIRTY.add(pid)
+    return True
+
+
+class _ConvLnSilu(torch.autograd.Function):
+    """Conv2dSamePad(k=4, s=2, no bias) -> channel LayerNorm -> SiLU on channels-last rows
+    (reference networks.py:463-487): im2col -> tcgen05 GEMM -> LN/SiLU row kernel."""
+
+    @staticmethod
+    def forward(ctx, x2d, geom, W, g, b, need_dx):
+        n, H, Wd = geom
+        Cout, Cin = W.shape[0], W.shape[1]
+        cols = im2col_split(_f32(x2d), n, H, Wd, Cin)
+        w2 = _conv_w2(W)
+        pre = gemm_tc(cols, w2)                                     # [Mo, Cout]
+        out, osp = ln_silu_fwd(pre, _c(g.detach()), _c(b.detach()), with_split=True)
+        _LAST_OUT_SPLIT[0] = osp
+        ctx.save_for_backward(cols.hi, cols.lo, w2.hi, w2.lo, pre, g.detach(), b.detach())
+        ctx.cfg = (geom, tuple(W.shape), (id(W), id(g), id(b)), need_dx)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        ch, cl, wh, wl, pre, g, b = ctx.saved_tensors
+        (n, H, Wd), wshape, (wid, gid, bid), need_dx = ctx.cfg
+        Cout, Cin = wshape[0], wshape[1]
+        Mo = pre.shape[0]
+        cols, w2 = Split(ch, cl, Mo, 16 * Cin), Split(wh, wl, Cout, 16 * Cin)
+        d_pre, d_ln, ds = ln_silu_bwd(pre, _c(g), _c(b), _f32(d_out), with_split=True)
+        dW = dg = db = dx = None
+        if ctx.needs_input_grad[2]:
+            dW2 = gemm_tc(ds, cols, a_t=True, b_t=True, split_k=True)     # [Cout, 16 Cin]
+            if not _sink_w2(wid, dW2, wshape):
+                dW = _w2_grad_to_param(dW2, wshape)
+        if ctx.needs_input_grad[3] or ctx.needs_input_grad[4]:
+            dg, db = _ln_grads(pre, d_ln, gid, bid)
+        if need_dx and ctx.needs_input_grad[0]:
+            dcols = gemm_tc(ds, w2, b_t=True)                             # [Mo, 16 Cin]
+            dx = col2im(dcols, n, H, Wd, Cin)
+        return dx, None, dW, dg, db, None
+
+
+def conv_ln_silu(x2d, geom, W, g, b, need_dx=True):
+    """-> [n*H/2*W/2, Cout] with its tf32 planes attached (the next block's im2col does not need
+    them, the decoder's first product does)."""
+    out = _ConvLnSilu.apply(x2d, geom, W, g, b, need_dx)
+    osp, _LAST_OUT_SPLIT[0] = _LAST_OUT_SPLIT[0], None
+    return attach_split(out, osp) if osp is not None else out
+
+
+class _DeconvBlock(torch.autograd.Function):
+    """ConvTranspose2d(k=4, s=2, padding=1) [+ bias] [-> channel LayerNorm -> SiLU] on channels-last
+    rows (reference networks.py:533-560): tcgen05 GEMM -> col2im gather -> LN/SiLU row kernel."""
+
+    @staticmethod
+    def forward(ctx, x2d, xs, geom, W, g, b, bias, shift):
+        n, h, w = geom
+        Cin, Cout = W.shape[0], W.shape[1]
+        w2 = _conv_w2(W)                                            # [Cin, (ky,kx,co)]
+        cols = gemm_tc(xs, w2, b_t=True)                            # [Mi, 16 Cout]
+        pre = col2im(cols, n, 2 * h, 2 * w, Cout, None if bias is None else _c(bias.detach()), shift)
+        norm = g is not None
+        if norm:
+            out, osp = ln_silu_fwd(pre, _c(g.detach()), _c(b.detach()), with_split=True)
+            _LAST_OUT_SPLIT[0] = osp
+            ctx.save_for_backward(xs.hi, xs.lo, w2.hi, w2.lo, pre, g.detach(), b.detach())
+        else:
+            out = pre
+            ctx.save_for_backward(xs.hi, xs.lo, w2.hi, w2.lo)
+        ctx.cfg = (geom, tuple(W.shape), (id(W), id(g) if norm else None, id(b) if norm else None,
+                                          id(bias) if bias is not None else None), norm,
+                   (xs.rows, xs.cols))
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        (n, h, w), wshape, (wid, gid, bid, biasid), norm, (Mi, Kx) = ctx.cfg
+        Cin, Cout = wshape[0], wshape[1]
+        if norm:
+            xh, xl, wh, wl, pre, g, b = ctx.saved_tensors
+            d_pre, d_ln = ln_silu_bwd(pre, _c(g), _c(b), _f32(d_out))
+        else:
+            xh, xl, wh, wl = ctx.saved_tensors
+            d_pre = _c(_f32(d_out)).reshape(n * 4 * h * w, Cout)
+        xs, w2 = Split(xh, xl, Mi, Kx), Split(wh, wl, Cin, 16 * Cout)
+        dcols = im2col_split(d_pre, n, 2 * h, 2 * w, Cout)          # [Mi, 16 Cout]
+        dx = dW = dg = db = dbias = None
+        if ctx.needs_input_grad[0]:
+            dx = gemm_tc(dcols, w2)                                 # [Mi, Cin]
+        if ctx.needs_input_grad[3]:
+            dW2 = gemm_tc(xs, dcols, a_t=True, b_t=True, split_k=True)    # [Cin, 16 Cout]
+            if not _sink_w2(wid, dW2, wshape):
+                dW = _w2_grad_to_param(dW2, wshape)
+        if norm and (ctx.needs_input_grad[4] or ctx.needs_input_grad[5]):
+            dg, db = _ln_grads(pre, d_ln, gid, bid)
+        if biasid is not None and ctx.needs_input_grad[6]:
+            dbias = _bias_grad(d_pre, biasid)
+        return dx, None, None, dW, dg, db, dbias, None
+
+
+def deconv_block(x2d, geom, W, g=None, b=None, bias=None, shift=0.0):
+    """x2d [n*h*w, Cin] -> [n*2h*2w, Cout]."""
+    x2 = _f32(x2d)
+    out = _DeconvBlock.apply(x2, split_of(x2, x2d), geom, W, g, b, bias, float(shift))
+    if g is not None:
+        osp, _LAST_OUT_SPLIT[0] = _LAST_OUT_SPLIT[0], None
+        if osp is not None:
+            attach_split(out, osp)
+    return out

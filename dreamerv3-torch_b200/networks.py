@@ -3,8 +3,9 @@ names, dict keys and ``state_dict`` names, so reference checkpoints load unchang
 
 ``RSSM.observe`` / ``imagine_with_action`` / ``obs_step`` / ``img_step`` / ``kl_loss`` run on
 the sm_100a kernels of libdv3_b200.so; there is no PyTorch fallback for them.  The batched
-encoder / decoder / head MLPs around the rollout are "next" rows of the scope table and stay
-on torch ops (cuBLAS / cuDNN) in this version.
+encoder / decoder / head MLPs and the 4x4 stride-2 conv / transposed-conv stacks of the image
+encoder / decoder run on the same tcgen05 GEMM + row kernels (CPU tensors and other conv
+geometries fall back to torch ops).
 
 Reference lines: RSSM networks.py:13-290, GRUCell 742-768, MLP 588-739, MultiEncoder /
 MultiDecoder 293-441, ConvEncoder / ConvDecoder 444-585, Conv2dSamePad / ImgChLayerNorm 771-810.
@@ -366,8 +367,39 @@ class ConvEncoder(nn.Module):
         self.layers = nn.Sequential(*mods)
         self.layers.apply(tools.weight_init)
 
+    def _blocks(self):
+        """[(conv, norm)] when the stack is the one the kernels implement: 4x4 stride-2 'same'
+        convolutions without bias, each followed by channel LayerNorm and SiLU."""
+        mods = list(self.layers)
+        if len(mods) % 3:
+            return None
+        out = []
+        for i in range(0, len(mods), 3):
+            conv, norm, act = mods[i:i + 3]
+            if not (isinstance(conv, Conv2dSamePad) and isinstance(norm, ImgChLayerNorm)
+                    and isinstance(act, nn.SiLU) and conv.kernel_size == (4, 4)
+                    and conv.stride == (2, 2) and conv.bias is None and conv.dilation == (1, 1)):
+                return None
+            out.append((conv, norm))
+        return out
+
     def forward(self, obs):
         lead = obs.shape[:-3]
+        h, w, c = obs.shape[-3:]
+        if not obs.is_cuda:
+            raise L.Dv3Error("ConvEncoder forward needs CUDA tensors: the B200 path has no CPU fallback")
+        blocks = self._blocks()
+        if blocks is not None and h % (1 << len(blocks)) == 0 and w % (1 << len(blocks)) == 0:
+            # channels-last rows [n*h*w, c]: every stage is im2col -> tcgen05 GEMM -> LN/SiLU rows
+            n = int(np.prod(lead)) if len(lead) else 1
+            x = (obs - 0.5).reshape(n * h * w, c)
+            for i, (conv, norm) in enumerate(blocks):
+                x = K.conv_ln_silu(x, (n, h, w), conv.weight, norm.norm.weight, norm.norm.bias,
+                                   need_dx=i > 0)
+                h, w = h // 2, w // 2
+            # the reference flattens NCHW: (c, y, x) order
+            x = x.view(n, h * w, x.shape[1]).transpose(1, 2)
+            return x.reshape(list(lead) + [-1])
         x = (obs - 0.5).reshape((-1,) + tuple(obs.shape[-3:])).permute(0, 3, 1, 2)
         x = self.layers(x)
         return x.reshape(list(lead) + [-1])
@@ -402,7 +434,49 @@ class ConvDecoder(nn.Module):
         mods[-1].apply(tools.uniform_weight_init(outscale))
         self.layers = nn.Sequential(*mods)
 
+    def _blocks(self):
+        """[(deconv, norm | None)] when the stack is the one the kernels implement: 4x4 stride-2
+        padding-1 transposed convolutions, channel LayerNorm + SiLU between them, bias on the last."""
+        mods = list(self.layers)
+        out, i = [], 0
+        while i < len(mods):
+            dc = mods[i]
+            if not (isinstance(dc, nn.ConvTranspose2d) and dc.kernel_size == (4, 4)
+                    and dc.stride == (2, 2) and dc.padding == (1, 1) and dc.output_padding == (0, 0)
+                    and dc.dilation == (1, 1) and dc.groups == 1):
+                return None
+            if i + 2 < len(mods) and isinstance(mods[i + 1], ImgChLayerNorm) \
+                    and isinstance(mods[i + 2], nn.SiLU) and dc.bias is None:
+                out.append((dc, mods[i + 1]))
+                i += 3
+            elif i == len(mods) - 1:
+                out.append((dc, None))
+                i += 1
+            else:
+                return None
+        return out
+
     def forward(self, features, dtype=None):
+        if not features.is_cuda:
+            raise L.Dv3Error("ConvDecoder forward needs CUDA tensors: the B200 path has no CPU fallback")
+        blocks = self._blocks()
+        if blocks is not None:
+            # the Linear output viewed [n, minres, minres, C] is already channels-last rows
+            x = K.linear_bias(features, self._linear_layer.weight, self._linear_layer.bias)
+            ch = self._embed_size // self._minres ** 2
+            n = x.numel() // self._embed_size
+            h = w = self._minres
+            x = x.reshape(n * h * w, ch)
+            for dc, norm in blocks:
+                if norm is not None:
+                    x = K.deconv_block(x, (n, h, w), dc.weight, norm.norm.weight, norm.norm.bias)
+                else:
+                    x = K.deconv_block(x, (n, h, w), dc.weight, bias=dc.bias,
+                                       shift=0.0 if self._cnn_sigmoid else 0.5)
+                h, w = 2 * h, 2 * w
+            # rows are (n, y, x) with the channels last: the reference's permuted output
+            mean = x.reshape(tuple(features.shape[:-1]) + (h, w, self._shape[0]))
+            return torch.sigmoid(mean) if self._cnn_sigmoid else mean
         x = self._linear_layer(features)
         x = x.reshape(-1, self._minres, self._minres, self._embed_size // self._minres ** 2)
         x = self.layers(x.permute(0, 3, 1, 2))

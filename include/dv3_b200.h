@@ -521,6 +521,20 @@ int dv3_tensorstats(const float* x, long long n, float* out4, void* stream);
 /* slow-critic update (models.py:683-689) over flat buffers: dst = mix * src + (1 - mix) * dst */
 int dv3_ema_mix(float* dst, const float* src, long long n, double mix, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * 4x4 stride-2 convolution / transposed convolution as GEMMs (dv3_conv.cu): the image encoder /
+ * decoder of reference networks.py:448-585 on channels-last [pixels, C] matrices.
+ * im2col: x [n,H,W,C] -> cols [n*H/2*W/2, 16*C], column (ky*4+kx)*C + c = x[n, 2oy-1+ky, 2ox-1+kx, c]
+ * (zero outside): the patch matrix of Conv2dSamePad(k=4, s=2) (networks.py:771-799), written as fp32
+ * (cols, optional) and / or as the tf32 hi / lo planes dv3_gemm_tc reads.
+ * col2im: the adjoint (ConvTranspose2d(k=4, s=2, padding=1), networks.py:533-556): out [n,H,W,C] from
+ * cols [n*H/2*W/2, 16*C], gathered (deterministic), plus bias[c] (optional) and a constant shift.
+ * ---------------------------------------------------------------------------------------- */
+int dv3_im2col_s2k4(const float* x, int32_t n, int32_t H, int32_t W, int32_t C, float* cols, float* hi,
+                    float* lo, void* stream);
+int dv3_col2im_s2k4(const float* cols, int32_t n, int32_t H, int32_t W, int32_t C, const float* bias,
+                    float shift, float* out, void* stream);
+
 /* Debug aid: with DV3_OBSERVE_TIMING=1 in the environment the persistent observe kernel stamps
  * %globaltimer (ns) at its 8 phase boundaries per step on CTA 0; this copies [T][8] stamps out. */
 int dv3_debug_observe_timing(unsigned long long* host, int32_t T);

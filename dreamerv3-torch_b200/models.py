@@ -143,6 +143,15 @@ class WorldModel(nn.Module):
                     logps[key] = lp
         for st in streams:
             main.wait_stream(st)
+        if streams and self._model_opt._sync is not None:
+            # data parallel: each head's slice of the flat gradient is all-reduced on the head's
+            # stream, overlapping the rest of the backward pass
+            segs = []
+            for i, head in enumerate(self.heads.values()):
+                rng = self._model_opt.param_range(list(head.parameters()))
+                if rng is not None:
+                    segs.append((rng[0], rng[1], streams[i]))
+            self._model_opt.set_segments(segs or None)
         # model_loss = mean(sum_k scale_k * (-log_prob_k) + kl_loss) (reference models.py:140-152)
         names = list(logps)
         if embed.is_cuda and len(names) < 8:

@@ -319,13 +319,40 @@ class GradSync:
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
 
-    def flat(self, flat_grad):
-        """Average one flat gradient buffer in place (tools.Optimizer's CUDA path)."""
+    def _avg(self, t):
+        import torch.distributed as dist
+        if dist.get_backend(self.group) == "nccl":
+            dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.group)     # no divide pass
+        else:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            t.div_(self.world)
+
+    def flat(self, flat_grad, segments=None):
+        """Average one flat gradient buffer in place (tools.Optimizer's CUDA path).
+
+        ``segments`` = [(start, end, stream)]: ranges of the buffer whose gradients were produced
+        on a side stream (the world model's heads run their backward on their own streams).  Each
+        is all-reduced on that stream, i.e. as soon as its producer branch is done and
+        concurrently with the rest of the backward pass (the persistent observe backward); the
+        remainder follows on the current stream.  Every rank issues the collectives in the same
+        order."""
         if self.world == 1:
             return
-        import torch.distributed as dist
-        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=self.group)
-        flat_grad.div_(self.world)
+        if not segments:
+            self._avg(flat_grad)
+            return
+        cur = torch.cuda.current_stream()
+        segs = sorted(segments, key=lambda s: s[0])
+        for a, b, st in segs:
+            with torch.cuda.stream(st):
+                self._avg(flat_grad[a:b])
+        pos = 0
+        for a, b, _ in segs + [(flat_grad.numel(), flat_grad.numel(), None)]:
+            if a > pos:
+                self._avg(flat_grad[pos:a])
+            pos = max(pos, b)
+        for _, _, st in segs:
+            cur.wait_stream(st)
 
     def __call__(self, params):
         if self.world == 1:
@@ -443,6 +470,22 @@ class Optimizer:
     def set_grad_sync(self, sync):
         self._sync = sync
 
+    def param_range(self, params):
+        """[start, end) of the flat buffers covered by ``params`` (a contiguous run of this
+        optimizer's parameters), or None."""
+        if not self._flat:
+            return None
+        index = {id(p): i for i, p in enumerate(self._params)}
+        ids = sorted(index[id(p)] for p in params if id(p) in index)
+        if not ids or ids != list(range(ids[0], ids[-1] + 1)):
+            return None
+        last = self._params[ids[-1]]
+        return self._offsets[ids[0]], self._offsets[ids[-1]] + ((last.numel() + 3) & ~3)
+
+    def set_segments(self, segments):
+        """[(start, end, stream)] for GradSync.flat; None = one collective over the whole buffer."""
+        self._segments = segments
+
     def state_dict(self):
         """torch.optim.Adam's layout (what the reference checkpoints, dreamer.py:502-506)."""
         return self._opt.state_dict()
@@ -526,7 +569,7 @@ class Optimizer:
             pv, mv, vv = self._views(self._fp), self._views(self._fm), self._views(self._fv)
             keep = [(pv[i], pv[i].clone(), mv[i], mv[i].clone(), vv[i], vv[i].clone()) for i in skipped]
         if self._sync is not None:
-            self._sync.flat(self._fg)
+            self._sync.flat(self._fg, getattr(self, "_segments", None))
         L_ = K.L
         L_.check(L_.lib().dv3_adam_clip_step_planes(
             L_.fptr(self._fp), L_.fptr(self._fg), L_.fptr(self._fm), L_.fptr(self._fv),

@@ -199,6 +199,10 @@ SIGNATURES = {
     "dv3_value_loss_bwd": (C.c_int, [_f, _f, _i32, _f, _v]),
     "dv3_normal_policy_fwd": (C.c_int, [_f, _f, _f, _f32, _f32, _i32, _i32, _f, _f, _v]),
     "dv3_normal_policy_bwd": (C.c_int, [_f, _f, _f, _f, _f, _f32, _f32, _i32, _i32, _f, _f, _f, _v]),
+    "dv3_rssm_initial_bwd_scratch_floats": (C.c_size_t, [_P(RssmDims)]),
+    "dv3_rssm_initial_bwd": (C.c_int, [_P(RssmDims), _P(RssmParams), _f, _f, _f, _f, _f, _f, _f, _f, _f, _f,
+                                       _f, _f, _f, _v]),
+    "dv3_col_sum": (C.c_int, [_f, _i32, _i32, _i32, _f, _i32, _v]),
     "dv3_tensorstats": (C.c_int, [_f, C.c_longlong, _f, _v]),
     "dv3_ema_mix": (C.c_int, [_f, _f, C.c_longlong, _dbl, _v]),
 }

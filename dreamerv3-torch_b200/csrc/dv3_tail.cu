@@ -438,6 +438,27 @@ __global__ void ema_mix_kernel(float* __restrict__ dst, const float* __restrict_
   if (i < n) dst[i] = __fadd_rn(__fmul_rn(mix, src[i]), __fmul_rn(one_minus_mix, dst[i]));
 }
 
+// out[j] (+)= sum_r x[r, j]: a Linear bias gradient.  Block = 32 columns x 8 row-strided warps,
+// fixed summation order (deterministic).
+__global__ void __launch_bounds__(256)
+col_sum_kernel(const float* __restrict__ x, int ld, int M, int n, float* __restrict__ out,
+               int accumulate) {
+  __shared__ float part[8][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + lane;
+  float acc = 0.f;
+  if (j < n)
+    for (int r = warp; r < M; r += 8) acc += x[(size_t)r * ld + j];
+  part[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0 && j < n) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += part[w][lane];
+    out[j] = accumulate ? out[j] + s : s;
+  }
+}
+
 static inline int nblk(long long n, int t) { return (int)((n + t - 1) / t); }
 
 }  // namespace dv3
@@ -632,5 +653,167 @@ extern "C" int dv3_ema_mix(float* dst, const float* src, long long n, double mix
   DV3_REQUIRE(dst && src, DV3_ERR_NULL, "ema_mix: null pointer");
   ema_mix_kernel<<<nblk(n, 256), 256, 0, ST>>>(dst, src, n, (float)mix, (float)(1.0 - mix));
   DV3_CHECK_LAUNCH("ema_mix_kernel");
+  return 0;
+}
+
+extern "C" int dv3_col_sum(const float* x, int32_t ld, int32_t M, int32_t n, float* out,
+                           int32_t accumulate, void* stream) {
+  DV3_REQUIRE(x && out && n > 0 && M >= 0 && ld >= n, DV3_ERR_NULL, "col_sum: null pointer / M=%d n=%d ld=%d",
+              M, n, ld);
+  col_sum_kernel<<<nblk(n, 32), 256, 0, ST>>>(x, ld, M, n, out, accumulate);
+  DV3_CHECK_LAUNCH("col_sum_kernel");
+  return 0;
+}
+
+// ---- backward of RSSM.initial (networks.py:99-125), one row ----------------------------------------
+//   deter0 = tanh(W);  y0 = SiLU(LN(W_out deter0));  lg = W_ims y0 + b_ims;  norm = unimix log-probs
+// upstream: g_norm [S*C] (gradient reaching the straight-through mode's log-probs), g_deter0 [D].
+// One CTA: lane = class for the categorical chain, then the two GEMVs and the LayerNorm backward.
+// Outputs: d_lg [S*C] (= d b_ims), d_ypre [Hd], d_ln [Hd] (LN affine-output gradient), xhat [Hd],
+// d_w_init [D]; the two rank-1 weight gradients follow in rank1_add_kernel.
+namespace dv3 {
+
+__global__ void __launch_bounds__(1024)
+rssm_initial_bwd_kernel(const float* __restrict__ init_deter, const float* __restrict__ init_ypre,
+                        const float* __restrict__ init_logit, const float* __restrict__ w_out,
+                        const float* __restrict__ ln_g, const float* __restrict__ ln_b,
+                        const float* __restrict__ w_ims, const float* __restrict__ g_norm,
+                        const float* __restrict__ g_deter0, int S, int C, int D, int Hd, float unimix,
+                        float eps, float* __restrict__ d_lg, float* __restrict__ d_ypre,
+                        float* __restrict__ d_ln, float* __restrict__ xhat_out,
+                        float* __restrict__ d_w_init) {
+  extern __shared__ float sm[];
+  float* s_dlg = sm;                 // [S*C]
+  float* s_v = s_dlg + S * C;        // [Hd] scratch (d_y0, then d_ypre)
+  __shared__ float red[4 * 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  // 1. categorical chain, one warp per group
+  for (int s = warp; s < S; s += nw) {
+    const bool valid = lane < C;
+    const float l = valid ? init_logit[s * C + lane] : 0.f;
+    const Unimix um = unimix_probs(l, valid, C, unimix);
+    const float g = valid ? g_norm[s * C + lane] : 0.f;
+    // norm = l' - lse(l'):  d l'_k = g_k - softmax(l')_k sum(g)
+    const float gs = warp_sum(g);
+    float dl = g - um.probs * gs;
+    if (unimix > 0.f) {
+      // l' = log(q), q = (1-u) p + u/C, p = softmax(l)
+      const float q = um.p * (1.f - unimix) + unimix / (float)C;
+      const float dp = valid ? (1.f - unimix) * dl / q : 0.f;
+      const float dot = warp_sum(valid ? um.p * dp : 0.f);
+      dl = um.p * (dp - dot);
+    }
+    if (valid) { s_dlg[s * C + lane] = dl; d_lg[s * C + lane] = dl; }
+  }
+  __syncthreads();
+  // 2. d_y0[j] = sum_sc d_lg[sc] W_ims[sc, j]
+  const int SC = S * C;
+  for (int j = tid; j < Hd; j += blockDim.x) {
+    float a = 0.f;
+    for (int sc = 0; sc < SC; ++sc) a = fmaf(s_dlg[sc], w_ims[(size_t)sc * Hd + j], a);
+    s_v[j] = a;
+  }
+  __syncthreads();
+  // 3. LayerNorm + SiLU backward of the row
+  float acc[1] = {0.f};
+  for (int j = tid; j < Hd; j += blockDim.x) acc[0] += init_ypre[j];
+  block_sum<1>(acc, red);
+  const float mean = acc[0] / (float)Hd;
+  float q2[1] = {0.f};
+  for (int j = tid; j < Hd; j += blockDim.x) { const float d = init_ypre[j] - mean; q2[0] = fmaf(d, d, q2[0]); }
+  block_sum<1>(q2, red);
+  const float rstd = 1.f / sqrtf(q2[0] / (float)Hd + eps);
+  float m[2] = {0.f, 0.f};
+  for (int j = tid; j < Hd; j += blockDim.x) {
+    const float xh = (init_ypre[j] - mean) * rstd;
+    const float v = fmaf(xh, ln_g[j], ln_b[j]);
+    const float dv = s_v[j] * silu_grad(v);
+    d_ln[j] = dv;
+    xhat_out[j] = xh;
+    const float dx = dv * ln_g[j];
+    m[0] += dx;
+    m[1] = fmaf(dx, xh, m[1]);
+  }
+  block_sum<2>(m, red);
+  const float m1 = m[0] / (float)Hd, m2 = m[1] / (float)Hd;
+  for (int j = tid; j < Hd; j += blockDim.x) {
+    const float xh = (init_ypre[j] - mean) * rstd;
+    const float dp = rstd * (d_ln[j] * ln_g[j] - m1 - xh * m2);
+    s_v[j] = dp;
+    d_ypre[j] = dp;
+  }
+  __syncthreads();
+  // 4. d_deter0[k] = sum_j d_ypre[j] W_out[j, k] + g_deter0[k];  d W = d_deter0 (1 - deter0^2)
+  for (int k = tid; k < D; k += blockDim.x) {
+    float a = g_deter0 ? g_deter0[k] : 0.f;
+    for (int j = 0; j < Hd; ++j) a = fmaf(s_v[j], w_out[(size_t)j * D + k], a);
+    const float t = init_deter[k];
+    d_w_init[k] = a * (1.f - t * t);
+  }
+}
+
+// out[i, j] += a[i] * b[j]
+__global__ void rank1_add_kernel(const float* __restrict__ a, const float* __restrict__ b, int M, int N,
+                                 float* __restrict__ out, int ld) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long long)M * N) return;
+  const int i = (int)(e / N), j = (int)(e % N);
+  out[(size_t)i * ld + j] += a[i] * b[j];
+}
+
+// the vector gradients of the initial path, added onto the caller's buffers in one launch
+__global__ void initial_vec_add_kernel(const float* __restrict__ d_lg, const float* __restrict__ d_ln,
+                                       const float* __restrict__ xhat, const float* __restrict__ dw,
+                                       int SC, int Hd, int D, float* __restrict__ d_b_ims,
+                                       float* __restrict__ d_ln_g, float* __restrict__ d_ln_b,
+                                       float* __restrict__ d_w_init) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < SC) { d_b_ims[i] += d_lg[i]; return; }
+  i -= SC;
+  if (i < Hd) { d_ln_g[i] += d_ln[i] * xhat[i]; return; }
+  i -= Hd;
+  if (i < Hd) { d_ln_b[i] += d_ln[i]; return; }
+  i -= Hd;
+  if (i < D) d_w_init[i] += dw[i];
+}
+
+}  // namespace dv3
+
+extern "C" size_t dv3_rssm_initial_bwd_scratch_floats(const dv3_rssm_dims* d) {
+  if (!d) return 0;
+  return (size_t)d->stoch * d->classes + 3 * (size_t)d->hidden + d->deter;
+}
+
+extern "C" int dv3_rssm_initial_bwd(const dv3_rssm_dims* d, const dv3_rssm_params* p,
+                                    const float* init_deter, const float* init_ypre,
+                                    const float* init_y, const float* init_logit, const float* g_norm,
+                                    const float* g_deter0, float* d_w_init, float* d_w_out,
+                                    float* d_ln_out_g, float* d_ln_out_b, float* d_w_ims,
+                                    float* d_b_ims, float* scratch, void* stream) {
+  DV3_REQUIRE(d && p && init_deter && init_ypre && init_y && init_logit && g_norm && d_w_init &&
+                  d_w_out && d_ln_out_g && d_ln_out_b && d_w_ims && d_b_ims && scratch,
+              DV3_ERR_NULL, "rssm_initial_bwd: null pointer");
+  const int S = d->stoch, C = d->classes, SC = S * C, D = d->deter, Hd = d->hidden;
+  DV3_REQUIRE(C <= 32, DV3_ERR_BAD_SHAPE, "rssm_initial_bwd: classes=%d > 32", C);
+  // scratch: d_lg [SC] | d_ypre [Hd] | d_ln [Hd] | xhat [Hd] | d_w_init [D]
+  float* s_dlg = scratch;
+  float* s_dyp = s_dlg + SC;
+  float* s_dln = s_dyp + Hd;
+  float* s_xh = s_dln + Hd;
+  float* s_dw = s_xh + Hd;
+  const size_t smem = (size_t)(SC + Hd) * 4;
+  DV3_REQUIRE(smem <= 48 * 1024, DV3_ERR_BAD_SHAPE, "rssm_initial_bwd: S*C + Hd = %d too large", SC + Hd);
+  rssm_initial_bwd_kernel<<<1, 1024, smem, ST>>>(init_deter, init_ypre, init_logit, p->w_out, p->ln_out_g,
+                                                 p->ln_out_b, p->w_ims, g_norm, g_deter0, S, C, D, Hd,
+                                                 d->unimix, d->ln_eps, s_dlg, s_dyp, s_dln, s_xh, s_dw);
+  DV3_CHECK_LAUNCH("rssm_initial_bwd_kernel");
+  // all outputs are ADDED onto the caller's buffers (which hold the bulk contributions, or zeros)
+  rank1_add_kernel<<<nblk((long long)SC * Hd, 256), 256, 0, ST>>>(s_dlg, init_y, SC, Hd, d_w_ims, Hd);
+  DV3_CHECK_LAUNCH("rank1_add_kernel");
+  rank1_add_kernel<<<nblk((long long)Hd * D, 256), 256, 0, ST>>>(s_dyp, init_deter, Hd, D, d_w_out, D);
+  DV3_CHECK_LAUNCH("rank1_add_kernel");
+  initial_vec_add_kernel<<<nblk(SC + 2 * Hd + D, 256), 256, 0, ST>>>(s_dlg, s_dln, s_xh, s_dw, SC, Hd, D,
+                                                                    d_b_ims, d_ln_out_g, d_ln_out_b, d_w_init);
+  DV3_CHECK_LAUNCH("initial_vec_add_kernel");
   return 0;
 }

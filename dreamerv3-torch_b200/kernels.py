@@ -598,9 +598,27 @@ def _ln_grads(pre2d, d_ln2d, gid=None, bid=None):
     return dg, db
 
 
+def col_sum(d2d, out=None, accumulate=False):
+    """out[j] (+)= sum_r d2d[r, j] (fixed order)."""
+    M, n = d2d.shape
+    if d2d.stride(1) != 1:
+        d2d = d2d.contiguous()
+    if out is None:
+        out = torch.empty(n, dtype=torch.float32, device=d2d.device)
+    L.check(L.lib().dv3_col_sum(_raw(d2d), d2d.stride(0), M, n, L.fptr(out), int(accumulate),
+                                L.stream_ptr()), "col_sum")
+    return out
+
+
 def _bias_grad(d2d, pid=None):
-    """Column sums of a delta [M,n] = the gradient of a Linear bias."""
-    return _sink_add(pid, lambda out: torch.sum(d2d, 0, out=out), lambda: d2d.sum(0))
+    """Column sums of a delta [M,n] = the gradient of a Linear bias (into the armed sink, which is
+    pre-zeroed, or as a fresh tensor)."""
+    view = _sink_of(pid)
+    if view is None:
+        return col_sum(d2d)
+    col_sum(d2d, view, accumulate=True)
+    _SINK_DIRTY.add(pid)
+    return None
 
 
 # --------------------------------------------------------------------------------------
@@ -635,6 +653,7 @@ class _Observe(torch.autograd.Function):
     @staticmethod
     def forward(ctx, embed, action, is_first, u_prior, u_post, state_idx, state_deter, dims,
                 *params):
+        ctx.set_materialize_grads(False)     # unused outputs: None, not a zero-filled tensor
         S, Cc, D, Hd, A, E, unimix = dims
         B, T = embed.shape[:2]
         dev = embed.device
@@ -664,7 +683,7 @@ class _Observe(torch.autograd.Function):
         ctx.save_for_backward(embed, o["first_eff"], o["post_logit"], o["prior_logit"],
                               o["hprev"], o["x_pre"], o["g_pre"], o["y_pre"], o["z_pre"],
                               o["sprev_idx"], o["aprev"], o["x"], o["y"], o["z"], o["deter"],
-                              *keep)
+                              o["init_deter"], o["init_ypre"], o["init_y"], o["init_logit"], *keep)
         ctx.mark_non_differentiable(o["aprev"], o["post_idx"], o["prior_idx"])
         return (o["post_stoch"], o["post_logit"], o["prior_stoch"], o["prior_logit"], o["deter"],
                 o["aprev"], o["post_idx"], o["prior_idx"])
@@ -672,7 +691,7 @@ class _Observe(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_post_stoch, g_post_logit, g_prior_stoch, g_prior_logit, g_deter, *_):
         (embed, first_eff, post_logit, prior_logit, hprev, x_pre, g_pre, y_pre, z_pre, sprev_idx,
-         aprev, x, y, z, deter, *params) = ctx.saved_tensors
+         aprev, x, y, z, deter, init_deter, init_ypre, init_y, init_logit, *params) = ctx.saved_tensors
         S, Cc, D, Hd, A, E, unimix = ctx.dims
         B, T = ctx.BT
         dev = embed.device
@@ -747,28 +766,27 @@ class _Observe(torch.autograd.Function):
             dw("w_os", dpos, r2(z))
             bias("b_os", dpo)
             # RSSM.initial (networks.py:99-125): tanh(W) -> prior head -> mode (straight-through
-            # on the normalised log-probs).  One row; differentiated with autograd.
+            # on the normalised log-probs).  One row: dv3_rssm_initial_bwd adds its six parameter
+            # gradients onto the bulk sums (the armed sink views, or the tensors built above).
             names = ["w_init", "w_out", "ln_out_g", "ln_out_b", "w_ims", "b_ims"]
-            with torch.enable_grad():
-                leaf = {k: P[k].detach().requires_grad_(True) for k in names}
-                deter0 = torch.tanh(leaf["w_init"])
-                y0 = F.silu(F.layer_norm(deter0 @ leaf["w_out"].t(), (Hd,), leaf["ln_out_g"],
-                                         leaf["ln_out_b"], LN_EPS))
-                lg = (y0 @ leaf["w_ims"].t() + leaf["b_ims"]).reshape(S, Cc)
-                if unimix > 0:
-                    lg = torch.log(F.softmax(lg, -1) * (1.0 - unimix) + unimix / Cc)
-                norm = lg - torch.logsumexp(lg, -1, keepdim=True)
-                gi = torch.autograd.grad([norm.reshape(-1), deter0.reshape(-1)],
-                                         [leaf[k] for k in names],
-                                         [o["d_init_stoch"], o["d_init_deter"]])
-            for k, g in zip(names, gi):
+            bufs = {}
+            for k in names:
                 view = _sink_of(pid[k])
                 if view is not None:
-                    view.add_(g.reshape(view.shape))
+                    bufs[k] = view
                     _SINK_DIRTY.add(pid[k])
                     G[k] = _SUNK
                 else:
-                    G[k] = g if G[k] is None else G[k] + g
+                    if G[k] is None or G[k] is _SUNK:
+                        G[k] = torch.zeros(P[k].shape, dtype=torch.float32, device=dev)
+                    bufs[k] = G[k]
+            scr = f(int(L.lib().dv3_rssm_initial_bwd_scratch_floats(C.byref(d))))
+            L.check(L.lib().dv3_rssm_initial_bwd(
+                C.byref(d), C.byref(pst), L.fptr(init_deter), L.fptr(init_ypre), L.fptr(init_y),
+                L.fptr(init_logit), L.fptr(o["d_init_stoch"]), L.fptr(o["d_init_deter"]),
+                L.fptr(bufs["w_init"]), L.fptr(bufs["w_out"]), L.fptr(bufs["ln_out_g"]),
+                L.fptr(bufs["ln_out_b"]), L.fptr(bufs["w_ims"]), L.fptr(bufs["b_ims"]), L.fptr(scr),
+                L.stream_ptr()), "rssm_initial_bwd")
         grads = [G[k] if need[k] and G[k] is not _SUNK else None for k in L.RSSM_PARAM_FIELDS]
         d_embed = o["d_embed"] if ctx.needs_input_grad[0] else None
         return (d_embed, None, None, None, None, None, d_state_deter, None, *grads)
@@ -820,6 +838,7 @@ class _Imagine(torch.autograd.Function):
     @staticmethod
     def forward(ctx, start_idx, start_deter, act_noise, u_state, given_action, start_logit, H,
                 dims, spec, *params):
+        ctx.set_materialize_grads(False)     # unused outputs: None, not a zero-filled tensor
         S, Cc, D, Hd, A, E, unimix = dims
         N = start_idx.shape[0]
         dev = start_deter.device
@@ -1105,6 +1124,7 @@ class _DiscountWeights(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, cont_logit, gamma):
+        ctx.set_materialize_grads(False)
         H = cont_logit.shape[0]
         lg = _f32(cont_logit).reshape(H, -1)
         N = lg.shape[1]
@@ -1119,6 +1139,8 @@ class _DiscountWeights(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_disc, _gw):
+        if g_disc is None:
+            return None, None
         (lg,) = ctx.saved_tensors
         gamma, shape = ctx.cfg
         d = torch.empty_like(lg)
@@ -1228,6 +1250,7 @@ class _NormalPolicy(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, mean_raw, std_raw, action, min_std, max_std, want_logp):
+        ctx.set_materialize_grads(False)
         A = mean_raw.shape[-1]
         lead = mean_raw.shape[:-1]
         mr, sr, ac = (_f32(t).reshape(-1, A) for t in (mean_raw, std_raw, action))

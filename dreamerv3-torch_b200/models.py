@@ -178,9 +178,9 @@ class WorldModel(nn.Module):
         metrics["rep_scale"] = cfg.rep_scale
         metrics["dyn_loss"] = aux["dyn_loss"]
         metrics["rep_loss"] = aux["rep_loss"]
-        metrics["kl"] = torch.mean(aux["kl_value"])
-        metrics["prior_ent"] = torch.mean(aux["prior_ent"])
-        metrics["post_ent"] = torch.mean(aux["post_ent"])
+        metrics["kl"] = tools.mean_scalar(aux["kl_value"])
+        metrics["prior_ent"] = tools.mean_scalar(aux["prior_ent"])
+        metrics["post_ent"] = tools.mean_scalar(aux["post_ent"])
         context = dict(embed=aux["embed"], feat=aux["feat"], kl=aux["kl_value"],
                        postent=aux["post_ent"])
         idx = self.dynamics._to_idx(post["stoch"])
@@ -396,7 +396,7 @@ class ImagBehavior(nn.Module):
                                                  "imag_action"))
             else:
                 metrics.update(tools.tensorstats(imag_action, "imag_action"))
-            metrics["actor_entropy"] = torch.mean(actor_ent.detach())
+            metrics["actor_entropy"] = tools.mean_scalar(actor_ent)
         if side is not None:
             main.wait_stream(side)                  # callers continue on the current stream
         aux = dict(reward=reward, target=target, value=value)

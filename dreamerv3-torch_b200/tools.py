@@ -294,6 +294,14 @@ def tensorstats(tensor, prefix=None):
     return {f"{prefix}_{k}" if prefix else k: v for k, v in out.items()}
 
 
+def mean_scalar(x):
+    """Mean of all elements as a 0-dim device tensor (one library kernel on CUDA)."""
+    x = x.detach()
+    if x.is_cuda and x.numel() > 0:
+        return K.tensorstats4(x)[0]
+    return torch.mean(x.float())
+
+
 def to_host(metrics):
     """One device->host transfer for all scalar metrics; arrays go individually."""
     scalars = {k: v for k, v in metrics.items() if torch.is_tensor(v) and v.numel() == 1}

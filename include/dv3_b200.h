@@ -518,6 +518,21 @@ int dv3_normal_policy_bwd(const float* mean_raw, const float* std_raw, const flo
                           void* stream);
 /* tools.tensorstats (tools.py:949-958): out4 = {mean, unbiased std, min, max} of x[n] */
 int dv3_tensorstats(const float* x, long long n, float* out4, void* stream);
+/* Backward of RSSM.initial (networks.py:99-125): deter0 = tanh(W), stoch0 = mode(prior head(deter0))
+ * with straight-through log-probs -- one row, evaluated once per observe call.  init_* are the
+ * intermediates dv3_observe_fwd returned; g_norm [S*C] / g_deter0 [D] are dv3_observe_bwd's
+ * d_init_stoch / d_init_deter.  The six parameter gradients are ADDED onto the given buffers (the
+ * bulk dW sums of the same parameters, or zeros).  scratch: dv3_rssm_initial_bwd_scratch_floats. */
+size_t dv3_rssm_initial_bwd_scratch_floats(const dv3_rssm_dims* d);
+int dv3_rssm_initial_bwd(const dv3_rssm_dims* d, const dv3_rssm_params* p, const float* init_deter,
+                         const float* init_ypre, const float* init_y, const float* init_logit,
+                         const float* g_norm, const float* g_deter0, float* d_w_init, float* d_w_out,
+                         float* d_ln_out_g, float* d_ln_out_b, float* d_w_ims, float* d_b_ims,
+                         float* scratch, void* stream);
+/* out[j] = sum_r x[r,j] (+ out[j] when accumulate != 0): the gradient of a Linear bias from the
+ * deltas of its output rows (autograd of networks.py:640-655); fixed summation order */
+int dv3_col_sum(const float* x, int32_t ld, int32_t M, int32_t n, float* out, int32_t accumulate,
+                void* stream);
 /* slow-critic update (models.py:683-689) over flat buffers: dst = mix * src + (1 - mix) * dst */
 int dv3_ema_mix(float* dst, const float* src, long long n, double mix, void* stream);
 

@@ -438,25 +438,53 @@ __global__ void ema_mix_kernel(float* __restrict__ dst, const float* __restrict_
   if (i < n) dst[i] = __fadd_rn(__fmul_rn(mix, src[i]), __fmul_rn(one_minus_mix, dst[i]));
 }
 
-// out[j] (+)= sum_r x[r, j]: a Linear bias gradient.  Block = 32 columns x 8 row-strided warps,
-// fixed summation order (deterministic).
+// out[j] += sum_r x[r, j]: a Linear bias gradient.  Block = 32 columns x 8 row-strided warps over
+// one chunk of rows; the chunks of a column meet through fp32 atomics (out is pre-zeroed by the
+// caller or by the launcher).
 __global__ void __launch_bounds__(256)
-col_sum_kernel(const float* __restrict__ x, int ld, int M, int n, float* __restrict__ out,
-               int accumulate) {
+col_sum_kernel(const float* __restrict__ x, int ld, int M, int n, int rows_per_block,
+               float* __restrict__ out) {
   __shared__ float part[8][33];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int j = blockIdx.x * 32 + lane;
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
   float acc = 0.f;
   if (j < n)
-    for (int r = warp; r < M; r += 8) acc += x[(size_t)r * ld + j];
+    for (int r = r0 + warp; r < r1; r += 8) acc += x[(size_t)r * ld + j];
   part[warp][lane] = acc;
   __syncthreads();
   if (warp == 0 && j < n) {
     float s = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) s += part[w][lane];
-    out[j] = accumulate ? out[j] + s : s;
+    atomicAdd(out + j, s);
   }
+}
+
+// narrow matrices (n <= 8, e.g. the 3 image channels): one thread strides the flat array, so that
+// the loads stay coalesced; lanes holding the same column meet in shared memory
+__global__ void __launch_bounds__(256)
+col_sum_narrow_kernel(const float* __restrict__ x, long long total, int n, float* __restrict__ out) {
+  __shared__ float part[8];
+  float acc[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int c = (int)(e % n);
+    const float v = x[e];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] += (k == c) ? v : 0.f;
+  }
+  if (threadIdx.x < 8) part[threadIdx.x] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float s = warp_sum(acc[k]);
+    if ((threadIdx.x & 31) == 0 && k < n) atomicAdd(&part[k], s);
+  }
+  __syncthreads();
+  if (threadIdx.x < n) atomicAdd(out + threadIdx.x, part[threadIdx.x]);
 }
 
 static inline int nblk(long long n, int t) { return (int)((n + t - 1) / t); }
@@ -660,7 +688,22 @@ extern "C" int dv3_col_sum(const float* x, int32_t ld, int32_t M, int32_t n, flo
                            int32_t accumulate, void* stream) {
   DV3_REQUIRE(x && out && n > 0 && M >= 0 && ld >= n, DV3_ERR_NULL, "col_sum: null pointer / M=%d n=%d ld=%d",
               M, n, ld);
-  col_sum_kernel<<<nblk(n, 32), 256, 0, ST>>>(x, ld, M, n, out, accumulate);
+  if (!accumulate) DV3_CHECK_CUDA(cudaMemsetAsync(out, 0, (size_t)n * 4, ST));
+  if (M == 0) return 0;
+  if (n <= 8 && ld == n) {
+    const long long total = (long long)M * n;
+    int blocks = nblk(total, 256 * 8);
+    if (blocks > 592) blocks = 592;
+    col_sum_narrow_kernel<<<blocks, 256, 0, ST>>>(x, total, n, out);
+    DV3_CHECK_LAUNCH("col_sum_narrow_kernel");
+    return 0;
+  }
+  const int cb = nblk(n, 32);
+  int rb = (2 * 148 + cb - 1) / cb;                 // about two blocks per SM in total
+  if (rb > (M + 63) / 64) rb = (M + 63) / 64;       // at least 64 rows per block
+  if (rb < 1) rb = 1;
+  const int rpb = (M + rb - 1) / rb;
+  col_sum_kernel<<<dim3(cb, rb), 256, 0, ST>>>(x, ld, M, n, rpb, out);
   DV3_CHECK_LAUNCH("col_sum_kernel");
   return 0;
 }

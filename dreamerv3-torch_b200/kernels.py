@@ -599,7 +599,7 @@ def _ln_grads(pre2d, d_ln2d, gid=None, bid=None):
 
 
 def col_sum(d2d, out=None, accumulate=False):
-    """out[j] (+)= sum_r d2d[r, j] (fixed order)."""
+    """out[j] (+)= sum_r d2d[r, j]."""
     M, n = d2d.shape
     if d2d.stride(1) != 1:
         d2d = d2d.contiguous()

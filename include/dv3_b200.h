@@ -530,7 +530,7 @@ int dv3_rssm_initial_bwd(const dv3_rssm_dims* d, const dv3_rssm_params* p, const
                          float* d_ln_out_g, float* d_ln_out_b, float* d_w_ims, float* d_b_ims,
                          float* scratch, void* stream);
 /* out[j] = sum_r x[r,j] (+ out[j] when accumulate != 0): the gradient of a Linear bias from the
- * deltas of its output rows (autograd of networks.py:640-655); fixed summation order */
+ * deltas of its output rows (autograd of networks.py:640-655); row chunks meet through fp32 atomics */
 int dv3_col_sum(const float* x, int32_t ld, int32_t M, int32_t n, float* out, int32_t accumulate,
                 void* stream);
 /* slow-critic update (models.py:683-689) over flat buffers: dst = mix * src + (1 - mix) * dst */

@@ -47,8 +47,23 @@ RSSM_STATE_KEYS = {
 }
 
 
+class TcOperand(C.Structure):
+    _fields_ = _fields([("hi", "f"), ("lo", "f"), ("ld", "i32"), ("mn_major", "i32")])
+
+
+class RssmPlanes(C.Structure):
+    """dv3_rssm_planes: caller-derived forms of the RSSM weights (made once per optimizer step)."""
+    _fields_ = [("w_gru", TcOperand), ("w_out", TcOperand), ("w_ims", TcOperand), ("w_in_t", _f),
+                ("w_in_t_sp", TcOperand)]
+
+
 class RssmParams(C.Structure):
-    _fields_ = _fields([(n, "f") for n in RSSM_PARAM_FIELDS])
+    _fields_ = _fields([(n, "f") for n in RSSM_PARAM_FIELDS]) + [("planes", C.POINTER(RssmPlanes))]
+
+
+class ActorPlanes(C.Structure):
+    """dv3_actor_planes"""
+    _fields_ = [("w", TcOperand * 16), ("w0_t", _f)]
 
 
 class ObserveIO(C.Structure):
@@ -84,7 +99,8 @@ class Actor(C.Structure):
     _fields_ = _fields([
         ("layers", "i32"), ("units", "i32"), ("dist", "i32"), ("min_std", "f32"),
         ("max_std", "f32"), ("unimix", "f32"), ("w", "pf"), ("ln_g", "pf"), ("ln_b", "pf"),
-        ("w_mean", "f"), ("b_mean", "f"), ("w_std", "f"), ("b_std", "f")])
+        ("w_mean", "f"), ("b_mean", "f"), ("w_std", "f"), ("b_std", "f")]) + [
+        ("planes", C.POINTER(ActorPlanes))]
 
 
 class ImagineIO(C.Structure):
@@ -110,11 +126,8 @@ class ImagineBwdIO(C.Structure):
         ("workspace", "v"), ("workspace_bytes", "sz")])
 
 
-class TcOperand(C.Structure):
-    _fields_ = _fields([("hi", "f"), ("lo", "f"), ("ld", "i32"), ("mn_major", "i32")])
-
-
-STRUCTS = {"dv3_tc_operand": TcOperand, "dv3_rssm_dims": RssmDims, "dv3_rssm_params": RssmParams, "dv3_observe_io": ObserveIO,
+STRUCTS = {"dv3_tc_operand": TcOperand, "dv3_rssm_dims": RssmDims, "dv3_rssm_params": RssmParams,
+           "dv3_rssm_planes": RssmPlanes, "dv3_actor_planes": ActorPlanes, "dv3_observe_io": ObserveIO,
            "dv3_observe_bwd_io": ObserveBwdIO, "dv3_actor": Actor, "dv3_imagine_io": ImagineIO,
            "dv3_imagine_bwd_io": ImagineBwdIO}
 

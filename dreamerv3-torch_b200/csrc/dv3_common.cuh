@@ -289,6 +289,18 @@ struct LinW {
   float* hi = nullptr;
   float* lo = nullptr;
   bool tc = false;
+  int ldp = 0;        // plane pitch (0: K)
+  bool mn = false;    // planes stored [K, N] (a weight used through its transpose)
+
+  // use caller-supplied planes of (a column block of) the weight instead of splitting per call
+  bool adopt(const dv3_tc_operand* o, int col0, bool stored_kn) {
+    if (!tc || !o || !o->hi || !o->lo || o->mn_major != 0 || (o->ld & 3) || (col0 & 3)) return false;
+    hi = const_cast<float*>(o->hi) + col0;
+    lo = const_cast<float*>(o->lo) + col0;
+    ldp = o->ld;
+    mn = stored_kn;
+    return true;
+  }
 
   void reserve(Arena& a, bool use_tc, int n, int k) {
     N = n; K = k; tc = use_tc && (k % 4 == 0);
@@ -302,7 +314,8 @@ struct LinW {
   // C = [A1|A2] W^T from A planes a producer kernel already wrote (tensor-core path only)
   int apply_split(const SplitOut& a1, int K1, const SplitOut* a2, int K2, const float* bias,
                   const float* addend, int ldadd, float* C, int ldc, int M, cudaStream_t st) const {
-    TcOperand o1{a1.hi, a1.lo, a1.ld, false}, o2{nullptr, nullptr, 0, false}, b{hi, lo, K, false};
+    TcOperand o1{a1.hi, a1.lo, a1.ld, false}, o2{nullptr, nullptr, 0, false},
+        b{hi, lo, ldp ? ldp : K, mn};
     if (a2) { o2.hi = a2->hi; o2.lo = a2->lo; o2.ld = a2->ld; }
     return tc_gemm_ops(o1, K1, a2 ? &o2 : nullptr, K2, b, bias, addend, ldadd, C, ldc, M, N, 0, st);
   }

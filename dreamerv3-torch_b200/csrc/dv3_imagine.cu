@@ -221,14 +221,29 @@ extern "C" int dv3_imagine_fwd(const dv3_rssm_dims* d, const dv3_rssm_params* p,
               "imagine_fwd: workspace %zu < %zu bytes", io->workspace_bytes, arena.used);
   const int U = a ? a->units : 0, L = a ? a->layers : 0;
 
-  DV3_TRY(launch_transpose(p->w_in, SC + A, Hd, SC + A, w.WinT, st));
-  DV3_TRY(w.gru.prepare(p->w_gru, Hd + D, st));
-  DV3_TRY(w.out.prepare(p->w_out, D, st));
-  DV3_TRY(w.ims.prepare(p->w_ims, Hd, st));
+  // weight forms: the caller's (made once per optimizer step, dv3_rssm_planes / dv3_actor_planes)
+  // where supplied, else derived here per call
+  const dv3_rssm_planes* rp = p->planes;
+  const dv3_actor_planes* ap = a ? a->planes : nullptr;
+  const float* WinT = w.WinT;
+  if (rp && rp->w_in_t) WinT = rp->w_in_t;
+  else DV3_TRY(launch_transpose(p->w_in, SC + A, Hd, SC + A, w.WinT, st));
+  if (!w.gru.adopt(rp ? &rp->w_gru : nullptr, 0, false)) DV3_TRY(w.gru.prepare(p->w_gru, Hd + D, st));
+  else w.gru.W = p->w_gru, w.gru.ldw = Hd + D;
+  if (!w.out.adopt(rp ? &rp->w_out : nullptr, 0, false)) DV3_TRY(w.out.prepare(p->w_out, D, st));
+  else w.out.W = p->w_out, w.out.ldw = D;
+  if (!w.ims.adopt(rp ? &rp->w_ims : nullptr, 0, false)) DV3_TRY(w.ims.prepare(p->w_ims, Hd, st));
+  else w.ims.W = p->w_ims, w.ims.ldw = Hd;
+  const float* Wa0T = w.Wa0T;
   if (a) {
-    DV3_TRY(launch_transpose(a->w[0], F, U, F, w.Wa0T, st));
-    DV3_TRY(w.a0d.prepare(a->w[0] + SC, F, st));
-    for (int i = 1; i < L; ++i) DV3_TRY(w.al[i].prepare(a->w[i], U, st));
+    if (ap && ap->w0_t) Wa0T = ap->w0_t;
+    else DV3_TRY(launch_transpose(a->w[0], F, U, F, w.Wa0T, st));
+    if (!w.a0d.adopt(ap ? &ap->w[0] : nullptr, SC, false)) DV3_TRY(w.a0d.prepare(a->w[0] + SC, F, st));
+    else w.a0d.W = a->w[0] + SC, w.a0d.ldw = F;
+    for (int i = 1; i < L; ++i) {
+      if (!w.al[i].adopt(ap ? &ap->w[i] : nullptr, 0, false)) DV3_TRY(w.al[i].prepare(a->w[i], U, st));
+      else w.al[i].W = a->w[i], w.al[i].ldw = U;
+    }
   }
   // state 0
   DV3_TRY(copy_rows_i32(io->start_idx, S, N, S, io->idx, S, st));
@@ -257,7 +272,7 @@ extern "C" int dv3_imagine_fwd(const dv3_rssm_dims* d, const dv3_rssm_params* p,
       float* act0 = io->a_act + (size_t)k * N * U;
       // layer 0: deter columns dense, stoch columns gathered
       DV3_TRY(lin(w.a0d, featk + SC, F, D, dcur, nullptr, 0, 0, nullptr, nullptr, w.a_add, U));
-      DV3_TRY(gather_ln_silu(idxk, S, S, C, nullptr, 0, 0, w.Wa0T, w.a_add, U, a->ln_g[0],
+      DV3_TRY(gather_ln_silu(idxk, S, S, C, nullptr, 0, 0, Wa0T, w.a_add, U, a->ln_g[0],
                              a->ln_b[0], d->ln_eps, N, U, pre0, U, act0, U, st, w.asp[0]));
       for (int i = 1; i < L; ++i) {
         float* prei = io->a_pre + i * lstride + (size_t)k * N * U;
@@ -315,7 +330,7 @@ extern "C" int dv3_imagine_fwd(const dv3_rssm_dims* d, const dv3_rssm_params* p,
     float* ypre = io->y_pre + (size_t)k * N * Hd;
     float* yk = io->y + (size_t)k * N * Hd;
     float* logn = io->logit + (size_t)(k + 1) * N * SC;
-    DV3_TRY(gather_ln_silu(idxk, S, S, C, actk, A, A, w.WinT, nullptr, 0, p->ln_in_g, p->ln_in_b,
+    DV3_TRY(gather_ln_silu(idxk, S, S, C, actk, A, A, WinT, nullptr, 0, p->ln_in_g, p->ln_in_b,
                            d->ln_eps, N, Hd, xpre, Hd, xk, Hd, st, w.xsp));
     DV3_TRY(lin(w.gru, xk, Hd, Hd, w.xsp, featk + SC, F, D, &dcur, nullptr, gpre, 3 * D));
     DV3_TRY(gru_gates_fwd(gpre, 3 * D, p->ln_gru_g, p->ln_gru_b, d->ln_eps, featk + SC, F, N, D,
@@ -412,14 +427,25 @@ extern "C" int dv3_imagine_bwd(const dv3_rssm_dims* d, const dv3_rssm_params* p,
   DV3_REQUIRE(io->workspace && arena.ok(), DV3_ERR_WORKSPACE,
               "imagine_bwd: workspace %zu < %zu bytes", io->workspace_bytes, arena.used);
 
-  DV3_TRY(launch_transpose(p->w_ims, Hd, SC, Hd, w.WimsT, st));
-  DV3_TRY(launch_transpose(p->w_out, D, Hd, D, w.WoutT, st));
-  DV3_TRY(launch_transpose(p->w_gru, Hd + D, 3 * D, Hd + D, w.WgruT, st));
-  DV3_TRY(launch_transpose(p->w_in, SC + A, Hd, SC + A, w.WinT, st));
-  DV3_TRY(w.ims.prepare(w.WimsT, SC, st));
-  DV3_TRY(w.out.prepare(w.WoutT, Hd, st));
-  DV3_TRY(w.gru.prepare(w.WgruT, 3 * D, st));
-  DV3_TRY(w.in.prepare(w.WinT, Hd, st));
+  // dx = dy W: with caller-supplied planes of W ([N_out, K_in] = [K, N] of this product) the weight
+  // is read MN-major in place -- no transposed copy, no split; W_in^T comes K-major (w_in_t_sp)
+  const dv3_rssm_planes* rp = p->planes;
+  if (!w.ims.adopt(rp ? &rp->w_ims : nullptr, 0, true)) {
+    DV3_TRY(launch_transpose(p->w_ims, Hd, SC, Hd, w.WimsT, st));
+    DV3_TRY(w.ims.prepare(w.WimsT, SC, st));
+  }
+  if (!w.out.adopt(rp ? &rp->w_out : nullptr, 0, true)) {
+    DV3_TRY(launch_transpose(p->w_out, D, Hd, D, w.WoutT, st));
+    DV3_TRY(w.out.prepare(w.WoutT, Hd, st));
+  }
+  if (!w.gru.adopt(rp ? &rp->w_gru : nullptr, 0, true)) {
+    DV3_TRY(launch_transpose(p->w_gru, Hd + D, 3 * D, Hd + D, w.WgruT, st));
+    DV3_TRY(w.gru.prepare(w.WgruT, 3 * D, st));
+  }
+  if (!w.in.adopt(rp ? &rp->w_in_t_sp : nullptr, 0, false)) {
+    DV3_TRY(launch_transpose(p->w_in, SC + A, Hd, SC + A, w.WinT, st));
+    DV3_TRY(w.in.prepare(w.WinT, Hd, st));
+  }
   DV3_TRY(fill_zero(w.dxh_add, (size_t)N * (Hd + D) * 4, st));
 
   // C = A W^T with A = a delta the producing kernel also wrote as hi/lo planes

@@ -532,10 +532,96 @@ gru_gates_fwd_warp_kernel(const float* __restrict__ g_pre, int ldg, const float*
   }
 }
 
+// block-per-row form for wide states (D = 1024 Q, Q in {2, 4, 8}: dyn_deter 2048 / 4096 / 8192): the
+// 3 D row is read once (float4) and stays in registers, two block reductions give the LayerNorm
+// statistics.  The scalar kernel above reads the row three times: 66 us per 1024 x 12288 launch of
+// the large imagination config (ncu, profiles/ncu_large_rollout_r02.json).
+template <int Q>
+__global__ void __launch_bounds__(256)
+gru_gates_fwd_block_kernel(const float* __restrict__ g_pre, int ldg, const float* __restrict__ g,
+                           const float* __restrict__ b, float eps, const float* __restrict__ h,
+                           int ldh, int D, float* __restrict__ h_new, int ldn, SplitOut so) {
+  pdl_wait();
+  pdl_launch_dependents();
+  __shared__ float red[4 * 32];
+  const int r = blockIdx.x, t = threadIdx.x;
+  const float* row = g_pre + (size_t)r * ldg;
+  float4 x[3][Q];
+  float s[1] = {0.f};
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      x[k][q] = *reinterpret_cast<const float4*>(row + k * D + 4 * (t + 256 * q));
+      s[0] += (x[k][q].x + x[k][q].y) + (x[k][q].z + x[k][q].w);
+    }
+  block_sum<1>(s, red);
+  const float n3 = (float)(3 * D);
+  const float mean = s[0] / n3;
+  float v[1] = {0.f};
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      const float a = x[k][q].x - mean, c = x[k][q].y - mean, d = x[k][q].z - mean,
+                  e = x[k][q].w - mean;
+      v[0] = fmaf(a, a, v[0]); v[0] = fmaf(c, c, v[0]); v[0] = fmaf(d, d, v[0]); v[0] = fmaf(e, e, v[0]);
+    }
+  block_sum<1>(v, red);
+  const float rstd = 1.f / sqrtf(v[0] / n3 + eps);
+  auto gate = [&](float xr, float xc, float xu, float gr, float gc, float gu, float br, float bc,
+                  float bu, float hp) {
+    const float pr = fmaf((xr - mean) * rstd, gr, br);
+    const float pc = fmaf((xc - mean) * rstd, gc, bc);
+    const float pu = fmaf((xu - mean) * rstd, gu, bu);
+    const float rg = sigmoidf_(pr);
+    const float cc = tanhf(rg * pc);
+    const float u = sigmoidf_(pu - 1.f);
+    return u * cc + (1.f - u) * hp;
+  };
+#pragma unroll
+  for (int q = 0; q < Q; ++q) {
+    const int c = 4 * (t + 256 * q);
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(g + c));
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(g + D + c));
+    const float4 g2 = __ldg(reinterpret_cast<const float4*>(g + 2 * D + c));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(b + c));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(b + D + c));
+    const float4 b2 = __ldg(reinterpret_cast<const float4*>(b + 2 * D + c));
+    const float4 hp = *reinterpret_cast<const float4*>(h + (size_t)r * ldh + c);
+    float4 hn;
+    hn.x = gate(x[0][q].x, x[1][q].x, x[2][q].x, g0.x, g1.x, g2.x, b0.x, b1.x, b2.x, hp.x);
+    hn.y = gate(x[0][q].y, x[1][q].y, x[2][q].y, g0.y, g1.y, g2.y, b0.y, b1.y, b2.y, hp.y);
+    hn.z = gate(x[0][q].z, x[1][q].z, x[2][q].z, g0.z, g1.z, g2.z, b0.z, b1.z, b2.z, hp.z);
+    hn.w = gate(x[0][q].w, x[1][q].w, x[2][q].w, g0.w, g1.w, g2.w, b0.w, b1.w, b2.w, hp.w);
+    *reinterpret_cast<float4*>(h_new + (size_t)r * ldn + c) = hn;
+    put_split4(so, r, c, hn);
+  }
+}
+
 int gru_gates_fwd(const float* g_pre, int ldg, const float* g, const float* b, float eps,
                   const float* h, int ldh, int M, int D, float* h_new, int ldn, cudaStream_t st,
                   SplitOut so) {
   if (M <= 0) return 0;
+  {
+    const bool vec = ldg % 4 == 0 && ldh % 4 == 0 && ldn % 4 == 0 && al16(g_pre) && al16(g) &&
+                     al16(b) && al16(h) && al16(h_new) &&
+                     (!so.hi || (so.ld % 4 == 0 && al16(so.hi) && al16(so.lo)));
+    if (vec && (D == 2048 || D == 4096 || D == 8192)) {
+      const dim3 grid(M), block(256);
+      if (D == 2048)
+        DV3_CHECK_CUDA(launch_pdl(gru_gates_fwd_block_kernel<2>, grid, block, 0, st, g_pre, ldg, g, b,
+                                  eps, h, ldh, D, h_new, ldn, so));
+      else if (D == 4096)
+        DV3_CHECK_CUDA(launch_pdl(gru_gates_fwd_block_kernel<4>, grid, block, 0, st, g_pre, ldg, g, b,
+                                  eps, h, ldh, D, h_new, ldn, so));
+      else
+        DV3_CHECK_CUDA(launch_pdl(gru_gates_fwd_block_kernel<8>, grid, block, 0, st, g_pre, ldg, g, b,
+                                  eps, h, ldh, D, h_new, ldn, so));
+      DV3_CHECK_LAUNCH("gru_gates_fwd_block_kernel");
+      return 0;
+    }
+  }
   {
     const char* wf = getenv("DV3_GRU_WARP_FWD");         // "0": keep the block-per-row kernel
     const bool ok = !(wf && wf[0] == '0') && M >= 512 && (D == 512 || D == 1024) && ldg % 4 == 0 &&

@@ -716,6 +716,40 @@ extern "C" int dv3_col_sum(const float* x, int32_t ld, int32_t M, int32_t n, flo
 // d_w_init [D]; the two rank-1 weight gradients follow in rank1_add_kernel.
 namespace dv3 {
 
+// out[0..N) (shared, zero-initialised by the caller) += sum_r v[r] * W[r, 0..N)   (W row-major
+// [R, N], N % 4 == 0).  Warp w takes rows w, w+32, ...; a lane keeps float4 column slices in
+// registers (8 loads in flight per row), the 32 warps meet through shared-memory atomics.
+__device__ __forceinline__ void vec_mat_accum(const float* __restrict__ v, const float* __restrict__ W,
+                                              int R, int N, float* out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int cb = 0; cb < N; cb += 1024) {
+    float4 acc[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = warp; r < R; r += nw) {
+      const float g = v[r];
+      const float* row = W + (size_t)r * N + cb;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int c = lane * 4 + q * 128;
+        if (cb + c < N) {
+          const float4 w = __ldg(reinterpret_cast<const float4*>(row + c));
+          acc[q].x = fmaf(g, w.x, acc[q].x); acc[q].y = fmaf(g, w.y, acc[q].y);
+          acc[q].z = fmaf(g, w.z, acc[q].z); acc[q].w = fmaf(g, w.w, acc[q].w);
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int c = cb + lane * 4 + q * 128;
+      if (c < N) {
+        atomicAdd(out + c, acc[q].x); atomicAdd(out + c + 1, acc[q].y);
+        atomicAdd(out + c + 2, acc[q].z); atomicAdd(out + c + 3, acc[q].w);
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(1024)
 rssm_initial_bwd_kernel(const float* __restrict__ init_deter, const float* __restrict__ init_ypre,
                         const float* __restrict__ init_logit, const float* __restrict__ w_out,
@@ -727,7 +761,8 @@ rssm_initial_bwd_kernel(const float* __restrict__ init_deter, const float* __res
                         float* __restrict__ d_w_init) {
   extern __shared__ float sm[];
   float* s_dlg = sm;                 // [S*C]
-  float* s_v = s_dlg + S * C;        // [Hd] scratch (d_y0, then d_ypre)
+  float* s_v = s_dlg + S * C;        // [Hd] d_y0, then d_ypre
+  float* s_d = s_v + Hd;             // [D]  d_deter0
   __shared__ float red[4 * 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
   // 1. categorical chain, one warp per group
@@ -748,14 +783,12 @@ rssm_initial_bwd_kernel(const float* __restrict__ init_deter, const float* __res
     }
     if (valid) { s_dlg[s * C + lane] = dl; d_lg[s * C + lane] = dl; }
   }
+  const int SC = S * C;
+  for (int j = tid; j < Hd; j += blockDim.x) s_v[j] = 0.f;
+  for (int k = tid; k < D; k += blockDim.x) s_d[k] = 0.f;
   __syncthreads();
   // 2. d_y0[j] = sum_sc d_lg[sc] W_ims[sc, j]
-  const int SC = S * C;
-  for (int j = tid; j < Hd; j += blockDim.x) {
-    float a = 0.f;
-    for (int sc = 0; sc < SC; ++sc) a = fmaf(s_dlg[sc], w_ims[(size_t)sc * Hd + j], a);
-    s_v[j] = a;
-  }
+  vec_mat_accum(s_dlg, w_ims, SC, Hd, s_v);
   __syncthreads();
   // 3. LayerNorm + SiLU backward of the row
   float acc[1] = {0.f};
@@ -787,9 +820,10 @@ rssm_initial_bwd_kernel(const float* __restrict__ init_deter, const float* __res
   }
   __syncthreads();
   // 4. d_deter0[k] = sum_j d_ypre[j] W_out[j, k] + g_deter0[k];  d W = d_deter0 (1 - deter0^2)
+  vec_mat_accum(s_v, w_out, Hd, D, s_d);
+  __syncthreads();
   for (int k = tid; k < D; k += blockDim.x) {
-    float a = g_deter0 ? g_deter0[k] : 0.f;
-    for (int j = 0; j < Hd; ++j) a = fmaf(s_v[j], w_out[(size_t)j * D + k], a);
+    const float a = s_d[k] + (g_deter0 ? g_deter0[k] : 0.f);
     const float t = init_deter[k];
     d_w_init[k] = a * (1.f - t * t);
   }
@@ -844,8 +878,9 @@ extern "C" int dv3_rssm_initial_bwd(const dv3_rssm_dims* d, const dv3_rssm_param
   float* s_dln = s_dyp + Hd;
   float* s_xh = s_dln + Hd;
   float* s_dw = s_xh + Hd;
-  const size_t smem = (size_t)(SC + Hd) * 4;
-  DV3_REQUIRE(smem <= 48 * 1024, DV3_ERR_BAD_SHAPE, "rssm_initial_bwd: S*C + Hd = %d too large", SC + Hd);
+  const size_t smem = (size_t)(SC + Hd + D) * 4;
+  DV3_REQUIRE(smem <= 48 * 1024 && Hd % 4 == 0 && D % 4 == 0, DV3_ERR_BAD_SHAPE,
+              "rssm_initial_bwd: S*C + Hd + D = %d too large or widths not multiples of 4", SC + Hd + D);
   rssm_initial_bwd_kernel<<<1, 1024, smem, ST>>>(init_deter, init_ypre, init_logit, p->w_out, p->ln_out_g,
                                                  p->ln_out_b, p->w_ims, g_norm, g_deter0, S, C, D, Hd,
                                                  d->unimix, d->ln_eps, s_dlg, s_dyp, s_dln, s_xh, s_dw);

@@ -356,6 +356,65 @@ def split_param(w):
     return sp
 
 
+def transpose_param(w):
+    """(W^T as a contiguous fp32 [K, N] tensor, its Split), cached on the parameter per weight
+    epoch like split_param: the one-hot gather form of a Linear over [one-hot | dense] inputs."""
+    tag = (_WEIGHT_EPOCH[0], w._version, w.data_ptr(), tuple(w.shape))
+    hit = getattr(w, "_dv3_wt", None) if isinstance(w, torch.nn.Parameter) else None
+    if hit is not None and hit[0] == tag:
+        return hit[1]
+    wd = w.detach()
+    N, Kd = wd.shape
+    wt = torch.empty(Kd, N, dtype=torch.float32, device=wd.device)
+    L.check(L.lib().dv3_transpose(_raw(wd), wd.stride(0), N, Kd, L.fptr(wt), L.stream_ptr()),
+            "transpose")
+    out = (wt, split(wt))
+    if isinstance(w, torch.nn.Parameter):
+        w._dv3_wt = (tag, out)
+    return out
+
+
+def _operand(o, sp):
+    o.hi, o.lo, o.ld, o.mn_major = _raw(sp.hi), _raw(sp.lo), sp.ld, 0
+
+
+def rssm_planes(params):
+    """dv3_rssm_planes for the 17 RSSM parameters (L.RSSM_PARAM_FIELDS order): the weight forms
+    the imagination calls read, made once per optimizer step (planes written by the fused Adam
+    step where available) instead of inside every call.  -> (struct, keepalive)."""
+    P = dict(zip(L.RSSM_PARAM_FIELDS, params))
+    pl = L.RssmPlanes()
+    keep = []
+    for name in ("w_gru", "w_out", "w_ims"):
+        if P[name].shape[1] % 4:
+            return None, None
+        sp = split_param(P[name])
+        _operand(getattr(pl, name), sp)
+        keep.append(sp)
+    wt, wtsp = transpose_param(P["w_in"])
+    pl.w_in_t = L.fptr(wt)
+    _operand(pl.w_in_t_sp, wtsp)
+    keep += [wt, wtsp]
+    return pl, keep
+
+
+def actor_planes(spec, params):
+    """dv3_actor_planes for the flat actor parameter list [w_0, g_0, b_0, w_1, ...]."""
+    pl = L.ActorPlanes()
+    keep = []
+    for i in range(spec.layers):
+        w = params[3 * i]
+        if w.shape[1] % 4:
+            return None, None
+        sp = split_param(w)
+        _operand(pl.w[i], sp)
+        keep.append(sp)
+    wt, _ = transpose_param(params[0])
+    pl.w0_t = L.fptr(wt)
+    keep.append(wt)
+    return pl, keep
+
+
 def split_param_like(w):
     """Split of a detached weight tensor (saved for backward): no parameter object to cache on."""
     return split(w)
@@ -628,12 +687,16 @@ def make_dims(stoch, classes, deter, hidden, actions, embed, unimix):
     return L.RssmDims(stoch, classes, deter, hidden, actions, embed, unimix, LN_EPS)
 
 
-def pack_rssm(params):
-    """params: list of 17 tensors ordered as L.RSSM_PARAM_FIELDS -> (struct, keepalive)."""
+def pack_rssm(params, planes=None):
+    """params: list of 17 tensors ordered as L.RSSM_PARAM_FIELDS -> (struct, keepalive);
+    ``planes``: a dv3_rssm_planes struct to attach (kept alive by the caller)."""
     keep = [_c(p.detach()) for p in params]
     st = L.RssmParams()
     for name, t in zip(L.RSSM_PARAM_FIELDS, keep):
         setattr(st, name, L.fptr(t))
+    if planes is not None:
+        st.planes = C.pointer(planes)
+        keep.append(planes)
     return st, keep
 
 
@@ -811,7 +874,7 @@ class ActorSpec:
     def n_params(self):
         return 3 * self.layers + (4 if self.dist == "normal" else 2)
 
-    def pack(self, params):
+    def pack(self, params, planes=None):
         """params: [w_0, g_0, b_0, w_1, ...] + [w_mean, b_mean (, w_std, b_std)]."""
         keep = [_c(p.detach()) for p in params]
         Lr = self.layers
@@ -826,7 +889,9 @@ class ActorSpec:
         a.w_mean, a.b_mean = L.fptr(keep[3 * Lr]), L.fptr(keep[3 * Lr + 1])
         if self.dist == "normal":
             a.w_std, a.b_std = L.fptr(keep[3 * Lr + 2]), L.fptr(keep[3 * Lr + 3])
-        return a, (keep, w, g, b)
+        if planes is not None:
+            a.planes = C.pointer(planes)
+        return a, (keep, w, g, b, planes)
 
 
 class _Imagine(torch.autograd.Function):
@@ -845,8 +910,15 @@ class _Imagine(torch.autograd.Function):
         SC, Fw = S * Cc, S * Cc + D
         rssm_params, actor_params = params[:17], params[17:]
         d = make_dims(S, Cc, D, Hd, A, E, unimix)
-        pst, keep_r = pack_rssm(rssm_params)
-        act_struct, keep_a = (spec.pack(actor_params) if spec is not None else (None, None))
+        # weight forms made once per optimizer step (cached per parameter), not inside the call
+        rpl = apl = keep_pl = None
+        if N >= 64:
+            rpl, k1 = rssm_planes(rssm_params)
+            apl, k2 = actor_planes(spec, actor_params) if spec is not None else (None, None)
+            keep_pl = (rpl, k1, apl, k2)
+        ctx.planes = keep_pl
+        pst, keep_r = pack_rssm(rssm_params, rpl)
+        act_struct, keep_a = (spec.pack(actor_params, apl) if spec is not None else (None, None))
         f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
         U, Lr = (spec.units, spec.layers) if spec is not None else (0, 0)
         o = dict(feat=f(H, N, Fw), logit=f(H, N, S, Cc), action=f(H, N, A),
@@ -918,7 +990,8 @@ class _Imagine(torch.autograd.Function):
             feat_sp = Split(saved[ctx.n_saved - 2], saved[ctx.n_saved - 1], H * N, SC + D)
         dev = feat.device
         d = make_dims(S, Cc, D, Hd, A, E, unimix)
-        pst, keep_r = pack_rssm(rssm_params)
+        rpl = ctx.planes[0] if ctx.planes is not None else None     # the forward's (weights unchanged)
+        pst, keep_r = pack_rssm(rssm_params, rpl)
         act_struct, keep_a = spec.pack(actor_params)
         f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
         g_stoch = g_deter = None

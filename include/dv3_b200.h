@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DV3_ABI_VERSION 1
+#define DV3_ABI_VERSION 2
 
 typedef enum {
   DV3_OK = 0,
@@ -66,6 +66,29 @@ typedef struct {
   float ln_eps;     /* 1e-3                                                     */
 } dv3_rssm_dims;
 
+/* One operand of dv3_gemm_tc: tf32 hi / lo planes (hi = x with the 13 low mantissa bits cleared,
+ * lo = x - hi) with a common row pitch ld (floats, % 4 == 0); mn_major == 0: stored [rows, K],
+ * != 0: stored [K, rows]. */
+typedef struct {
+  const float* hi;
+  const float* lo;
+  int32_t ld;
+  int32_t mn_major;
+} dv3_tc_operand;
+
+/* Optional derived forms of the RSSM weights, made by the CALLER once per optimizer step and
+ * reused by every call until the weights change (dv3_split_tf32 / dv3_transpose, or the planes
+ * dv3_adam_clip_step_planes writes).  With `planes == NULL` in dv3_rssm_params the library derives
+ * what it needs inside each call (transposes + splits per call).  Used by dv3_imagine_fwd / _bwd
+ * and dv3_img_step_fwd when the tensor-core path is taken (N >= 64 rows). */
+typedef struct {
+  dv3_tc_operand w_gru;      /* planes of _cell.layers.GRU_linear.weight [3D, Hd+D]          */
+  dv3_tc_operand w_out;      /* planes of _img_out_layers.0.weight       [Hd, D]             */
+  dv3_tc_operand w_ims;      /* planes of _imgs_stat_layer.weight        [S*C, Hd]           */
+  const float* w_in_t;       /* (_img_in_layers.0.weight)^T              [S*C+A, Hd] fp32    */
+  dv3_tc_operand w_in_t_sp;  /* planes of w_in_t                         [S*C+A, Hd]         */
+} dv3_rssm_planes;
+
 typedef struct {
   const float* w_in;      /* _img_in_layers.0.weight        [Hd, S*C+A]  */
   const float* ln_in_g;   /* _img_in_layers.1.weight        [Hd]         */
@@ -84,6 +107,7 @@ typedef struct {
   const float* w_os;      /* _obs_stat_layer.weight         [S*C, Hd]    */
   const float* b_os;      /* _obs_stat_layer.bias           [S*C]        */
   const float* w_init;    /* W                              [1, D]       */
+  const dv3_rssm_planes* planes;  /* optional caller-derived forms, or NULL                  */
 } dv3_rssm_params;
 
 /* ------------------------------------------------------------------------------------------
@@ -194,6 +218,12 @@ int dv3_observe_bwd(const dv3_rssm_dims* d, const dv3_rssm_params* p,
  * with actor == NULL and given actions it is RSSM.imagine_with_action (networks.py:145-152).
  * Time-major [H,N,...] like the reference.
  * ---------------------------------------------------------------------------------------- */
+/* Optional derived forms of the actor trunk weights (see dv3_rssm_planes). */
+typedef struct {
+  dv3_tc_operand w[16];  /* planes of Actor_linear{i}.weight: [U, F] for i == 0, then [U, U]  */
+  const float* w0_t;     /* (Actor_linear0.weight)^T [F, U] fp32 (one-hot gather form)        */
+} dv3_actor_planes;
+
 typedef struct {
   int32_t layers;        /* trunk layers (2 or 5) */
   int32_t units;         /* U */
@@ -205,6 +235,7 @@ typedef struct {
   const float* const* ln_b;  /* [layers] */
   const float* w_mean; const float* b_mean;  /* mean_layer [A, U], [A] */
   const float* w_std;  const float* b_std;   /* std_layer  [A, U], [A] (normal only) */
+  const dv3_actor_planes* planes;            /* optional caller-derived forms, or NULL */
 } dv3_actor;
 
 typedef struct {
@@ -356,12 +387,6 @@ int dv3_linear_tc_fwd(const float* A, int32_t lda, int32_t transA, const float* 
  * stages, fp32 accumulation in TMEM promoted to registers every 128 k.
  * Replaces: every nn.Linear product of the path (networks.py:48-78 RSSM layers, 623-655 MLP,
  * 742-768 GRUCell) and the dx / dW matmuls autograd derives from them. */
-typedef struct {
-  const float* hi;
-  const float* lo;
-  int32_t ld;
-  int32_t mn_major;
-} dv3_tc_operand;
 int dv3_gemm_tc(const dv3_tc_operand* A1, int32_t K1, const dv3_tc_operand* A2, int32_t K2,
                 const dv3_tc_operand* B, const float* bias, const float* addend, int32_t ldadd,
                 float* C, int32_t ldc, int32_t M, int32_t N, int32_t accumulate, void* stream);

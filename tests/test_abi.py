@@ -27,6 +27,7 @@ def header_structs():
             decl = decl.strip()
             if not decl:
                 continue
+            decl = re.sub(r"\[\d+\]", "", decl)
             names = re.findall(r"(\w+)\s*(?:,|$)", decl)
             fields += names
         out[name] = fields
@@ -41,7 +42,7 @@ def test_library_exports_every_declared_symbol(pkg):
         assert hasattr(lib, name), f"{name} declared in dv3_b200.h but not exported"
         assert name in pkg._lib.SIGNATURES, f"{name} has no ctypes signature"
     assert sorted(pkg._lib.SIGNATURES) == declared
-    assert lib.dv3_version() == 1
+    assert lib.dv3_version() == 2
 
 
 def test_struct_mirrors_match_header(pkg):

@@ -36,6 +36,19 @@ METRIC = "train_steps_per_s"
 UNIT = "train steps/s (1 step = WM update on 16x64 replay batch + AC update on 1024x15 imagination, per GPU)"
 
 
+def _ncu_traffic():
+    """Per-launch DRAM bytes of the dominant kernel family (the tcgen05 GEMMs) from the committed
+    ncu launch list of one eager step (profiles/launches_r02_step.json: dram__bytes_read.sum +
+    dram__bytes_write.sum summed over the family / its launches)."""
+    path = os.path.join(ROOT, "profiles", "launches_r02_step.json")
+    try:
+        with open(path) as f:
+            g = json.load(f)["gemm_family"]
+        return 1e6 * (g["dram_read_mb"] + g["dram_write_mb"]) / g["launches"]
+    except Exception:
+        return None
+
+
 def _peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(path):
@@ -453,7 +466,10 @@ def run_ours(args):
             "kernel": "umma2x_gemm_kernel / umma2_gemm_kernel (persistent tcgen05 3xTF32 GEMM on CTA pairs / single "
                       "CTAs: every imagination-step and bulk-row contraction, y / dx / dW; dominant by time)",
             "bound": "tensor", "achieved": ach, "peak": peaks["tf"], "unit": "TFLOP/s",
-            "frac": ach / peaks["tf"], "traffic": None, "peak_source": peaks["src"],
+            "frac": ach / peaks["tf"], "traffic": _ncu_traffic(),
+            "traffic_note": "mean DRAM bytes per GEMM launch (ncu dram__bytes_read.sum + dram__bytes_write.sum over "
+                            "the 229 GEMM launches of one eager step, profiles/launches_r02_step.json)",
+            "peak_source": peaks["src"],
             "ceiling_3xtf32": peaks["tf"] / 6.0, "frac_of_3xtf32_ceiling": ach / (peaks["tf"] / 6.0),
             "flops": "algorithmic 2*M*N*K per launch (fp32 result); the kernel issues 3 tf32 MMAs per product, "
                      "so the tensor pipe does 3x this against a tf32 peak of half the bf16 figure",

@@ -436,13 +436,31 @@ def run_ours(args):
     barrier()
 
     def leave():
-        # The NCCL communicator is referenced by the captured graph; tearing the process group
-        # down while the graph is alive blocks (measured: destroy_process_group never returns
-        # after a capture that contains the allreduce).  All collective work is finished here,
-        # so every rank just flushes and exits.
+        # Clean NCCL teardown first: drop the captured graph (it references the communicator),
+        # synchronise, destroy the process group.  Measured in round 1: destroy_process_group can
+        # block forever after a capture that contains collectives, so it runs under a watchdog
+        # and the rank falls back to a hard exit (all collective work is finished here).
         sys.stdout.flush()
         sys.stderr.flush()
         if world > 1:
+            done = threading.Event()
+
+            def teardown():
+                try:
+                    import gc
+                    graph._graph = None          # the CUDA graph holds the communicator's kernels
+                    graph._out = None
+                    gc.collect()
+                    torch.cuda.synchronize()
+                    dist.destroy_process_group()
+                finally:
+                    done.set()
+
+            t = threading.Thread(target=teardown, daemon=True)
+            t.start()
+            if not done.wait(timeout=15):
+                stage("destroy_process_group did not return in 15 s; hard exit")
+            sys.stdout.flush()
             os._exit(0)
 
     if rank != 0:

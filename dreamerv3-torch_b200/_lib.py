@@ -139,6 +139,7 @@ SIGNATURES = {
     "dv3_version": (C.c_int, []),
     "dv3_last_error": (C.c_char_p, []),
     "dv3_device_arch": (C.c_int, []),
+    "dv3_reload_env": (None, []),
     "dv3_launch_count": (C.c_longlong, []),
     "dv3_prof_enable": (None, [C.c_int]),
     "dv3_prof_read": (C.c_int, [_P(C.c_double), _P(C.c_double), _P(C.c_longlong)]),

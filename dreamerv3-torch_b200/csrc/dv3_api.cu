@@ -2,6 +2,7 @@
 // single-step wrappers (obs_step / img_step) over the sequence kernels.
 #include <stdarg.h>
 #include <stdlib.h>
+#include <string.h>
 #include <atomic>
 #include <mutex>
 #include <vector>
@@ -23,13 +24,35 @@ int cuda_fail(cudaError_t e, const char* what) {
   return DV3_ERR_CUDA;
 }
 
-bool pdl_enabled() {
-  static int on = -1;
-  if (on < 0) {
-    const char* e = getenv("DV3_PDL");
-    on = (e && e[0] == '1') ? 1 : 0;   // measured: 16.76 ms/step with it, 16.33 without -> off
+static std::atomic<unsigned> g_env_epoch{1};
+
+const char* env_cached(const char* name, EnvSlot& slot) {
+  const unsigned ep = g_env_epoch.load(std::memory_order_relaxed);
+  if (slot.epoch != ep) {
+    const char* e = getenv(name);
+    slot.has = e != nullptr;
+    slot.val[0] = 0;
+    if (e) { strncpy(slot.val, e, sizeof(slot.val) - 1); slot.val[sizeof(slot.val) - 1] = 0; }
+    slot.epoch = ep;
   }
-  return on != 0;
+  return slot.has ? slot.val : nullptr;
+}
+
+bool pdl_enabled() {
+  const char* e = DV3_ENV("DV3_PDL");
+  return e && e[0] == '1';             // measured: 16.76 ms/step with it, 16.33 without -> off
+}
+
+int sm_count() {
+  static int sms[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& v = sms[dev & 63];
+  if (!v) {
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    if (v <= 0) v = 148;
+  }
+  return v;
 }
 
 // ---- launch counter + optional GEMM timing --------------------------------------------
@@ -89,6 +112,8 @@ extern "C" int dv3_prof_read(double* ms, double* flops, long long* launches) {
 }
 
 extern "C" int dv3_version(void) { return DV3_ABI_VERSION; }
+
+extern "C" void dv3_reload_env(void) { dv3::g_env_epoch.fetch_add(1); }
 
 extern "C" const char* dv3_last_error(void) { return dv3::g_err; }
 

@@ -63,6 +63,31 @@ __device__ __forceinline__ void pdl_launch_dependents() {
 }
 bool pdl_enabled();
 
+// ---- process-level caches ------------------------------------------------------------------
+// Environment knobs are read once and cached; dv3_reload_env() (tests, A/B runs) drops the cache.
+struct EnvSlot {
+  unsigned epoch = 0;
+  bool has = false;
+  char val[64] = {0};
+};
+const char* env_cached(const char* name, EnvSlot& slot);
+#define DV3_ENV(name) ([]() -> const char* { static ::dv3::EnvSlot slot_; return ::dv3::env_cached(name, slot_); }())
+
+// "once per device" latch for per-context settings (cudaFuncSetAttribute): a process may drive
+// several GPUs through the library.
+struct DeviceOnce {
+  unsigned long long done = 0;
+  bool need() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (done & bit) return false;
+    done |= bit;
+    return true;
+  }
+};
+int sm_count();     // multiprocessors of the current device (cached per device)
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
                               cudaStream_t st, Args... args) {

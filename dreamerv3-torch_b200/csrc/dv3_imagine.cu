@@ -288,13 +288,11 @@ extern "C" int dv3_imagine_fwd(const dv3_rssm_dims* d, const dv3_rssm_params* p,
       const int nh = a->dist == 0 ? 2 : 1;
       const size_t ah_smem = (size_t)nh * A * U * sizeof(float);
       if (nh * A <= 32 && ah_smem <= 160 * 1024) {
-        static bool attr = false;
-        if (!attr) {
+        static DeviceOnce attr;
+        if (attr.need())
           DV3_CHECK_CUDA(cudaFuncSetAttribute(actor_head_kernel,
                                               cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               160 * 1024));
-          attr = true;
-        }
         const int nw = AH_THREADS / 32;
         int grid = (N + nw - 1) / nw;
         if (grid > 148) grid = 148;

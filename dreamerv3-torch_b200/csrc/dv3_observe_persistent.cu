@@ -315,7 +315,7 @@ static unsigned long long* g_po_timing = nullptr;
 
 // debug stamp buffer ([4096][8] u64), allocated on first use when DV3_OBSERVE_TIMING=1
 unsigned long long* po_timing_buffer() {
-  const char* te = getenv("DV3_OBSERVE_TIMING");
+  const char* te = DV3_ENV("DV3_OBSERVE_TIMING");
   if (!te || (te[0] != '1' && te[0] != '2')) return nullptr;
   if (!g_po_timing && cudaMalloc(&g_po_timing, 4096 * 8 * sizeof(unsigned long long)) != cudaSuccess)
     return nullptr;
@@ -355,7 +355,7 @@ int observe_fwd_persistent(const dv3_rssm_dims* d, const dv3_rssm_params* p,
                            const dv3_observe_io* io, const float* WinT, const float* pre_e,
                            unsigned* bar, cudaStream_t st, bool* used) {
   *used = false;
-  const char* env = getenv("DV3_OBSERVE_STEPWISE");
+  const char* env = DV3_ENV("DV3_OBSERVE_STEPWISE");
   if (env && env[0] == '1') return 0;
   const int D = d->deter, Hd = d->hidden, S = d->stoch, C = d->classes;
   if (io->B > PO_ROWS || D % 32 != 0 || (D / 32 != 2 && D / 32 != 4 && D / 32 != 8 && D / 32 != 16))
@@ -383,7 +383,7 @@ int observe_fwd_persistent(const dv3_rssm_dims* d, const dv3_rssm_params* p,
   a.z_pre = io->z_pre; a.z = io->z; a.post_idx = io->post_idx; a.sprev_idx = io->sprev_idx;
   a.bar = bar;
   a.timing = nullptr;
-  if (const char* te = getenv("DV3_OBSERVE_TIMING"))
+  if (const char* te = DV3_ENV("DV3_OBSERVE_TIMING"))
     if (te[0] == '1' && io->T <= 4096) a.timing = po_timing_buffer();
   a.ncg = (3 * D + G - 1) / G;
   a.bufw = ((D > Hd ? D : Hd) + 3) & ~3;

@@ -470,7 +470,7 @@ int observe_bwd_persistent(const dv3_rssm_dims* d, const dv3_rssm_params* p,
                            const dv3_observe_bwd_io* io, const ObsBwdShared& w, cudaStream_t st,
                            bool* used) {
   *used = false;
-  const char* env = getenv("DV3_OBSERVE_STEPWISE");
+  const char* env = DV3_ENV("DV3_OBSERVE_STEPWISE");
   if (env && env[0] == '1') return 0;
   const int D = d->deter, Hd = d->hidden, S = d->stoch, C = d->classes, B = io->B;
   if (B > PO_ROWS || D % 32 != 0 || (D / 32 != 2 && D / 32 != 4 && D / 32 != 8 && D / 32 != 16))
@@ -500,7 +500,7 @@ int observe_bwd_persistent(const dv3_rssm_dims* d, const dv3_rssm_params* p,
   a.d_z = w.d_z; a.dh_z = w.dh_z; a.dhdir = w.dhdir; a.dxh = w.dxh;
   a.bar = w.bar;
   a.timing = nullptr;
-  if (const char* te = getenv("DV3_OBSERVE_TIMING"))
+  if (const char* te = DV3_ENV("DV3_OBSERVE_TIMING"))
     if (te[0] == '2' && io->T <= 4096) a.timing = po_timing_buffer();
   a.ncz = (Hd + G - 1) / G;
   a.cpd = (D + S - 1) / S;

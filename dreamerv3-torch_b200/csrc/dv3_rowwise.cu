@@ -69,13 +69,9 @@ ln_silu_fwd_kernel(const float* __restrict__ pre, int ld, const float* __restric
 // writes 16-byte vectors.  Needs n % 4 == 0, n <= 128 NV and 16-byte aligned rows.
 constexpr int BULK_WARPS = 8;
 static int bulk_rows() {               // row count from which the warp-per-row kernels take over
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("DV3_BULK_ROWS");
-    v = e ? atoi(e) : 4096;
-    if (v < 1) v = 1;
-  }
-  return v;
+  const char* e = DV3_ENV("DV3_BULK_ROWS");
+  const int v = e ? atoi(e) : 4096;
+  return v < 1 ? 1 : v;
 }
 
 __device__ __forceinline__ float4 split_hi4(float4 v) {
@@ -415,7 +411,7 @@ int gather_ln_silu(const int32_t* idx, int ldi, int S, int C, const float* act, 
   {
     // opt-in ("1"): measured 0.5 % slower over the train step than the block-per-row kernel
     // (same-box A/B, 80.5 vs 80.9 steps/s) -- 128 blocks of 8 warps leave the gathers latency-bound
-    const char* wf = getenv("DV3_GATHER_WARP");
+    const char* wf = DV3_ENV("DV3_GATHER_WARP");
     const bool ok = (wf && wf[0] == '1') && M >= 512 && S <= 32 && A <= 32 && n % 4 == 0 &&
                     n <= 1024 && ldp % 4 == 0 && ldo % 4 == 0 && al16(WT) && al16(pre) && al16(out) &&
                     al16(g) && al16(b) && (!addend || (ldadd % 4 == 0 && al16(addend))) &&
@@ -623,7 +619,7 @@ int gru_gates_fwd(const float* g_pre, int ldg, const float* g, const float* b, f
     }
   }
   {
-    const char* wf = getenv("DV3_GRU_WARP_FWD");         // "0": keep the block-per-row kernel
+    const char* wf = DV3_ENV("DV3_GRU_WARP_FWD");         // "0": keep the block-per-row kernel
     const bool ok = !(wf && wf[0] == '0') && M >= 512 && (D == 512 || D == 1024) && ldg % 4 == 0 &&
                     ldh % 4 == 0 && ldn % 4 == 0 && al16(g_pre) && al16(g) && al16(b) && al16(h) &&
                     al16(h_new) && (!so.hi || (so.ld % 4 == 0 && al16(so.hi) && al16(so.lo)));
@@ -831,7 +827,7 @@ int gru_gates_bwd(const float* g_pre, int ldg, const float* g, const float* b, f
   DhIn dh;
   for (int q = 0; q < 4; ++q) { dh.p[q] = dh_in[q]; dh.ld[q] = ld_in[q]; }
   {
-    const char* wf = getenv("DV3_GRU_WARP");             // "0": keep the block-per-row kernel
+    const char* wf = DV3_ENV("DV3_GRU_WARP");             // "0": keep the block-per-row kernel
     bool ok = !(wf && wf[0] == '0') && M >= 512 && (D == 512 || D == 1024) && ldg % 4 == 0 &&
               ldh % 4 == 0 && ldp % 4 == 0 && ldd % 4 == 0 && al16(g_pre) && al16(g) && al16(b) &&
               al16(h) && al16(d_g_pre) && al16(dh_direct) &&
@@ -852,12 +848,10 @@ int gru_gates_bwd(const float* g_pre, int ldg, const float* g, const float* b, f
     }
   }
   const size_t smem = (size_t)(3 * D + 4 * 32) * 4;
-  static bool attr_set = false;
-  if (smem > 48 * 1024 && !attr_set) {
+  static DeviceOnce attr_set;
+  if (smem > 48 * 1024 && attr_set.need())
     DV3_CHECK_CUDA(cudaFuncSetAttribute(gru_gates_bwd_kernel,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
   DV3_REQUIRE(smem <= 200 * 1024, DV3_ERR_BAD_SHAPE, "gru_gates_bwd: deter %d too wide", D);
   DV3_CHECK_CUDA(launch_pdl(gru_gates_bwd_kernel, dim3(M), dim3(ROW_THREADS), smem, st, g_pre, ldg, g,
                             b, eps, h, ldh, dh, D, d_g_pre, ldp, d_g_ln, ldl, dh_direct, ldd, so));
@@ -993,7 +987,7 @@ int onehot_sample(const float* logits, int ldl, const float* u, int ldu, int per
                   cudaStream_t st) {
   if (M <= 0) return 0;
   DV3_REQUIRE(C >= 1 && C <= 32, DV3_ERR_BAD_SHAPE, "onehot_sample: classes=%d (max 32)", C);
-  const char* gf = getenv("DV3_SAMPLE_GROUP");         // "0": keep the lane-per-class kernel
+  const char* gf = DV3_ENV("DV3_SAMPLE_GROUP");         // "0": keep the lane-per-class kernel
   const bool group_form = !(gf && gf[0] == '0');
   if (group_form && C == 32 && onehot && (long long)M * S >= 4096 && (long long)M * S < (1ll << 28) &&
       ldl % 4 == 0 && ldo % 4 == 0 && al16(logits) && al16(onehot) && (!u || (ldu % 4 == 0 && al16(u)))) {
@@ -1099,7 +1093,7 @@ int onehot_st_bwd(const float* logits, int ldl, const float* g1, int ldg1, const
   if (M <= 0) return 0;
   DV3_REQUIRE(C >= 1 && C <= 32, DV3_ERR_BAD_SHAPE, "onehot_st_bwd: classes=%d (max 32)", C);
   {
-    const char* gf = getenv("DV3_STBWD_GROUP");          // "0": keep the lane-per-class kernel
+    const char* gf = DV3_ENV("DV3_STBWD_GROUP");          // "0": keep the lane-per-class kernel
     if (!(gf && gf[0] == '0') && C == 32 && (long long)M * S >= 4096 &&
         (long long)M * S < (1ll << 28)) {
       const long long lanes = 4ll * M * S;

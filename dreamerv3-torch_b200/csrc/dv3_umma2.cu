@@ -550,17 +550,6 @@ int make_map2(CUtensorMap* m, const float* base, int rows, int K, int ld, int bo
   return 0;
 }
 
-int sm_count() {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-  }
-  return sms;
-}
-
 // resident clusters of `sk` CTAs of the 128-wide kernel (0 = cluster launch unavailable)
 template <int SK>
 static int max_clusters_sk();
@@ -569,12 +558,10 @@ template <int BN, bool AMN, bool BMN, bool RAW, bool WIDE = false, int SK = 1>
 static int launch_umma2(const Gemm2Maps& mp, Gemm2Args g, double flops, cudaStream_t st) {
   using Cfg = G2Cfg<BN>;
   auto kern = umma2_gemm_kernel<BN, AMN, BMN, RAW, WIDE, SK>;
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce attr;
+  if (attr.need())
     DV3_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)Cfg::SMEM));
-    attr = true;
-  }
   g.tiles_n = (g.N + BN - 1) / BN;
   g.tiles_m = (g.M + G2_BM - 1) / G2_BM;
   g.tiles = g.tiles_n * g.tiles_m;
@@ -626,8 +613,12 @@ static int dispatch_major(bool amn, bool bmn, const Gemm2Maps& mp, const Gemm2Ar
 
 template <int SK>
 static int max_clusters_sk() {
-  static int n = -1;
-  if (n < 0) {
+  static int per_dev[64];
+  static DeviceOnce probed;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& n = per_dev[dev & 63];
+  if (probed.need()) {
     using Cfg = G2Cfg<128>;
     auto kern = umma2_gemm_kernel<128, false, false, false, true, SK>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
@@ -730,16 +721,13 @@ int tc_gemm_ops(const TcOperand& A1, int K1, const TcOperand* A2, int K2, const 
   const int K = K1 + K2;
   const int nk_all = (K1 + G2_BK - 1) / G2_BK + (K2 + G2_BK - 1) / G2_BK;
   int BN = 32, splitk = 1, pair = 0, csk = 0;
-  static int allow_pair = -1, allow_csk = -1;
-  if (allow_pair < 0) {
-    const char* e = getenv("DV3_TC_PAIR");
-    allow_pair = (e && e[0] == '0') ? 0 : 1;
-    e = getenv("DV3_TC_CSK");
-    allow_csk = (e && e[0] == '0') ? 0 : 1;
-  }
+  const char* e_pair = DV3_ENV("DV3_TC_PAIR");
+  const char* e_csk = DV3_ENV("DV3_TC_CSK");
+  const int allow_pair = (e_pair && e_pair[0] == '0') ? 0 : 1;
+  const int allow_csk = (e_csk && e_csk[0] == '0') ? 0 : 1;
   pick_shape(M, N, nk_all, (accumulate & 2) != 0, allow_pair && !raw, allow_csk && !raw, &BN,
              &splitk, &pair, &csk);
-  if (const char* f = getenv("DV3_TC_FORCE")) {       // experiment knob: "<BN>,<pair>[,<cluster K>]"
+  if (const char* f = DV3_ENV("DV3_TC_FORCE")) {       // experiment knob: "<BN>,<pair>[,<cluster K>]"
     int fb = 0, fp = 0, fc = 0;
     const int got = sscanf(f, "%d,%d,%d", &fb, &fp, &fc);
     if (got >= 2 && (fb == 32 || fb == 64 || fb == 128) &&
@@ -774,7 +762,7 @@ int tc_gemm_ops(const TcOperand& A1, int K1, const TcOperand* A2, int K2, const 
   g.K1 = K1; g.nk1 = (K1 + G2_BK - 1) / G2_BK; g.nk = g.nk1 + (K2 + G2_BK - 1) / G2_BK;
   g.accumulate = accumulate & 1;
   g.splitk = splitk;
-  if (const char* te = getenv("DV3_GEMM_TIMING")) g.stamps = te[0] == '1' ? po_timing_buffer() : nullptr;
+  if (const char* te = DV3_ENV("DV3_GEMM_TIMING")) g.stamps = te[0] == '1' ? po_timing_buffer() : nullptr;
   const double flops = 2.0 * M * N * K;
   if (raw) {
     if (BN == 128) return dispatch_major<128, true>(false, false, mp, g, flops, st);
@@ -783,11 +771,8 @@ int tc_gemm_ops(const TcOperand& A1, int K1, const TcOperand* A2, int K2, const 
   }
   // two-MMA issue: measured 12-20 % faster for BN = 32, 10-12 % for BN = 64, 5 % for BN = 128
   // while the launch is a single wave, 1-3 % slower for multi-wave BN = 128 (tensor-pipe bound)
-  static int wide = -1;
-  if (wide < 0) {
-    const char* e = getenv("DV3_TC_WIDE");
-    wide = (e && e[0] == '0') ? 0 : 1;
-  }
+  const char* e_wide = DV3_ENV("DV3_TC_WIDE");
+  const int wide = (e_wide && e_wide[0] == '0') ? 0 : 1;
   if (csk == 2) return dispatch_major<128, false, true, 2>(A1.mn, B.mn, mp, g, flops, st);
   if (csk == 4) return dispatch_major<128, false, true, 4>(A1.mn, B.mn, mp, g, flops, st);
   if (csk == 8) return dispatch_major<128, false, true, 8>(A1.mn, B.mn, mp, g, flops, st);

@@ -330,18 +330,15 @@ umma2x_gemm_kernel(const __grid_constant__ GemmX2Maps mp, GemmX2Args g) {
 
 // ---- host ------------------------------------------------------------------------------------
 int make_map2(CUtensorMap* m, const float* base, int rows, int K, int ld, int box_rows, bool mn);
-int sm_count();
 
 template <int BN, bool AMN, bool BMN>
 static int launch_x2(const GemmX2Maps& mp, GemmX2Args g, double flops, cudaStream_t st) {
   using Cfg = X2Cfg<BN>;
   auto kern = umma2x_gemm_kernel<BN, AMN, BMN>;
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce attr;
+  if (attr.need())
     DV3_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)Cfg::SMEM));
-    attr = true;
-  }
   g.tiles_n = (g.N + BN - 1) / BN;
   g.tiles_m = (g.M + 2 * X2_BM - 1) / (2 * X2_BM);
   g.tiles = g.tiles_n * g.tiles_m;

@@ -40,6 +40,9 @@ typedef enum {
 
 int dv3_version(void);
 const char* dv3_last_error(void);
+/* The library reads its environment knobs (DV3_*) once and caches them;
+ * call this after changing one inside a running process (tests, A/B measurements). */
+void dv3_reload_env(void);
 /* compute capability major*10+minor of the current device, or negative on error */
 int dv3_device_arch(void);
 /* number of kernels this library has launched in this process (all entry points) */

@@ -29,3 +29,24 @@ def device():
     lib = os.path.join(ROOT, "dreamerv3-torch_b200", "libdv3_b200.so")
     assert os.path.isfile(lib), "libdv3_b200.so not built (python -c 'import __graft_entry__ as g; g.build()')"
     return "cuda:0"
+
+
+@pytest.fixture
+def knob(pkg):
+    """Set a library environment knob (DV3_*) for one test: the library caches its environment,
+    so every change is followed by dv3_reload_env(); restored afterwards."""
+    import os
+    saved = {}
+
+    def set_(name, value):
+        saved.setdefault(name, os.environ.get(name))
+        os.environ[name] = value
+        pkg._lib.lib().dv3_reload_env()
+
+    yield set_
+    for name, old in saved.items():
+        if old is None:
+            os.environ.pop(name, None)
+        else:
+            os.environ[name] = old
+    pkg._lib.lib().dv3_reload_env()

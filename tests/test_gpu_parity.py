@@ -44,10 +44,10 @@ def test_onehot_sample_and_straight_through(pkg, device, C, unimix):
 @pytest.mark.parametrize("stepwise", ["0", "1"])
 @pytest.mark.parametrize("config,B,T", [("tiny", 3, 5), ("dmc_proprio", 16, 64), ("dmc_vision", 16, 16),
                                         ("dmc_proprio", 7, 9)])
-def test_observe_fwd_bwd(pkg, device, config, B, T, stepwise, monkeypatch):
+def test_observe_fwd_bwd(pkg, device, config, B, T, stepwise, knob):
     """stepwise=0: persistent cooperative kernel for the forward recurrence (B <= 16);
     stepwise=1: the launch-per-phase path (what larger shapes use)."""
-    monkeypatch.setenv("DV3_OBSERVE_STEPWISE", stepwise)
+    knob("DV3_OBSERVE_STEPWISE", stepwise)
     before = pkg._lib.lib().dv3_launch_count()
     _assert(pc.observe_case(pkg, device, config=config, B=B, T=T, backward=False))
     launches = pkg._lib.lib().dv3_launch_count() - before
@@ -273,7 +273,7 @@ def test_split_is_exact(pkg, device, M, K):
 @pytest.mark.gpu
 @pytest.mark.parametrize("unimix", [0.01, 0.0])
 @pytest.mark.parametrize("with_u", [True, False])
-def test_onehot_sample_group_form_is_bit_identical(pkg, device, monkeypatch, unimix, with_u):
+def test_onehot_sample_group_form_is_bit_identical(pkg, device, knob, unimix, with_u):
     """The thread-per-group sampler (32 classes in registers, sums in the butterfly's association
     order) must pick exactly the indices of the lane-per-class kernel -- which is the one pinned
     against the oracle -- for draws (reference tools.py:436-460 + ATen multinomial) and modes."""
@@ -283,9 +283,9 @@ def test_onehot_sample_group_form_is_bit_identical(pkg, device, monkeypatch, uni
     logits[5, 3] = 0.0                      # exact ties: first index must win
     logits[6, 0, 7] = float("nan")
     u = torch.rand(4096, 32, 32, generator=g).clamp_(1e-30, 1.0).to(device) if with_u else None
-    monkeypatch.setenv("DV3_SAMPLE_GROUP", "0")
+    knob("DV3_SAMPLE_GROUP", "0")
     idx0, hot0 = K.onehot_sample(logits, u, unimix)
-    monkeypatch.setenv("DV3_SAMPLE_GROUP", "1")
+    knob("DV3_SAMPLE_GROUP", "1")
     idx1, hot1 = K.onehot_sample(logits, u, unimix)
     assert torch.equal(idx0, idx1) and torch.equal(hot0, hot1)
     if not with_u:
@@ -296,13 +296,13 @@ def test_onehot_sample_group_form_is_bit_identical(pkg, device, monkeypatch, uni
 @pytest.mark.gpu
 @pytest.mark.parametrize("M,D", [(1024, 512), (600, 1024), (1024, 256)])
 @pytest.mark.parametrize("warp_form", ["1", "0"])
-def test_gru_gates_bwd_matches_autograd(pkg, device, monkeypatch, M, D, warp_form):
+def test_gru_gates_bwd_matches_autograd(pkg, device, knob, M, D, warp_form):
     """Backward of the LayerNorm-GRU gate block (reference networks.py:760-768) through the C ABI,
     block-per-row and warp-per-row kernels (the latter takes D = 512 / 1024 at M >= 512), against
     torch autograd of the same expression."""
     import ctypes as C
     L = pkg._lib
-    monkeypatch.setenv("DV3_GRU_WARP", warp_form)
+    knob("DV3_GRU_WARP", warp_form)
     gen = torch.Generator().manual_seed(M + D)
     g_pre = torch.randn(M, 3 * D, generator=gen).to(device).requires_grad_(True)
     gam = (1 + 0.1 * torch.randn(3 * D, generator=gen)).to(device)
@@ -327,7 +327,7 @@ def test_gru_gates_bwd_matches_autograd(pkg, device, monkeypatch, M, D, warp_for
 
 
 @pytest.mark.gpu
-def test_onehot_st_bwd_group_form_matches(pkg, device, monkeypatch):
+def test_onehot_st_bwd_group_form_matches(pkg, device, knob):
     """Straight-through backward of the unimix categorical (reference tools.py:436-460 through
     autograd): the four-lanes-per-group kernel against the lane-per-class one and torch autograd."""
     K = pkg.kernels
@@ -335,9 +335,9 @@ def test_onehot_st_bwd_group_form_matches(pkg, device, monkeypatch):
     logits = (torch.randn(2048, 32, 32, generator=g) * 2).to(device)
     gs = torch.randn(2048, 32, 32, generator=g).to(device)
     ext = torch.randn(2048, 32, 32, generator=g).to(device)
-    monkeypatch.setenv("DV3_STBWD_GROUP", "0")
+    knob("DV3_STBWD_GROUP", "0")
     d0 = K.onehot_st_bwd(logits, gs, ext, 0.01)
-    monkeypatch.setenv("DV3_STBWD_GROUP", "1")
+    knob("DV3_STBWD_GROUP", "1")
     d1 = K.onehot_st_bwd(logits, gs, ext, 0.01)
     d0 = d0[0] if isinstance(d0, tuple) else d0
     d1 = d1[0] if isinstance(d1, tuple) else d1
@@ -352,7 +352,7 @@ def test_onehot_st_bwd_group_form_matches(pkg, device, monkeypatch):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("n,A,with_add", [(512, 6, False), (1024, 17, True), (500, 0, True)])
-def test_onehot_linear_warp_form_matches(pkg, device, monkeypatch, n, A, with_add):
+def test_onehot_linear_warp_form_matches(pkg, device, knob, n, A, with_add):
     """One-hot Linear + LN + SiLU (reference networks.py:208-221 on cat(one-hot stoch, action)):
     the warp-per-row kernel accumulates in the block-per-row kernel's order, so `pre` must be
     bit-identical and `out` equal to fp32 rounding; both against a dense torch product."""
@@ -367,7 +367,7 @@ def test_onehot_linear_warp_form_matches(pkg, device, monkeypatch, n, A, with_ad
     bet = (0.1 * torch.randn(n, generator=gen)).to(device)
     res = {}
     for form in ("0", "1"):
-        monkeypatch.setenv("DV3_GATHER_WARP", form)
+        knob("DV3_GATHER_WARP", form)
         pre = torch.empty(M, n, device=device); out = torch.empty(M, n, device=device)
         L.check(L.lib().dv3_onehot_linear_ln_silu(L.iptr(idx), S, Cc, L.fptr(act), A, L.fptr(WT), L.fptr(add),
                                                   L.fptr(gam), L.fptr(bet), 1e-3, M, n, L.fptr(pre), L.fptr(out),

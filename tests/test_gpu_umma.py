@@ -177,12 +177,12 @@ def test_gemm_pair_kernel_is_used(pkg, device):
 
 @pytest.mark.parametrize("force", ["32,0", "64,0", "128,0", "128,0,2", "128,0,4", "128,0,8"])
 @pytest.mark.parametrize("M,N,K", [(1024, 512, 512), (1000, 255, 1030), (1024, 1024, 96)])
-def test_gemm_forced_tilings_agree(pkg, device, monkeypatch, force, M, N, K):
+def test_gemm_forced_tilings_agree(pkg, device, knob, force, M, N, K):
     """Every tiling of the single-CTA kernel -- the two-MMA issue at BN = 32 / 64 / 128 and the
     cluster split-K mode (K over 2 / 4 / 8 CTAs of a cluster, partial tiles reduced through
     distributed shared memory in a fixed order) -- against fp64, with bias + addend + accumulate
     into a strided view, and bit-identical from run to run."""
-    monkeypatch.setenv("DV3_TC_FORCE", force)
+    knob("DV3_TC_FORCE", force)
     g = torch.Generator().manual_seed(M + 3 * N + 5 * K)
     Kp = (K + 3) // 4 * 4
     a = torch.zeros(M, Kp); a[:, :K] = torch.randn(M, K, generator=g)

@@ -51,7 +51,7 @@ __device__ __forceinline__ void po_stamp(const PoArgs& p, int t, int slot) {
   }
 }
 
-template <int DV>   // DV = D / 32
+template <int DV, bool FASTA>   // DV = D / 32; FASTA: phase A spread over the grid (see PoArgs::fastA)
 __global__ void __launch_bounds__(PO_THREADS, 1) observe_persistent_fwd_kernel(PoArgs p) {
   extern __shared__ __align__(16) float smf[];
   const int G = gridDim.x, cta = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(PO_THREADS, 1) observe_persistent_fwd_kernel(P
   // a thread owns
   const int ca0 = cta * 4;
   float4 lg4 = make_float4(0.f, 0.f, 0.f, 0.f), lb4 = lg4;
-  if (p.fastA && tid < (Hd >> 2)) {
+  if (FASTA && tid < (Hd >> 2)) {
     lg4 = __ldg(reinterpret_cast<const float4*>(p.ln_in_g + 4 * tid));
     lb4 = __ldg(reinterpret_cast<const float4*>(p.ln_in_b + 4 * tid));
   }
@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(PO_THREADS, 1) observe_persistent_fwd_kernel(P
   unsigned gen = 0;
   for (int t = 0; t < T; ++t) {
     po_stamp(p, t, 0);
-    if (p.fastA) {
+    if (FASTA) {
       // ---------------- phase A (all CTAs): previous-state select spread over the grid, and
       // x_pre[:, own 4 columns] = sum_s W_in^T[s C + idx_s] + sum_a act_a W_in^T[S C + a]:
       // warp = row, lane = categorical group (then action component), float4 column slice,
@@ -207,57 +207,51 @@ __global__ void __launch_bounds__(PO_THREADS, 1) observe_persistent_fwd_kernel(P
     po_stamp(p, t, 2);
 
     // ---------------- phase B: GRU pre-activations, own columns ----------------
-    if (p.fastA) {
+    if (FASTA) {
       // every CTA holds the whole [x | h] input in registers (one k-quad per thread, 16 rows):
       // the threads that own x quads first turn x_pre into x = SiLU(LN(x_pre)) in place (row
-      // statistics through shared memory); one CTA per step stores x for the backward pass
+      // statistics through shared memory: sums in part[0..128), squared deviations in
+      // part[128..256)); one CTA per step stores x for the backward pass
       float* gp = p.g_pre;
       const int nxq = Hd >> 2;
       auto ln_x = [&](float4 (&a)[1][PO_ROWS]) {
         const bool isx = tid < nxq;
-        float sv[PO_ROWS];
-#pragma unroll
-        for (int m = 0; m < PO_ROWS; ++m)
-          sv[m] = warp_sum(isx ? (a[0][m].x + a[0][m].y) + (a[0][m].z + a[0][m].w) : 0.f);
-        if (lane == 0) {
-#pragma unroll
-          for (int m = 0; m < PO_ROWS; ++m) part[warp * PO_ROWS + m] = sv[m];
-        }
-        __syncthreads();
-        float mean[PO_ROWS];
 #pragma unroll
         for (int m = 0; m < PO_ROWS; ++m) {
+          const float sm_ = warp_sum(isx ? (a[0][m].x + a[0][m].y) + (a[0][m].z + a[0][m].w) : 0.f);
+          if (lane == 0) part[warp * PO_ROWS + m] = sm_;
+        }
+        __syncthreads();
+        auto mean_of = [&](int m) {
           float s2 = 0.f;
 #pragma unroll
           for (int w2 = 0; w2 < PO_WARPS; ++w2) s2 += part[w2 * PO_ROWS + m];
-          mean[m] = s2 / (float)Hd;
-        }
-        __syncthreads();
+          return s2 / (float)Hd;
+        };
 #pragma unroll
         for (int m = 0; m < PO_ROWS; ++m) {
-          const float dx = a[0][m].x - mean[m], dy = a[0][m].y - mean[m], dz = a[0][m].z - mean[m],
-                      dw = a[0][m].w - mean[m];
-          sv[m] = warp_sum(isx ? fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, dw * dw))) : 0.f);
-        }
-        if (lane == 0) {
-#pragma unroll
-          for (int m = 0; m < PO_ROWS; ++m) part[warp * PO_ROWS + m] = sv[m];
+          const float mu = mean_of(m);
+          const float dx = a[0][m].x - mu, dy = a[0][m].y - mu, dz = a[0][m].z - mu, dw = a[0][m].w - mu;
+          const float q_ = warp_sum(isx ? fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, dw * dw))) : 0.f);
+          if (lane == 0) part[PO_WARPS * PO_ROWS + warp * PO_ROWS + m] = q_;
         }
         __syncthreads();
         if (isx) {
+          const bool writer = cta == (t % G);
 #pragma unroll
           for (int m = 0; m < PO_ROWS; ++m) {
+            const float mu = mean_of(m);
             float q2 = 0.f;
 #pragma unroll
-            for (int w2 = 0; w2 < PO_WARPS; ++w2) q2 += part[w2 * PO_ROWS + m];
+            for (int w2 = 0; w2 < PO_WARPS; ++w2) q2 += part[PO_WARPS * PO_ROWS + w2 * PO_ROWS + m];
             const float rstd = 1.f / sqrtf(q2 / (float)Hd + p.eps);
             float4 y;
-            y.x = siluf_(fmaf((a[0][m].x - mean[m]) * rstd, lg4.x, lb4.x));
-            y.y = siluf_(fmaf((a[0][m].y - mean[m]) * rstd, lg4.y, lb4.y));
-            y.z = siluf_(fmaf((a[0][m].z - mean[m]) * rstd, lg4.z, lb4.z));
-            y.w = siluf_(fmaf((a[0][m].w - mean[m]) * rstd, lg4.w, lb4.w));
+            y.x = siluf_(fmaf((a[0][m].x - mu) * rstd, lg4.x, lb4.x));
+            y.y = siluf_(fmaf((a[0][m].y - mu) * rstd, lg4.y, lb4.y));
+            y.z = siluf_(fmaf((a[0][m].z - mu) * rstd, lg4.z, lb4.z));
+            y.w = siluf_(fmaf((a[0][m].w - mu) * rstd, lg4.w, lb4.w));
             a[0][m] = y;
-            if (cta == (t % G) && m < B)
+            if (writer && m < B)
               *reinterpret_cast<float4*>(p.x + ((size_t)m * T + t) * Hd + 4 * tid) = y;
           }
         }
@@ -446,9 +440,9 @@ static size_t po_smem_bytes(const PoArgs& a) {
   return fl * 4;
 }
 
-template <int DV>
+template <int DV, bool FASTA = false>
 static int po_launch(PoArgs& a, int G, size_t smem, cudaStream_t st, bool* used) {
-  auto kern = observe_persistent_fwd_kernel<DV>;
+  auto kern = observe_persistent_fwd_kernel<DV, FASTA>;
   DV3_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   DV3_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PO_THREADS, smem));
@@ -517,7 +511,7 @@ int observe_fwd_persistent(const dv3_rssm_dims* d, const dv3_rssm_params* p,
   // every CTA must own GRU columns (all of them run the phase-B prologue)
   {
     const char* fa = DV3_ENV("DV3_OBSERVE_FASTA");
-    a.fastA = !(fa && fa[0] == '0') && Hd == 4 * G && Hd + D == 4 * PO_THREADS && S <= 32 &&
+    a.fastA = !(fa && fa[0] == '0') && D == 512 && Hd == 4 * G && Hd + D == 4 * PO_THREADS && S <= 32 &&
               d->actions <= 32 && (3 * D) >= G && a.ncg * (G - 1) < 3 * D;
   }
   const size_t smem = po_smem_bytes(a);
@@ -526,7 +520,8 @@ int observe_fwd_persistent(const dv3_rssm_dims* d, const dv3_rssm_params* p,
     case 2: return po_launch<2>(a, G, smem, st, used);
     case 4: return po_launch<4>(a, G, smem, st, used);
     case 8: return po_launch<8>(a, G, smem, st, used);
-    default: return po_launch<16>(a, G, smem, st, used);
+    default:
+      return a.fastA ? po_launch<16, true>(a, G, smem, st, used) : po_launch<16>(a, G, smem, st, used);
   }
 }
 

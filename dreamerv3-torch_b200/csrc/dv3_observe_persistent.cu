@@ -39,7 +39,6 @@ struct PoArgs {
   int ncg, bufw;
   int nrbC, rpbC, cpb;          // phase C/D: row blocks, rows per block, W_obs columns per CTA
   int nrbE, rpbE;               // phase E: row blocks per categorical group, rows per block
-  int fastA;                    // phase A spread over all CTAs, LayerNorm of x folded into phase B
   unsigned long long* timing;   // debug: [T][8] %globaltimer stamps of CTA 0 (NULL = off)
 };
 
@@ -51,7 +50,7 @@ __device__ __forceinline__ void po_stamp(const PoArgs& p, int t, int slot) {
   }
 }
 
-template <int DV, bool FASTA>   // DV = D / 32; FASTA: phase A spread over the grid (see PoArgs::fastA)
+template <int DV>   // DV = D / 32
 __global__ void __launch_bounds__(PO_THREADS, 1) observe_persistent_fwd_kernel(PoArgs p) {
   extern __shared__ __align__(16) float smf[];
   const int G = gridDim.x, cta = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -101,66 +100,11 @@ __global__ void __launch_bounds__(PO_THREADS, 1) observe_persistent_fwd_kernel(P
   for (int i = tid; i < Hd; i += PO_THREADS) { lzg[i] = p.ln_obs_g[i]; lzb[i] = p.ln_obs_b[i]; }
   __syncthreads();
 
-  // fast phase A: this CTA's four x_pre columns, and (phase B) the LN affine terms of the k-quad
-  // a thread owns
-  const int ca0 = cta * 4;
-  float4 lg4 = make_float4(0.f, 0.f, 0.f, 0.f), lb4 = lg4;
-  if (FASTA && tid < (Hd >> 2)) {
-    lg4 = __ldg(reinterpret_cast<const float4*>(p.ln_in_g + 4 * tid));
-    lb4 = __ldg(reinterpret_cast<const float4*>(p.ln_in_b + 4 * tid));
-  }
-
   unsigned gen = 0;
   for (int t = 0; t < T; ++t) {
+    // ---------------- phase A: row b = cta ----------------
     po_stamp(p, t, 0);
-    if (FASTA) {
-      // ---------------- phase A (all CTAs): previous-state select spread over the grid, and
-      // x_pre[:, own 4 columns] = sum_s W_in^T[s C + idx_s] + sum_a act_a W_in^T[S C + a]:
-      // warp = row, lane = categorical group (then action component), float4 column slice,
-      // butterfly sum.  The LayerNorm of x needs whole rows: it runs in phase B's prologue. ----
-      for (int i = cta * PO_THREADS + tid; i < B * D; i += G * PO_THREADS) {
-        const int b = i / D, j = i - b * D;
-        const size_t bt = (size_t)b * T + t;
-        const bool first = p.first_eff[bt] != 0.f;
-        const float* ph = t ? p.deter + (bt - 1) * D : (p.state_deter ? p.state_deter + (size_t)b * D : nullptr);
-        p.hprev[bt * D + j] = first ? p.init_deter[j] : __ldcg(ph + j);
-      }
-      for (int i = cta * PO_THREADS + tid; i < B * S; i += G * PO_THREADS) {
-        const int b = i / S, s_ = i - b * S;
-        const size_t bt = (size_t)b * T + t;
-        const bool first = p.first_eff[bt] != 0.f;
-        const int32_t* pidx = t ? p.post_idx + (bt - 1) * S : (p.state_idx ? p.state_idx + (size_t)b * S : nullptr);
-        p.sprev_idx[bt * S + s_] = first ? p.init_idx[s_] : __ldcg(pidx + s_);
-      }
-      for (int i = cta * PO_THREADS + tid; i < B * A; i += G * PO_THREADS) {
-        const int b = i / A, a_ = i - b * A;
-        const size_t bt = (size_t)b * T + t;
-        p.aprev[bt * A + a_] = (p.first_eff[bt] != 0.f) ? 0.f : p.action[bt * A + a_];
-      }
-      for (int b = warp; b < B; b += PO_WARPS) {
-        const size_t bt = (size_t)b * T + t;
-        const bool first = p.first_eff[bt] != 0.f;
-        const int32_t* pidx = t ? p.post_idx + (bt - 1) * S : (p.state_idx ? p.state_idx + (size_t)b * S : nullptr);
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (lane < S) {
-          const int v = first ? p.init_idx[lane] : __ldcg(pidx + lane);
-          acc = __ldg(reinterpret_cast<const float4*>(p.WinT + (size_t)(v + lane * C) * Hd + ca0));
-        }
-        if (lane < A && !first) {
-          const float av = p.action[bt * A + lane];
-          const float4 w = __ldg(reinterpret_cast<const float4*>(p.WinT + (size_t)(SC + lane) * Hd + ca0));
-          acc.x = fmaf(av, w.x, acc.x); acc.y = fmaf(av, w.y, acc.y);
-          acc.z = fmaf(av, w.z, acc.z); acc.w = fmaf(av, w.w, acc.w);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          acc.x += __shfl_xor_sync(FULL, acc.x, o); acc.y += __shfl_xor_sync(FULL, acc.y, o);
-          acc.z += __shfl_xor_sync(FULL, acc.z, o); acc.w += __shfl_xor_sync(FULL, acc.w, o);
-        }
-        if (lane == 0) *reinterpret_cast<float4*>(p.x_pre + bt * Hd + ca0) = acc;
-      }
-    } else if (cta < B) {
-      // ---------------- phase A: row b = cta ----------------
+    if (cta < B) {
       const int b = cta;
       const size_t bt = (size_t)b * T + t;
       const bool first = p.first_eff[bt] != 0.f;
@@ -207,61 +151,7 @@ __global__ void __launch_bounds__(PO_THREADS, 1) observe_persistent_fwd_kernel(P
     po_stamp(p, t, 2);
 
     // ---------------- phase B: GRU pre-activations, own columns ----------------
-    if (FASTA) {
-      // every CTA holds the whole [x | h] input in registers (one k-quad per thread, 16 rows):
-      // the threads that own x quads first turn x_pre into x = SiLU(LN(x_pre)) in place (row
-      // statistics through shared memory: sums in part[0..128), squared deviations in
-      // part[128..256)); one CTA per step stores x for the backward pass
-      float* gp = p.g_pre;
-      const int nxq = Hd >> 2;
-      auto ln_x = [&](float4 (&a)[1][PO_ROWS]) {
-        const bool isx = tid < nxq;
-#pragma unroll
-        for (int m = 0; m < PO_ROWS; ++m) {
-          const float sm_ = warp_sum(isx ? (a[0][m].x + a[0][m].y) + (a[0][m].z + a[0][m].w) : 0.f);
-          if (lane == 0) part[warp * PO_ROWS + m] = sm_;
-        }
-        __syncthreads();
-        auto mean_of = [&](int m) {
-          float s2 = 0.f;
-#pragma unroll
-          for (int w2 = 0; w2 < PO_WARPS; ++w2) s2 += part[w2 * PO_ROWS + m];
-          return s2 / (float)Hd;
-        };
-#pragma unroll
-        for (int m = 0; m < PO_ROWS; ++m) {
-          const float mu = mean_of(m);
-          const float dx = a[0][m].x - mu, dy = a[0][m].y - mu, dz = a[0][m].z - mu, dw = a[0][m].w - mu;
-          const float q_ = warp_sum(isx ? fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, dw * dw))) : 0.f);
-          if (lane == 0) part[PO_WARPS * PO_ROWS + warp * PO_ROWS + m] = q_;
-        }
-        __syncthreads();
-        if (isx) {
-          const bool writer = cta == (t % G);
-#pragma unroll
-          for (int m = 0; m < PO_ROWS; ++m) {
-            const float mu = mean_of(m);
-            float q2 = 0.f;
-#pragma unroll
-            for (int w2 = 0; w2 < PO_WARPS; ++w2) q2 += part[PO_WARPS * PO_ROWS + w2 * PO_ROWS + m];
-            const float rstd = 1.f / sqrtf(q2 / (float)Hd + p.eps);
-            float4 y;
-            y.x = siluf_(fmaf((a[0][m].x - mu) * rstd, lg4.x, lb4.x));
-            y.y = siluf_(fmaf((a[0][m].y - mu) * rstd, lg4.y, lb4.y));
-            y.z = siluf_(fmaf((a[0][m].z - mu) * rstd, lg4.z, lb4.z));
-            y.w = siluf_(fmaf((a[0][m].w - mu) * rstd, lg4.w, lb4.w));
-            a[0][m] = y;
-            if (writer && m < B)
-              *reinterpret_cast<float4*>(p.x + ((size_t)m * T + t) * Hd + 4 * tid) = y;
-          }
-        }
-        __syncthreads();        // `part` is reused by the column passes
-      };
-      gemv16<true, 6, 1>(Wg, gn, Kg, p.x_pre + (size_t)t * Hd, T * Hd, Hd, p.hprev + (size_t)t * D, T * D,
-                         B, part, [&](int m, int c, float r) {
-                           gp[((size_t)m * T + t) * D3 + g0 + c] = r;
-                         }, ln_x);
-    } else if (gn > 0) {
+    if (gn > 0) {
       float* gp = p.g_pre;
       gemv16<true, 6, 1>(Wg, gn, Kg, p.x + (size_t)t * Hd, T * Hd, Hd, p.hprev + (size_t)t * D, T * D, B,
                    part, [&](int m, int c, float r) {
@@ -440,9 +330,9 @@ static size_t po_smem_bytes(const PoArgs& a) {
   return fl * 4;
 }
 
-template <int DV, bool FASTA = false>
+template <int DV>
 static int po_launch(PoArgs& a, int G, size_t smem, cudaStream_t st, bool* used) {
-  auto kern = observe_persistent_fwd_kernel<DV, FASTA>;
+  auto kern = observe_persistent_fwd_kernel<DV>;
   DV3_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   DV3_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PO_THREADS, smem));
@@ -507,21 +397,13 @@ int observe_fwd_persistent(const dv3_rssm_dims* d, const dv3_rssm_params* p,
   if (a.nrbE > io->B) a.nrbE = io->B;
   a.rpbE = (io->B + a.nrbE - 1) / a.nrbE;
   if (ncb < 1 || a.cpb > 16 || a.rpbC > 4 || a.rpbE > 4 || Hd % 8 != 0) return 0;
-  // fast phase A: 4 x_pre columns per CTA and one [x | h] k-quad per thread (the dmc / atari sizes);
-  // every CTA must own GRU columns (all of them run the phase-B prologue)
-  {
-    const char* fa = DV3_ENV("DV3_OBSERVE_FASTA");
-    a.fastA = !(fa && fa[0] == '0') && D == 512 && Hd == 4 * G && Hd + D == 4 * PO_THREADS && S <= 32 &&
-              d->actions <= 32 && (3 * D) >= G && a.ncg * (G - 1) < 3 * D;
-  }
   const size_t smem = po_smem_bytes(a);
   if (smem > 220 * 1024) return 0;
   switch (D / 32) {
     case 2: return po_launch<2>(a, G, smem, st, used);
     case 4: return po_launch<4>(a, G, smem, st, used);
     case 8: return po_launch<8>(a, G, smem, st, used);
-    default:
-      return a.fastA ? po_launch<16, true>(a, G, smem, st, used) : po_launch<16>(a, G, smem, st, used);
+    default: return po_launch<16>(a, G, smem, st, used);
   }
 }
 

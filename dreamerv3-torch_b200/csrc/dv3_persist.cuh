@@ -40,17 +40,10 @@ __device__ __forceinline__ float4 load4(const float* p) {
 //   NQ: k-quads a thread keeps in registers; when K/4 <= NQ*256 the inputs are loaded from L2
 //       exactly once (all loads in flight together) and reused by every column pass -- otherwise
 //       they are re-read per pass and per quad, one L2 round trip each.
-struct NoPre {
-  template <typename A>
-  __device__ __forceinline__ void operator()(A&) const {}
-};
-
-// `pre(a)` (optional) transforms the inputs a thread holds right after they were loaded (all
-// threads call it; it may synchronise the block) -- only on the load-once path (K/4 <= NQ*256).
-template <bool GLOBAL_IN, int CP, int NQ, typename Epi, typename Pre = NoPre>
+template <bool GLOBAL_IN, int CP, int NQ, typename Epi>
 __device__ __forceinline__ void gemv16(const float* Ws, int ncols, int K, const float* in1, int ld1,
                                        int K1, const float* in2, int ld2, int B, float* part,
-                                       Epi epi, Pre pre = Pre()) {
+                                       Epi epi) {
   constexpr int NV = PO_ROWS * CP, PL = NV / 32;     // partials per thread / per lane after the fold
   static_assert(NV % 32 == 0 && NV <= PO_NV, "gemv16: CP must be 2, 4 or 6");
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -69,7 +62,6 @@ __device__ __forceinline__ void gemv16(const float* Ws, int ncols, int K, const 
   if (once) {
 #pragma unroll
     for (int j = 0; j < NQ; ++j) load_quad(tid + j * PO_THREADS, a[j]);
-    pre(a);
   }
   for (int cb = 0; cb < ncols; cb += CP) {
     float acc[NV];

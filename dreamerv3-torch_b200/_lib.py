@@ -183,6 +183,7 @@ SIGNATURES = {
     "dv3_im2col_s2k4": (C.c_int, [_f, _i32, _i32, _i32, _i32, _f, _f, _f, _v]),
     "dv3_col2im_s2k4": (C.c_int, [_f, _i32, _i32, _i32, _i32, _f, _f32, _f, _v]),
     "dv3_debug_observe_timing": (C.c_int, [_P(C.c_ulonglong), _i32]),
+    "dv3_debug_imagine_timing": (C.c_int, [_P(C.c_ulonglong), _i32]),
     "dv3_ln_silu_fwd_split": (C.c_int, [_f, _i32, _f, _f, _f32, _i32, _i32, _f, _i32, _f, _f, _i32,
                                         _v]),
     "dv3_ln_silu_bwd_split": (C.c_int, [_f, _i32, _f, _f, _f32, _f, _i32, _i32, _i32, _f, _f, _i32,

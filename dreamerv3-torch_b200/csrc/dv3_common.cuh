@@ -289,6 +289,20 @@ struct ObsBwdShared {
 int observe_bwd_persistent(const dv3_rssm_dims* d, const dv3_rssm_params* p,
                            const dv3_observe_bwd_io* io, const ObsBwdShared& w, cudaStream_t st,
                            bool* used);
+// persistent imagination forward (dv3_imagine_persistent.cu): the operand planes dv3_imagine_fwd
+// has prepared; *used == false on return -> shapes not covered, run the stepwise launches
+struct PiPlane { const float* hi; const float* lo; int ld; };
+struct PiPlanes {
+  bool ok;
+  float *dsp_hi[2], *dsp_lo[2], *asp_hi[2], *asp_lo[2], *xsp_hi, *xsp_lo, *ysp_hi, *ysp_lo;
+  PiPlane wa[3], gru, out, ims;
+  const float* Wa0T;
+  const float* WinT;
+};
+int imagine_fwd_persistent(const dv3_rssm_dims* d, const dv3_rssm_params* p, const dv3_actor* a,
+                           const dv3_imagine_io* io, const PiPlanes& pl, void* sync_ws,
+                           cudaStream_t st, bool* used);
+size_t imagine_persistent_sync_bytes(int N);
 unsigned long long* po_timing_buffer();   // debug stamps (DV3_OBSERVE_TIMING=1 fwd, =2 bwd)
 // rows below this go to the CUDA-core kernels (a 128-row MMA tile would be mostly padding)
 constexpr int TC_MIN_ROWS = 64;

@@ -121,6 +121,7 @@ struct ImgFwdWs {
   SplitOut ysp;      // y                        [N, Hd]
   SplitOut asp[2];   // actor activations        [N, U]
   LinW gru, out, ims, a0d, al[16];
+  void* pi_sync;     // counters + LayerNorm statistics of the persistent kernel
 };
 
 static SplitOut take_split(Arena& a, bool on, size_t rows, int cols) {
@@ -156,6 +157,7 @@ static void carve_img_fwd(Arena& a, const dv3_rssm_dims* d, const dv3_actor* act
   } else {
     w.Wa0T = w.a_add = nullptr;
   }
+  w.pi_sync = a.take<char>(imagine_persistent_sync_bytes(N));
 }
 
 static int check_actor(const dv3_rssm_dims* d, const dv3_actor* a, const char* who) {
@@ -251,6 +253,28 @@ extern "C" int dv3_imagine_fwd(const dv3_rssm_dims* d, const dv3_rssm_params* p,
   DV3_TRY(copy_rows(io->start_deter, D, N, D, io->feat + SC, F, st));
   const bool tc = w.gru.tc;
   if (tc) DV3_TRY(tc_split(io->start_deter, D, D, nullptr, 0, 0, N, w.dsp[0].hi, w.dsp[0].lo, st));
+  if (a && tc) {
+    // the whole rollout as one persistent kernel when the shapes allow it (dv3_imagine_persistent.cu)
+    auto plane = [](const LinW& W) { return PiPlane{W.hi, W.lo, W.ldp ? W.ldp : W.K}; };
+    PiPlanes pl{};
+    pl.ok = w.gru.tc && w.out.tc && w.ims.tc && w.a0d.tc && !w.gru.mn && !w.out.mn && !w.ims.mn &&
+            !w.a0d.mn && L <= 3;
+    for (int i = 1; i < L && i < 3; ++i) pl.ok = pl.ok && w.al[i].tc && !w.al[i].mn;
+    if (pl.ok) {
+      for (int b = 0; b < 2; ++b) {
+        pl.dsp_hi[b] = w.dsp[b].hi; pl.dsp_lo[b] = w.dsp[b].lo;
+        pl.asp_hi[b] = w.asp[b].hi; pl.asp_lo[b] = w.asp[b].lo;
+      }
+      pl.xsp_hi = w.xsp.hi; pl.xsp_lo = w.xsp.lo; pl.ysp_hi = w.ysp.hi; pl.ysp_lo = w.ysp.lo;
+      pl.wa[0] = plane(w.a0d);
+      for (int i = 1; i < L; ++i) pl.wa[i] = plane(w.al[i]);
+      pl.gru = plane(w.gru); pl.out = plane(w.out); pl.ims = plane(w.ims);
+      pl.Wa0T = Wa0T; pl.WinT = WinT;
+      bool used = false;
+      DV3_TRY(imagine_fwd_persistent(d, p, a, io, pl, w.pi_sync, st, &used));
+      if (used) return 0;
+    }
+  }
   // C = [A1|A2] W^T: from the producers' hi/lo planes on the tensor-core path, from the fp32
   // activations on the CUDA-core path (N < 64 rows)
   auto lin = [&](const LinW& W, const float* A1, int lda1, int K1, const SplitOut& s1,

@@ -100,6 +100,16 @@ __global__ void __launch_bounds__(PO_THREADS, 1) observe_persistent_fwd_kernel(P
   for (int i = tid; i < Hd; i += PO_THREADS) { lzg[i] = p.ln_obs_g[i]; lzb[i] = p.ln_obs_b[i]; }
   __syncthreads();
 
+  // constants the time loop would otherwise re-fetch from L2 after every barrier
+  float lin_g[4], lin_b[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int i = tid + u * PO_THREADS;
+    lin_g[u] = i < Hd ? p.ln_in_g[i] : 0.f;
+    lin_b[u] = i < Hd ? p.ln_in_b[i] : 0.f;
+  }
+  const float bos = (lane < C) ? p.b_os[(size_t)gE * C + lane] : 0.f;
+
   unsigned gen = 0;
   for (int t = 0; t < T; ++t) {
     // ---------------- phase A: row b = cta ----------------
@@ -123,11 +133,29 @@ __global__ void __launch_bounds__(PO_THREADS, 1) observe_persistent_fwd_kernel(P
         sact[a] = v;
       }
       __syncthreads();
+      // (the barrier's acquire has dropped L1: every load below is an L2 round trip, so all S + A of
+      // a column are issued before the first add; same summation order as the stepwise kernel)
       for (int i = tid; i < Hd; i += PO_THREADS) {
         float acc = 0.f;
-        for (int s = 0; s < S; ++s) acc += p.WinT[(size_t)sidx[s] * Hd + i];
+        if (S == 32) {
+          float w[32];
+#pragma unroll
+          for (int s = 0; s < 32; ++s) w[s] = __ldg(p.WinT + (size_t)sidx[s] * Hd + i);
+#pragma unroll
+          for (int s = 0; s < 32; ++s) acc += w[s];
+        } else {
+          for (int s = 0; s < S; ++s) acc += p.WinT[(size_t)sidx[s] * Hd + i];
+        }
         const float* wa = p.WinT + (size_t)SC * Hd + i;
-        for (int a = 0; a < A; ++a) acc = fmaf(sact[a], wa[(size_t)a * Hd], acc);
+        if (A <= 8) {
+          float w[8];
+#pragma unroll
+          for (int a = 0; a < 8; ++a) w[a] = a < A ? __ldg(wa + (size_t)a * Hd) : 0.f;
+#pragma unroll
+          for (int a = 0; a < 8; ++a) if (a < A) acc = fmaf(sact[a], w[a], acc);
+        } else {
+          for (int a = 0; a < A; ++a) acc = fmaf(sact[a], wa[(size_t)a * Hd], acc);
+        }
         buf[i] = acc;
         p.x_pre[bt * Hd + i] = acc;
       }
@@ -143,8 +171,11 @@ __global__ void __launch_bounds__(PO_THREADS, 1) observe_persistent_fwd_kernel(P
       }
       block_sum<1>(s2, red);
       const float rstd = 1.f / sqrtf(s2[0] / (float)Hd + p.eps);
-      for (int i = tid; i < Hd; i += PO_THREADS)
-        p.x[bt * Hd + i] = siluf_(fmaf((buf[i] - mean) * rstd, p.ln_in_g[i], p.ln_in_b[i]));
+      for (int i = tid, u = 0; i < Hd; i += PO_THREADS, ++u) {
+        const float gg = u < 4 ? lin_g[u < 4 ? u : 0] : p.ln_in_g[i];
+        const float bb = u < 4 ? lin_b[u < 4 ? u : 0] : p.ln_in_b[i];
+        p.x[bt * Hd + i] = siluf_(fmaf((buf[i] - mean) * rstd, gg, bb));
+      }
     }
     po_stamp(p, t, 1);
     grid_barrier(p.bar, G, gen);
@@ -295,7 +326,7 @@ __global__ void __launch_bounds__(PO_THREADS, 1) observe_persistent_fwd_kernel(P
       }
       __syncthreads();
       if (act && half == 0) {
-        const float l = valid ? (a0 + a1) + xch[rl * 32 + lane] + p.b_os[(size_t)gE * C + lane] : 0.f;
+        const float l = valid ? (a0 + a1) + xch[rl * 32 + lane] + bos : 0.f;
         const Unimix um = unimix_probs(l, valid, C, p.unimix);
         const int k = warp_argmax(um.probs / (-logf(uu)), valid, lane);
         if (valid) {

@@ -581,6 +581,10 @@ int dv3_col2im_s2k4(const float* cols, int32_t n, int32_t H, int32_t W, int32_t 
 /* Debug aid: with DV3_OBSERVE_TIMING=1 in the environment the persistent observe kernel stamps
  * %globaltimer (ns) at its 8 phase boundaries per step on CTA 0; this copies [T][8] stamps out. */
 int dv3_debug_observe_timing(unsigned long long* host, int32_t T);
+/* The same for the persistent imagination forward (DV3_IMAGINE_TIMING=1): [H][16] stamps of the
+ * first CTA's epilogue at the phase boundaries of each step (start, actor trunk, head, img_in, GRU,
+ * img_out, imgs_stat + draw). */
+int dv3_debug_imagine_timing(unsigned long long* host, int32_t H);
 
 #ifdef __cplusplus
 }

@@ -72,6 +72,21 @@ def test_imagine_fwd_bwd(pkg, device, config, N, H):
     _assert(pc.imagine_case(pkg, device, config=config, N=N, H=H))
 
 
+@pytest.mark.parametrize("config,N,H", [("dmc_proprio", 1024, 15), ("atari100k", 256, 15),
+                                        ("dmc_proprio", 128, 3)])
+def test_imagine_persistent_kernel(pkg, device, config, N, H, knob):
+    """DV3_IMAGINE_PERSISTENT=1: the whole rollout as one cooperative kernel (groups of 16 CTAs per
+    128 rows, every GEMM on tcgen05, LayerNorm / gates / draws in the epilogues) against the same
+    oracle and to the same bar as the stepwise launches: indices exact, floats 1e-4."""
+    knob("DV3_IMAGINE_PERSISTENT", "1")
+    before = pkg._lib.lib().dv3_launch_count()
+    res = pc.imagine_case(pkg, device, config=config, N=N, H=H, backward=False)
+    launches = pkg._lib.lib().dv3_launch_count() - before
+    assert launches < 20, launches              # state-0 set-up + one launch for all H steps
+    _assert(res)
+    _assert(pc.imagine_case(pkg, device, config=config, N=N, H=H))
+
+
 def test_policy_walk_public_methods(pkg, device):
     """Dreamer._policy (dreamer.py:117-190) through RSSM.obs_step(None, None, ...) / obs_step /
     img_step / get_feat / actor(feat): the acting path's public-method surface."""

@@ -170,6 +170,8 @@ SIGNATURES = {
                                     _i32, _i32, _v, C.c_size_t, _v]),
     "dv3_gemm_tc": (C.c_int, [_P(TcOperand), _i32, _P(TcOperand), _i32, _P(TcOperand), _f, _f, _i32,
                               _f, _i32, _i32, _i32, _i32, _v]),
+    "dv3_gemm_tc_rawa": (C.c_int, [_f, _i32, _i32, _f, _i32, _i32, _P(TcOperand), _f, _f, _i32, _f, _i32,
+                                   _i32, _i32, _v]),
     "dv3_split_tf32": (C.c_int, [_f, _i32, _i32, _i32, _f, _f, _i32, _v]),
     "dv3_linear_tc2_fwd": (C.c_int, [_f, _i32, _i32, _f, _i32, _i32, _f, _i32, _f, _f, _i32, _f,
                                      _i32, _i32, _i32, _i32, _v]),

@@ -269,6 +269,14 @@ struct TcOperand {
 int tc_gemm_ops(const TcOperand& A1, int K1, const TcOperand* A2, int K2, const TcOperand& B,
                 const float* bias, const float* addend, int ldadd, float* C, int ldc, int M, int N,
                 int accumulate, cudaStream_t st);
+// the same product from a plain fp32 A operand, split in the SM into tensor memory (dv3_umma2t.cu);
+// tc_gemm_rawa_ok: shapes / alignments the kernel covers
+bool tc_gemm_rawa_ok(const float* A1, int lda1, int K1, const float* A2, int lda2, int K2,
+                     const TcOperand& B, int M, int N);
+bool tc_gemm_rawa_single_wave(int M, int N);
+int tc_gemm_rawa(const float* A1, int lda1, int K1, const float* A2, int lda2, int K2,
+                 const TcOperand& B, const float* bias, const float* addend, int ldadd, float* C,
+                 int ldc, int M, int N, cudaStream_t st);
 // the same product on CTA pairs (cta_group::2, 256 x BN tiles; dv3_umma2x.cu)
 int tc_gemm_pair(const TcOperand& A1, int K1, const TcOperand* A2, int K2, const TcOperand& B,
                  const float* bias, const float* addend, int ldadd, float* C, int ldc, int M, int N,
@@ -357,6 +365,19 @@ struct LinW {
         b{hi, lo, ldp ? ldp : K, mn};
     if (a2) { o2.hi = a2->hi; o2.lo = a2->lo; o2.ld = a2->ld; }
     return tc_gemm_ops(o1, K1, a2 ? &o2 : nullptr, K2, b, bias, addend, ldadd, C, ldc, M, N, 0, st);
+  }
+  // C = [A1|A2] W^T from the fp32 activations (A split in the SM into tensor memory); false when
+  // the raw-A kernel does not cover the shapes -> the caller uses apply_split
+  bool rawa_ok(const float* A1, int lda1, int K1, const float* A2, int lda2, int K2, int M) const {
+    if (!tc || !tc_gemm_rawa_single_wave(M, N)) return false;
+    TcOperand b{hi, lo, ldp ? ldp : K, mn};
+    return tc_gemm_rawa_ok(A1, lda1, K1, A2, lda2, A2 ? K2 : 0, b, M, N);
+  }
+  int apply_rawa(const float* A1, int lda1, int K1, const float* A2, int lda2, int K2,
+                 const float* bias, const float* addend, int ldadd, float* C, int ldc, int M,
+                 cudaStream_t st) const {
+    TcOperand b{hi, lo, ldp ? ldp : K, mn};
+    return tc_gemm_rawa(A1, lda1, K1, A2, lda2, A2 ? K2 : 0, b, bias, addend, ldadd, C, ldc, M, N, st);
   }
   // ascr: 2*M*K floats of scratch (only used on the tensor-core path)
   int apply(const float* A1, int lda1, int K1, const float* A2, int lda2, int K2, const float* bias,

@@ -277,9 +277,15 @@ extern "C" int dv3_imagine_fwd(const dv3_rssm_dims* d, const dv3_rssm_params* p,
   }
   // C = [A1|A2] W^T: from the producers' hi/lo planes on the tensor-core path, from the fp32
   // activations on the CUDA-core path (N < 64 rows)
+  const char* e_rawa = DV3_ENV("DV3_TC_RAWA");
+  const bool rawa = !(e_rawa && e_rawa[0] == '0');
   auto lin = [&](const LinW& W, const float* A1, int lda1, int K1, const SplitOut& s1,
                  const float* A2, int lda2, int K2, const SplitOut* s2, const float* bias, float* Cc,
                  int ldc) -> int {
+    // fp32 A split in the SM into tensor memory where that kernel covers the shape (bit-identical
+    // to the pre-split product with the same tile; DV3_TC_RAWA=0 keeps the planes)
+    if (rawa && W.rawa_ok(A1, lda1, K1, A2, lda2, K2, N))
+      return W.apply_rawa(A1, lda1, K1, A2, lda2, K2, bias, nullptr, 0, Cc, ldc, N, st);
     if (W.tc) return W.apply_split(s1, K1, A2 ? s2 : nullptr, K2, bias, nullptr, 0, Cc, ldc, N, st);
     return W.apply(A1, lda1, K1, A2, lda2, K2, bias, nullptr, 0, Cc, ldc, N, nullptr, st);
   };
@@ -471,8 +477,12 @@ extern "C" int dv3_imagine_bwd(const dv3_rssm_dims* d, const dv3_rssm_params* p,
   DV3_TRY(fill_zero(w.dxh_add, (size_t)N * (Hd + D) * 4, st));
 
   // C = A W^T with A = a delta the producing kernel also wrote as hi/lo planes
+  const char* e_rawa = DV3_ENV("DV3_TC_RAWA");
+  const bool rawa = !(e_rawa && e_rawa[0] == '0');
   auto blin = [&](const LinW& W, const float* A1, int lda, int K, const SplitOut& sp,
                   const float* addend, int ldadd, float* Cc, int ldc) -> int {
+    if (rawa && K <= 640 && W.rawa_ok(A1, lda, K, nullptr, 0, 0, N))     // long K: cluster split-K wins
+      return W.apply_rawa(A1, lda, K, nullptr, 0, 0, nullptr, addend, ldadd, Cc, ldc, N, st);
     if (W.tc) return W.apply_split(sp, K, nullptr, 0, nullptr, addend, ldadd, Cc, ldc, N, st);
     return W.apply(A1, lda, K, nullptr, 0, 0, nullptr, addend, ldadd, Cc, ldc, N, nullptr, st);
   };

@@ -454,6 +454,29 @@ def gemm_tc(A, B, a_t=False, b_t=False, A2=None, bias=None, addend=None, out=Non
     return out
 
 
+def gemm_tc_rawa(a, B, b_t=False, a2=None, bias=None, addend=None, out=None):
+    """C[M,N] = [a | a2] op(B)^T (+bias +addend) with the A operand as plain fp32 rows: the tile is
+    split inside the SM and fed to the tensor core from tensor memory (dv3_umma2t.cu); B is a Split
+    (tensors are split on the fly).  Bit-identical to gemm_tc on the same tile; M >= 64."""
+    B = split(B)
+    M, K1 = a.shape
+    K2 = a2.shape[1] if a2 is not None else 0
+    N, K = (B.cols, B.rows) if b_t else (B.rows, B.cols)
+    if K1 + K2 != K:
+        raise L.Dv3Error(f"gemm_tc_rawa: contraction mismatch {K1}+{K2} vs {K}")
+    if a.stride(1) != 1 or (a2 is not None and a2.stride(1) != 1):
+        raise L.Dv3Error("gemm_tc_rawa: A rows must be contiguous")
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float32, device=a.device)
+    b = B.operand(b_t)
+    L.check(L.lib().dv3_gemm_tc_rawa(_raw(a), a.stride(0), K1, _raw(a2),
+                                     a2.stride(0) if a2 is not None else 0, K2, C.byref(b),
+                                     L.fptr(bias), _raw(addend),
+                                     addend.stride(0) if addend is not None else 0, _raw(out),
+                                     out.stride(0), M, N, L.stream_ptr()), "gemm_tc_rawa")
+    return out
+
+
 def linear_tc(a, w, bias=None, addend=None, trans_a=False, trans_w=False):
     """C[M,N] = op(a) op(w)^T (+bias +addend), fp32-accurate on the tensor cores.  op(a) is
     [M,K] (a stored [K,M] when trans_a); op(w) is [N,K] (w stored [K,N] when trans_w)."""

@@ -393,6 +393,13 @@ int dv3_linear_tc_fwd(const float* A, int32_t lda, int32_t transA, const float* 
 int dv3_gemm_tc(const dv3_tc_operand* A1, int32_t K1, const dv3_tc_operand* A2, int32_t K2,
                 const dv3_tc_operand* B, const float* bias, const float* addend, int32_t ldadd,
                 float* C, int32_t ldc, int32_t M, int32_t N, int32_t accumulate, void* stream);
+/* The same product with the A operand as plain fp32 ([M, K] row-major, 16-byte aligned, row strides
+ * % 4 == 0) and B as tf32 planes: the fp32 tile is split in the SM and fed to the tensor core from
+ * tensor memory (dv3_umma2t.cu) -- half the A bytes per k-block of dv3_gemm_tc, bit-identical
+ * results.  For the skinny products of the time loops (M >= 64; K1 % 32 == 0 when A2 is given). */
+int dv3_gemm_tc_rawa(const float* A1, int32_t lda1, int32_t K1, const float* A2, int32_t lda2,
+                     int32_t K2, const dv3_tc_operand* B, const float* bias, const float* addend,
+                     int32_t ldadd, float* C, int32_t ldc, int32_t M, int32_t N, void* stream);
 /* hi = x with the 13 low mantissa bits cleared, lo = x - hi; x is [rows, cols] with row stride
  * ld, the planes have row stride ld_out >= cols (pad columns are zeroed). */
 int dv3_split_tf32(const float* x, int32_t ld, int32_t rows, int32_t cols, float* hi, float* lo,

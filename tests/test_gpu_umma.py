@@ -206,3 +206,33 @@ def test_gemm_forced_tilings_agree(pkg, device, knob, force, M, N, K):
         At, Bt = pkg.kernels.split(a.t().contiguous()), pkg.kernels.split(b.t().contiguous())
         out = pkg.kernels.gemm_tc(At, Bt, a_t=True, b_t=True)
         assert float((out.double() - ref).abs().max() / ref.abs().max()) < 5e-6
+
+
+@pytest.mark.parametrize("M,N,K1,K2,b_t,force", [
+    (1024, 512, 512, 0, False, None), (1024, 1536, 512, 512, False, None), (1024, 1024, 512, 0, False, None),
+    (1024, 512, 512, 0, True, None), (1024, 1030, 512, 0, True, None), (1000, 130, 100, 0, False, None),
+    (64, 8, 4, 0, False, None), (257, 520, 96, 36, False, "64"), (1024, 1536, 512, 512, False, "32"),
+    (300, 96, 1024, 0, True, "64"), (2048, 1536, 512, 512, False, "96")])
+def test_gemm_rawa_tmem_operand(pkg, device, knob, M, N, K1, K2, b_t, force):
+    """The raw-A kernel (fp32 A split in the SM, tcgen05.mma with A from tensor memory) against fp64
+    and, where the pre-split kernel picks the same 128 x BN single-CTA tile, bit for bit against it."""
+    if force:
+        knob("DV3_TCT_FORCE", force)
+    g = torch.Generator().manual_seed(M + 3 * N + 5 * K1 + K2)
+    K = K1 + K2
+    a = torch.randn(M, K1, generator=g).to(device)
+    a2 = torch.randn(M, K2, generator=g).to(device) if K2 else None
+    w = (torch.randn(K, N, generator=g) if b_t else torch.randn(N, K, generator=g)).to(device) / K ** 0.5
+    bias = torch.randn(N, generator=g).to(device)
+    add = torch.randn(M, N + 4, generator=g).to(device)[:, :N]          # strided addend
+    full = torch.cat([a, a2], 1) if K2 else a
+    ref = full.double() @ (w.double() if b_t else w.double().t())
+    out = pkg.kernels.gemm_tc_rawa(a, w, b_t=b_t, a2=a2)
+    assert float((out.double() - ref).abs().max() / ref.abs().max()) < 5e-6
+    out2 = pkg.kernels.gemm_tc_rawa(a, w, b_t=b_t, a2=a2, bias=bias, addend=add)
+    ref2 = ref + bias.double() + add.double()
+    assert float((out2.double() - ref2).abs().max() / ref2.abs().max()) < 5e-6
+    if (M, N, K1, K2) == (1024, 512, 512, 0) and not force:
+        knob("DV3_TC_FORCE", "32,0")
+        same = pkg.kernels.gemm_tc(a, w, b_t=b_t)
+        assert torch.equal(same, out)

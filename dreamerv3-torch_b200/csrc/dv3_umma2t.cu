@@ -21,8 +21,10 @@
 //    land ~900 ns later -- the per-SM TMA path at this box pattern (128-byte rows) is the pacer at
 //    0.30-0.33 us per k-block, for the pre-split kernel (40 KB per k-block) and for this one (24 KB).
 //  * variants that did not move that pace: two MMA issuer warps on alternate chunks; stage release
-//    in pairs (one commit point per two k-blocks); four instead of eight converter warps.  Loading A
-//    with per-thread LDG.128 instead of TMA is 2x slower (per-lane rows, latency-bound).
+//    in pairs (one commit point per two k-blocks); four instead of eight converter warps.  Two
+//    producer threads (A tiles | B tiles) are 8 % slower -- the TMA unit, not the issuing thread, is
+//    the limit -- and loading A with per-thread LDG.128 instead of TMA is 2x slower (per-lane rows,
+//    latency-bound).
 // Net: 8-13 % faster than the pre-split kernel on the in-loop shapes (1024 x 512 x 512: 9.5 -> 8.6 us,
 // the GRU product 1024 x 1536 x 1024: 22.8 -> 20.2 us with single-wave 128 x 96 tiles); used for
 // single-wave launches only -- multi-wave products are tensor-pipe bound and stay on CTA pairs.

@@ -23,6 +23,12 @@ CONFIGS = {
                       actor_layers=2, actor_dist="onehot"),            # 176-190
     "large": dict(dims=dict(deter=4096, hidden=1024, actions=17, embed=12288), units=1024,
                   actor_layers=5, actor_dist="onehot"),                # 165-173, 203-212
+    # default widths with 1 / 3 actor layers and 16 continuous / 32 discrete actions: the corner
+    # cases of the persistent imagination kernel (test-only shapes, not reference configs)
+    "wide_l1": dict(dims=dict(deter=512, hidden=512, actions=16, embed=1024), units=512,
+                    actor_layers=1, actor_dist="normal"),
+    "wide_l3": dict(dims=dict(deter=512, hidden=512, actions=32, embed=1024), units=512,
+                    actor_layers=3, actor_dist="onehot"),
     # reduced widths for fast CPU-side checks
     "tiny": dict(dims=dict(stoch=8, classes=8, deter=64, hidden=48, actions=3, embed=40),
                  units=32, actor_layers=2, actor_dist="normal"),

@@ -73,7 +73,8 @@ def test_imagine_fwd_bwd(pkg, device, config, N, H):
 
 
 @pytest.mark.parametrize("config,N,H", [("dmc_proprio", 1024, 15), ("atari100k", 256, 15),
-                                        ("dmc_proprio", 128, 3)])
+                                        ("dmc_proprio", 128, 3), ("wide_l1", 256, 4), ("wide_l3", 384, 5),
+                                        ("dmc_proprio", 128, 1)])
 def test_imagine_persistent_kernel(pkg, device, config, N, H, knob):
     """DV3_IMAGINE_PERSISTENT=1: the whole rollout as one cooperative kernel (groups of 16 CTAs per
     128 rows, every GEMM on tcgen05, LayerNorm / gates / draws in the epilogues) against the same

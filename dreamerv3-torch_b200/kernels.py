@@ -12,7 +12,10 @@ the forward product and both backward products in either storage order.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
+
+import os
 
 import torch
 import torch.nn.functional as F
@@ -296,6 +299,33 @@ def disarm_grad_sink(params):
 
 
 _SUNK = object()     # marker: this gradient went into the sink (autograd gets None)
+
+# Parameter-gradient work that nothing downstream in the backward pass depends on (the bulk dW
+# products of the RSSM after the observe recurrence) runs on a side stream, i.e. as a parallel branch
+# of the captured step graph under the encoder's backward; in data-parallel runs the all-reduce of
+# that slice of the flat gradient follows on the same stream.  The optimizer joins the stream before
+# it reads the gradient (join_grad_streams).  DV3_OBS_DW_SIDE=0 keeps everything on one stream.
+_GRAD_STREAMS = {}
+_GRAD_PENDING = []   # (stream, tensors the branch reads that were allocated on another stream)
+
+
+def grad_side_enabled():
+    return os.environ.get("DV3_OBS_DW_SIDE", "1") != "0"
+
+
+def grad_side_stream(device):
+    dev = torch.device(device)
+    st = _GRAD_STREAMS.get(dev)
+    if st is None:
+        st = _GRAD_STREAMS[dev] = torch.cuda.Stream(device=dev)
+    return st
+
+
+def join_grad_streams():
+    cur = torch.cuda.current_stream()
+    for st, _keep in _GRAD_PENDING:
+        cur.wait_stream(st)
+    _GRAD_PENDING.clear()
 
 
 def _sink_of(pid):
@@ -804,75 +834,83 @@ class _Observe(torch.autograd.Function):
         pid = dict(zip(L.RSSM_PARAM_FIELDS, ctx.pids))
         need = dict(zip(L.RSSM_PARAM_FIELDS, ctx.needs_input_grad[8:]))
         G = {k: None for k in L.RSSM_PARAM_FIELDS}
-        if any(need.values()):
-            r2 = lambda t: t.reshape(B * T, -1)
-            hot = torch.empty(B * T, SC, dtype=torch.float32, device=dev)
-            L.check(L.lib().dv3_idx_to_onehot(L.iptr(sprev_idx.reshape(B * T, S)), B * T, S, Cc,
-                                              L.fptr(hot), SC, L.stream_ptr()), "idx_to_onehot")
-            dx, dg, dy, dz = (split(r2(o[k])) for k in ("d_x_pre", "d_g_pre", "d_y_pre", "d_z_pre"))
-            dpo, dpr = r2(o["d_post_logit"]), r2(o["d_prior_logit"])
-            dpos, dprs = split(dpo), split(dpr)
-            deters = split(r2(deter))
+        side = None
+        if any(need.values()) and grad_side_enabled() and all(
+                _sink_of(pid[k]) is not None for k in L.RSSM_PARAM_FIELDS if need[k]):
+            # every RSSM gradient goes into the armed sink and nothing downstream reads it: fork
+            side = grad_side_stream(dev)
+            side.wait_stream(torch.cuda.current_stream())
+            _GRAD_PENDING.append((side, (o, ctx.saved_tensors, ws)))
+        with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+            if any(need.values()):
+                r2 = lambda t: t.reshape(B * T, -1)
+                hot = torch.empty(B * T, SC, dtype=torch.float32, device=dev)
+                L.check(L.lib().dv3_idx_to_onehot(L.iptr(sprev_idx.reshape(B * T, S)), B * T, S, Cc,
+                                                  L.fptr(hot), SC, L.stream_ptr()), "idx_to_onehot")
+                dx, dg, dy, dz = (split(r2(o[k])) for k in ("d_x_pre", "d_g_pre", "d_y_pre", "d_z_pre"))
+                dpo, dpr = r2(o["d_post_logit"]), r2(o["d_prior_logit"])
+                dpos, dprs = split(dpo), split(dpr)
+                deters = split(r2(deter))
 
-            # dW = delta^T @ input over all B*T rows: transposed-operand tcgen05 products with the
-            # rows (K = B*T) partitioned over the SMs, accumulated into the optimizer's flat
-            # gradient buffer when it is armed (else into fresh tensors); column blocks of one
-            # weight are written through strided output views
-            def dw(name, d, inp, cols=None):
-                if _sink_gemm(pid[name], d, inp, cols) is not None:
-                    G[name] = _SUNK
-                elif cols is None:
-                    G[name] = gemm_tc(d, inp, a_t=True, b_t=True, split_k=True)
-                else:
-                    if G[name] is None:
-                        G[name] = torch.empty(P[name].shape, dtype=torch.float32, device=dev)
-                    gemm_tc(d, inp, a_t=True, b_t=True, out=G[name][:, cols[0]:cols[1]], split_k=True)
+                # dW = delta^T @ input over all B*T rows: transposed-operand tcgen05 products with the
+                # rows (K = B*T) partitioned over the SMs, accumulated into the optimizer's flat
+                # gradient buffer when it is armed (else into fresh tensors); column blocks of one
+                # weight are written through strided output views
+                def dw(name, d, inp, cols=None):
+                    if _sink_gemm(pid[name], d, inp, cols) is not None:
+                        G[name] = _SUNK
+                    elif cols is None:
+                        G[name] = gemm_tc(d, inp, a_t=True, b_t=True, split_k=True)
+                    else:
+                        if G[name] is None:
+                            G[name] = torch.empty(P[name].shape, dtype=torch.float32, device=dev)
+                        gemm_tc(d, inp, a_t=True, b_t=True, out=G[name][:, cols[0]:cols[1]], split_k=True)
 
-            def ln(gname, bname, pre, dln):
-                a, b_ = _ln_grads(r2(pre), r2(dln), pid[gname], pid[bname])
-                G[gname], G[bname] = (_SUNK, _SUNK) if a is None else (a, b_)
+                def ln(gname, bname, pre, dln):
+                    a, b_ = _ln_grads(r2(pre), r2(dln), pid[gname], pid[bname])
+                    G[gname], G[bname] = (_SUNK, _SUNK) if a is None else (a, b_)
 
-            def bias(name, d2d):
-                r = _bias_grad(d2d, pid[name])
-                G[name] = _SUNK if r is None else r
+                def bias(name, d2d):
+                    r = _bias_grad(d2d, pid[name])
+                    G[name] = _SUNK if r is None else r
 
-            dw("w_in", dx, hot, (0, SC))
-            dw("w_in", dx, r2(aprev), (SC, SC + A))
-            ln("ln_in_g", "ln_in_b", x_pre, o["d_x_ln"])
-            dw("w_gru", dg, r2(x), (0, Hd))
-            dw("w_gru", dg, r2(hprev), (Hd, Hd + D))
-            ln("ln_gru_g", "ln_gru_b", g_pre, o["d_g_ln"])
-            dw("w_out", dy, deters)
-            ln("ln_out_g", "ln_out_b", y_pre, o["d_y_ln"])
-            dw("w_ims", dprs, r2(y))
-            bias("b_ims", dpr)
-            dw("w_obs", dz, deters, (0, D))
-            dw("w_obs", dz, r2(embed), (D, D + E))
-            ln("ln_obs_g", "ln_obs_b", z_pre, o["d_z_ln"])
-            dw("w_os", dpos, r2(z))
-            bias("b_os", dpo)
-            # RSSM.initial (networks.py:99-125): tanh(W) -> prior head -> mode (straight-through
-            # on the normalised log-probs).  One row: dv3_rssm_initial_bwd adds its six parameter
-            # gradients onto the bulk sums (the armed sink views, or the tensors built above).
-            names = ["w_init", "w_out", "ln_out_g", "ln_out_b", "w_ims", "b_ims"]
-            bufs = {}
-            for k in names:
-                view = _sink_of(pid[k])
-                if view is not None:
-                    bufs[k] = view
-                    _SINK_DIRTY.add(pid[k])
-                    G[k] = _SUNK
-                else:
-                    if G[k] is None or G[k] is _SUNK:
-                        G[k] = torch.zeros(P[k].shape, dtype=torch.float32, device=dev)
-                    bufs[k] = G[k]
-            scr = f(int(L.lib().dv3_rssm_initial_bwd_scratch_floats(C.byref(d))))
-            L.check(L.lib().dv3_rssm_initial_bwd(
-                C.byref(d), C.byref(pst), L.fptr(init_deter), L.fptr(init_ypre), L.fptr(init_y),
-                L.fptr(init_logit), L.fptr(o["d_init_stoch"]), L.fptr(o["d_init_deter"]),
-                L.fptr(bufs["w_init"]), L.fptr(bufs["w_out"]), L.fptr(bufs["ln_out_g"]),
-                L.fptr(bufs["ln_out_b"]), L.fptr(bufs["w_ims"]), L.fptr(bufs["b_ims"]), L.fptr(scr),
-                L.stream_ptr()), "rssm_initial_bwd")
+                dw("w_in", dx, hot, (0, SC))
+                dw("w_in", dx, r2(aprev), (SC, SC + A))
+                ln("ln_in_g", "ln_in_b", x_pre, o["d_x_ln"])
+                dw("w_gru", dg, r2(x), (0, Hd))
+                dw("w_gru", dg, r2(hprev), (Hd, Hd + D))
+                ln("ln_gru_g", "ln_gru_b", g_pre, o["d_g_ln"])
+                dw("w_out", dy, deters)
+                ln("ln_out_g", "ln_out_b", y_pre, o["d_y_ln"])
+                dw("w_ims", dprs, r2(y))
+                bias("b_ims", dpr)
+                dw("w_obs", dz, deters, (0, D))
+                dw("w_obs", dz, r2(embed), (D, D + E))
+                ln("ln_obs_g", "ln_obs_b", z_pre, o["d_z_ln"])
+                dw("w_os", dpos, r2(z))
+                bias("b_os", dpo)
+                # RSSM.initial (networks.py:99-125): tanh(W) -> prior head -> mode (straight-through
+                # on the normalised log-probs).  One row: dv3_rssm_initial_bwd adds its six parameter
+                # gradients onto the bulk sums (the armed sink views, or the tensors built above).
+                names = ["w_init", "w_out", "ln_out_g", "ln_out_b", "w_ims", "b_ims"]
+                bufs = {}
+                for k in names:
+                    view = _sink_of(pid[k])
+                    if view is not None:
+                        bufs[k] = view
+                        _SINK_DIRTY.add(pid[k])
+                        G[k] = _SUNK
+                    else:
+                        if G[k] is None or G[k] is _SUNK:
+                            G[k] = torch.zeros(P[k].shape, dtype=torch.float32, device=dev)
+                        bufs[k] = G[k]
+                scr = f(int(L.lib().dv3_rssm_initial_bwd_scratch_floats(C.byref(d))))
+                L.check(L.lib().dv3_rssm_initial_bwd(
+                    C.byref(d), C.byref(pst), L.fptr(init_deter), L.fptr(init_ypre), L.fptr(init_y),
+                    L.fptr(init_logit), L.fptr(o["d_init_stoch"]), L.fptr(o["d_init_deter"]),
+                    L.fptr(bufs["w_init"]), L.fptr(bufs["w_out"]), L.fptr(bufs["ln_out_g"]),
+                    L.fptr(bufs["ln_out_b"]), L.fptr(bufs["w_ims"]), L.fptr(bufs["b_ims"]), L.fptr(scr),
+                    L.stream_ptr()), "rssm_initial_bwd")
         grads = [G[k] if need[k] and G[k] is not _SUNK else None for k in L.RSSM_PARAM_FIELDS]
         d_embed = o["d_embed"] if ctx.needs_input_grad[0] else None
         return (d_embed, None, None, None, None, None, d_state_deter, None, *grads)

@@ -151,6 +151,12 @@ class WorldModel(nn.Module):
                 rng = self._model_opt.param_range(list(head.parameters()))
                 if rng is not None:
                     segs.append((rng[0], rng[1], streams[i]))
+            if K.grad_side_enabled():
+                # the RSSM's parameter gradients are produced on the gradient side stream (a branch
+                # under the encoder's backward, kernels._Observe.backward): reduce them there
+                rng = self._model_opt.param_range(list(self.dynamics.parameters()))
+                if rng is not None:
+                    segs.append((rng[0], rng[1], K.grad_side_stream(feat.device)))
             self._model_opt.set_segments(segs or None)
         # model_loss = mean(sum_k scale_k * (-log_prob_k) + kl_loss) (reference models.py:140-152)
         names = list(logps)

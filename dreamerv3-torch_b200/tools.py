@@ -557,6 +557,8 @@ class Optimizer:
             loss.backward(retain_graph=retain_graph)
         finally:
             written = K.disarm_grad_sink(params)
+        if self._sync is None or not getattr(self, "_segments", None):
+            K.join_grad_streams()                # (data parallel: joined behind the segments' all-reduce)
         skipped = []
         with torch.no_grad():
             for i, (p, view, w) in enumerate(zip(params, self._gviews, written)):
@@ -578,6 +580,7 @@ class Optimizer:
             keep = [(pv[i], pv[i].clone(), mv[i], mv[i].clone(), vv[i], vv[i].clone()) for i in skipped]
         if self._sync is not None:
             self._sync.flat(self._fg, getattr(self, "_segments", None))
+            K.join_grad_streams()
         L_ = K.L
         L_.check(L_.lib().dv3_adam_clip_step_planes(
             L_.fptr(self._fp), L_.fptr(self._fg), L_.fptr(self._fm), L_.fptr(self._fv),

@@ -188,7 +188,7 @@ def host_batch(suite, cfg, seed):
     return host
 
 
-def suite_rate(pkg, suite, device, steps=20):
+def suite_rate(pkg, suite, device, steps=20, pipeline=False):
     """Train steps/s of another BASELINE suite (configs[1] dmc_vision, configs[2] atari100k) through
     the same graphs.TrainStepGraph API, batch resident in HBM, CUDA events."""
     import torch
@@ -199,7 +199,7 @@ def suite_rate(pkg, suite, device, steps=20):
     wm = pkg.models.WorldModel(cfgs.ObsSpace(shapes), None, 0, cfg)
     beh = pkg.models.ImagBehavior(cfg, wm)
     batch = {k: torch.from_numpy(v).to(device) for k, v in host_batch(suite, cfg, 0).items()}
-    graph = pkg.graphs.TrainStepGraph(wm, beh, warmup=2, device_metrics=True)
+    graph = pkg.graphs.TrainStepGraph(wm, beh, warmup=2, device_metrics=True, pipeline=pipeline)
     for _ in range(6):
         graph(batch)
     torch.cuda.synchronize()
@@ -212,6 +212,7 @@ def suite_rate(pkg, suite, device, steps=20):
     ms = e0.elapsed_time(e1) / steps
     out = {"train_steps_per_s": 1e3 / ms, "ms_per_step": ms, "steps": steps,
            "library_launches_per_step": graph.library_launches_per_step,
+           "schedule": "pipelined" if pipeline else "sequential",
            "workload": workload_string(suite)}
     del graph, wm, beh
     torch.cuda.empty_cache()
@@ -339,7 +340,8 @@ def run_ours(args):
             print(f"[bench rank {rank}] {msg}", file=sys.stderr, flush=True)
 
     never = 1 << 30 if args.no_graph else 2
-    graph = pkg.graphs.TrainStepGraph(wm, beh, reward_fn, warmup=never, device_metrics=True)
+    graph = pkg.graphs.TrainStepGraph(wm, beh, reward_fn, warmup=never, device_metrics=True,
+                                      pipeline=(args.schedule == "pipelined"))
     W = max(args.warmup, 3)
     stage("warm-up / capture")
     for i in range(W + 3):                    # 2 eager + capture + >= W replays
@@ -478,11 +480,22 @@ def run_ours(args):
         "clocks": sampler.summary() if sampler else None,
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),
+        "schedule": {
+            "name": args.schedule,
+            "what": ("each call = the world-model update of the batch passed in + the actor / critic update of "
+                     "the previous batch, the two running concurrently (the behaviour update only reads the "
+                     "world model; Adam follows the join): one WM + one AC update per call, the same updates "
+                     "on the same inputs as Dreamer._train's order -- tests/test_gpu_graph.py::"
+                     "test_pipelined_schedule_matches_sequential; `sequential_schedule` in this line is the "
+                     "same workload in the reference's own order")
+            if args.schedule == "pipelined" else
+            "Dreamer._train's own order: WorldModel._train then ImagBehavior._train on the same batch"},
         "imagined_states_per_s": imag_states,
         "imagine_fwd_ms": imag_ms,
         "roofline": {
-            "kernel": "umma2x_gemm_kernel / umma2_gemm_kernel (persistent tcgen05 3xTF32 GEMM on CTA pairs / single "
-                      "CTAs: every imagination-step and bulk-row contraction, y / dx / dW; dominant by time)",
+            "kernel": "umma2x_gemm_kernel / umma2_gemm_kernel / umma2t_gemm_kernel (persistent tcgen05 3xTF32 GEMM on "
+                      "CTA pairs / single CTAs / with the A operand fed from tensor memory: every imagination-step "
+                      "and bulk-row contraction, y / dx / dW; dominant by time)",
             "bound": "tensor", "achieved": ach, "peak": peaks["tf"], "unit": "TFLOP/s",
             "frac": ach / peaks["tf"], "traffic": _ncu_traffic(),
             "traffic_note": "mean DRAM bytes per GEMM launch (ncu dram__bytes_read.sum + dram__bytes_write.sum over "
@@ -509,12 +522,19 @@ def run_ours(args):
             line["large_imagination"] = li
         except Exception as e:      # informational only
             line["large_imagination"] = {"error": str(e)[:160]}
+        pipe = args.schedule == "pipelined"
+        try:
+            # the same suite on the OTHER schedule (a fresh agent), so that the line carries both
+            alt = suite_rate(pkg, args.suite, device, steps=30, pipeline=not pipe)
+            line["sequential_schedule" if pipe else "pipelined_schedule"] = alt
+        except Exception as e:      # informational only
+            line["sequential_schedule" if pipe else "pipelined_schedule"] = {"error": str(e)[:160]}
         line["other_suites"] = {}
         for other in ("dmc_vision", "atari100k"):
             if other == args.suite:
                 continue
             try:
-                line["other_suites"][other] = suite_rate(pkg, other, device)
+                line["other_suites"][other] = suite_rate(pkg, other, device, pipeline=pipe)
             except Exception as e:      # informational only
                 line["other_suites"][other] = {"error": f"{type(e).__name__}: {str(e)[:160]}"}
     if world == 1 and not args.no_cpu_baseline:
@@ -548,6 +568,11 @@ def main():
     ap.add_argument("--suite", default="dmc_proprio", choices=["dmc_proprio", "dmc_vision", "atari100k"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run every step eagerly (debugging)")
+    ap.add_argument("--schedule", default="pipelined", choices=["sequential", "pipelined"],
+                    help="pipelined (default): the behaviour update of batch t overlaps the world-model "
+                         "forward + backward of batch t+1 (graphs.TrainStepGraph(pipeline=True)): the "
+                         "same updates on the same inputs as the sequential schedule (tested), one "
+                         "WM + one AC update per call; sequential: Dreamer._train's own order")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -8,6 +8,16 @@ Inputs are copied into static device tensors before each replay (asynchronously 
 host memory); sampling noise is drawn inside the graph from torch's graph-safe generator, or
 supplied per call (``noise=dict(u_prior, u_post, act_noise, u_state)``, staged like the batch);
 metrics come back as device scalars, or as numpy after one stacked device->host copy.
+
+``pipeline=True`` -- the PIPELINED schedule.  The behaviour update of batch t only READS the world
+model (it imagines with the weights the world-model update of batch t produced and trains actor and
+critic), and the world-model forward + backward of batch t+1 reads the same weights; so call t+1 runs
+``ImagBehavior._train`` of batch t on a second stream, concurrently with ``WorldModel`` forward +
+backward of batch t+1, joins, and only then applies the world model's Adam.  Both halves are made of
+latency-bound kernels that leave most of the GPU idle on their own.  Every update sees exactly the
+inputs it sees in the sequential schedule -- the parameter trajectories are identical (tested bit for
+bit) -- but the actor / critic update of the batch passed to call t lands during call t+1 (``flush()``
+applies the last one), and the ``beh_metrics`` / ``imag_*`` a call returns belong to the previous batch.
 """
 from __future__ import annotations
 
@@ -18,8 +28,12 @@ from . import tools
 
 
 class TrainStepGraph:
-    def __init__(self, world_model, behavior, objective=None, warmup=3, device_metrics=False):
+    def __init__(self, world_model, behavior, objective=None, warmup=3, device_metrics=False,
+                 pipeline=False):
         self.wm, self.beh = world_model, behavior
+        self.pipeline = bool(pipeline)
+        self._start = None                   # static start states of the pending behaviour update
+        self._pending_noise = None
         if objective is None:
             objective = lambda f, s, a: world_model.heads["reward"](
                 world_model.dynamics.get_feat(s)).mode()
@@ -35,6 +49,9 @@ class TrainStepGraph:
         # remember the stream they were created on, and the legacy default stream must not be
         # made to wait on a capturing stream
         self._stream = torch.cuda.Stream(device=world_model._config.device)
+        self._beh_stream = torch.cuda.Stream(device=world_model._config.device)
+        if self.pipeline:
+            self.warmup = max(self.warmup, 2)    # the prologue (world model only) + one eager body
         cfg = world_model._config
         if cfg.critic["slow_target"] and cfg.critic["slow_target_update"] != 1:
             raise NotImplementedError("graph capture bakes in the slow-critic update of every "
@@ -72,12 +89,71 @@ class TrainStepGraph:
             n1 = (staged["__noise_u_prior"], staged["__noise_u_post"])
             n2 = (staged["__noise_act_noise"], staged["__noise_u_state"])
         try:
+            if self.pipeline:
+                return self._run_pipelined(batch, n1, n2)
             post, context, m1 = self.wm._train(batch, noise=n1)
             feat, state, action, weights, m2 = self.beh._train(post, self.objective, noise=n2)
         finally:
             cfg.device_metrics = keep
         return dict(post=post, context=context, wm_metrics=m1, imag_feat=feat, imag_state=state,
                     imag_action=action, weights=weights, beh_metrics=m2)
+
+    # -- pipelined schedule ----------------------------------------------------------------
+    def _stash(self, post):
+        """The posterior of this batch -> the static start-state buffers the NEXT call's behaviour
+        update reads (fixed addresses: the captured graph feeds itself through them)."""
+        dyn = self.wm.dynamics
+        idx = dyn._to_idx(post["stoch"])
+        if self._start is None:
+            self._start = {k: torch.empty_like(v) for k, v in post.items()}
+            self._start_idx = torch.empty_like(idx)
+        for k, v in post.items():
+            self._start[k].copy_(v)
+        self._start_idx.copy_(idx)
+        dyn.tag_idx(self._start["stoch"], self._start_idx)
+
+    def _run_pipelined(self, batch, n1, n2):
+        if self._start is None:
+            # prologue: nothing to train the behaviour on yet
+            post, context, m1 = self.wm._train(batch, noise=n1)
+            self._stash(post)
+            return dict(post=post, context=context, wm_metrics=m1, imag_feat=None, imag_state=None,
+                        imag_action=None, weights=None, beh_metrics={})
+        cur = torch.cuda.current_stream()
+        sb = self._beh_stream
+        sb.wait_stream(cur)
+        with torch.cuda.stream(sb):          # batch t: reads the world model, updates actor / critic
+            feat, state, action, weights, m2 = self.beh._train(self._start, self.objective, noise=n2)
+        st = self.wm._train_begin(batch, noise=n1)      # batch t+1: forward + backward, no update yet
+        cur.wait_stream(sb)
+        post, context, m1 = self.wm._train_end(st)      # ... now the world model may change
+        self._stash(post)
+        return dict(post=post, context=context, wm_metrics=m1, imag_feat=feat, imag_state=state,
+                    imag_action=action, weights=weights, beh_metrics=m2)
+
+    def flush(self, noise=None):
+        """Pipelined schedule: apply the behaviour update of the last batch (eagerly).  Returns its
+        (feat, state, action, weights, metrics), or None when nothing is pending."""
+        if not self.pipeline or self._start is None:
+            return None
+        cfg = self.wm._config
+        keep = getattr(cfg, "device_metrics", False)
+        cfg.device_metrics = True
+        n2 = None
+        if noise is not None:
+            dev = cfg.device
+            n2 = (torch.as_tensor(noise["act_noise"]).to(dev), torch.as_tensor(noise["u_state"]).to(dev))
+        try:
+            cur = torch.cuda.current_stream()
+            self._stream.wait_stream(cur)
+            with torch.cuda.stream(self._stream):
+                out = self.beh._train(self._start, self.objective, noise=n2)
+            cur.wait_stream(self._stream)
+        finally:
+            cfg.device_metrics = keep
+        K.invalidate_weight_splits()
+        self._start = None
+        return out
 
     # -- one training step ---------------------------------------------------------------
     def __call__(self, data, noise=None):

@@ -173,11 +173,22 @@ class WorldModel(nn.Module):
         return mean_loss, post, aux
 
     def _train(self, data, noise=None):
-        cfg = self._config
+        return self._train_end(self._train_begin(data, noise))
+
+    def _train_begin(self, data, noise=None):
+        """Forward + backward of the world-model step (gradients in the optimizer's buffer, weights
+        untouched).  ``_train_end`` applies the update and builds the metrics; work that only reads
+        the weights may run in between (graphs.TrainStepGraph, pipelined schedule)."""
         data = self.preprocess(data)
         with tools.RequiresGrad(self):
             loss, post, aux = self.loss(data, noise)
-            metrics = self._model_opt(loss, self.parameters())
+            opt_state = self._model_opt.backward(loss)
+        return dict(post=post, aux=aux, opt_state=opt_state)
+
+    def _train_end(self, st):
+        cfg = self._config
+        post, aux = st["post"], st["aux"]
+        metrics = self._model_opt.step(st["opt_state"])
         metrics.update({f"{k}_loss": v.detach() for k, v in aux["losses"].items()})
         metrics["kl_free"] = cfg.kl_free
         metrics["dyn_scale"] = cfg.dyn_scale

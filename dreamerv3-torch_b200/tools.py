@@ -526,6 +526,12 @@ class Optimizer:
 
     # ---- one optimisation step ---------------------------------------------------------
     def __call__(self, loss, params=None, retain_graph=False):
+        return self.step(self.backward(loss, retain_graph=retain_graph))
+
+    def backward(self, loss, retain_graph=False):
+        """First half of a step: zero_grad -> backward (gradients into the flat buffer).  Returns
+        the state ``step`` needs.  Split from ``step`` so that a caller can put work that only
+        READS the parameters between the two (graphs.TrainStepGraph, pipelined schedule)."""
         if loss.dim() != 0:
             raise AssertionError(loss.shape)
         params = self._params
@@ -533,18 +539,7 @@ class Optimizer:
         if not self._flat:
             self._opt.zero_grad(set_to_none=True)
             loss.backward(retain_graph=retain_graph)
-            if self._sync is not None:
-                self._sync(params)
-            norm = nn.utils.clip_grad_norm_(params, self._clip)
-            if self._wd:
-                with torch.no_grad():
-                    for p in params:
-                        p.mul_(1 - self._wd)
-            self._opt.step()
-            K.invalidate_weight_splits()
-            self._opt.zero_grad(set_to_none=True)
-            metrics[f"{self._name}_grad_norm"] = norm.detach()
-            return metrics
+            return dict(metrics=metrics)
         # The flat gradient buffer is zeroed once and armed as the gradient sink: the library's
         # backward Functions accumulate dW / LayerNorm / bias gradients straight into its views
         # (kernels.arm_grad_sink); gradients that still arrive through autograd (torch modules:
@@ -570,6 +565,26 @@ class Optimizer:
                     p.grad = None
                 elif not w:
                     skipped.append(i)
+        return dict(metrics=metrics, skipped=skipped)
+
+    def step(self, state):
+        """Second half: [DP all-reduce] -> clip -> (weight decay) -> Adam; returns the metrics."""
+        params = self._params
+        metrics = state["metrics"]
+        if not self._flat:
+            if self._sync is not None:
+                self._sync(params)
+            norm = nn.utils.clip_grad_norm_(params, self._clip)
+            if self._wd:
+                with torch.no_grad():
+                    for p in params:
+                        p.mul_(1 - self._wd)
+            self._opt.step()
+            K.invalidate_weight_splits()
+            self._opt.zero_grad(set_to_none=True)
+            metrics[f"{self._name}_grad_norm"] = norm.detach()
+            return metrics
+        skipped = state["skipped"]
         # torch.optim.Adam leaves a parameter that received no gradient untouched (no moment
         # decay, no move on stale momentum): keep that by restoring it after the fused update.
         # (The step counter stays global: a parameter that is skipped in some steps gets the

@@ -111,3 +111,53 @@ def test_eager_forwards_between_replays_see_updated_weights(pkg, device):
     with torch.no_grad():
         fresh = _agent(pkg, device)[2].actor(feat).mean
     assert float((fresh - got[0]).abs().max()) > 1e-5
+
+
+def test_pipelined_schedule_matches_sequential(pkg, device):
+    """TrainStepGraph(pipeline=True): the behaviour update of batch t runs concurrently with the
+    world-model forward + backward of batch t+1 (it only reads the world model; Adam follows the
+    join).  Every update sees the inputs it sees in the sequential schedule, so after the same
+    batches and noise (+ flush) all parameters equal those of an agent trained by sequential eager
+    calls; the noise of call r drives the behaviour update of batch r-1."""
+    B, T, K = 6, 10, 6
+    cfg, wm_a, beh_a = _agent(pkg, device)
+    _, wm_b, beh_b = _agent(pkg, device)
+    wm_b.load_state_dict(wm_a.state_dict())
+    beh_b.load_state_dict(beh_a.state_dict())
+    A, S, C, H = cfg.num_actions, cfg.dyn_stoch, cfg.dyn_discrete, cfg.imag_horizon
+    N = B * T
+    graph = pkg.graphs.TrainStepGraph(wm_b, beh_b, warmup=2, pipeline=True)
+    reward = lambda f, s, a: wm_a.heads["reward"](wm_a.dynamics.get_feat(s)).mode()
+    rs = np.random.RandomState(3)
+    gen = torch.Generator().manual_seed(5)
+    prev_beh = dict(act_noise=torch.zeros(H, N, A), u_state=torch.ones(H, N, S, C))
+    m2_prev = None
+    for step in range(K):
+        data = _batch(rs, B, T, A)
+        wm_noise = dict(u_prior=torch.rand(T, B, S, C, generator=gen).clamp_(1e-30, 1.0),
+                        u_post=torch.rand(T, B, S, C, generator=gen).clamp_(1e-30, 1.0))
+        beh_noise = dict(act_noise=torch.randn(H, N, A, generator=gen),
+                         u_state=torch.rand(H, N, S, C, generator=gen).clamp_(1e-30, 1.0))
+        post, _, m1 = wm_a._train(data, noise=(wm_noise["u_prior"].to(device), wm_noise["u_post"].to(device)))
+        _, _, _, _, m2 = beh_a._train(post, reward, noise=(beh_noise["act_noise"].to(device),
+                                                           beh_noise["u_state"].to(device)))
+        out = graph(data, noise=dict(wm_noise, **prev_beh))
+        assert graph.captured == (step >= 2)
+        assert torch.equal(out["post"]["stoch"], post["stoch"]), step
+        for k in ("model_loss", "model_grad_norm", "kl"):
+            assert abs(float(out["wm_metrics"][k]) - float(m1[k])) <= 2e-5 * abs(float(m1[k])) + 1e-7, (step, k)
+        if step == 0:
+            assert not out["beh_metrics"]
+        else:                                   # the behaviour metrics of the PREVIOUS batch
+            for k in ("actor_loss", "value_loss", "actor_grad_norm", "value_grad_norm"):
+                assert abs(float(out["beh_metrics"][k]) - float(m2_prev[k])) <= \
+                    2e-5 * abs(float(m2_prev[k])) + 1e-7, (step, k)
+        prev_beh, m2_prev = beh_noise, m2
+    last = graph.flush(noise=prev_beh)
+    assert last is not None
+    for k in ("actor_loss", "value_loss"):
+        assert abs(float(last[4][k]) - float(m2_prev[k])) <= 2e-5 * abs(float(m2_prev[k])) + 1e-7, k
+    for (k, a), b in zip(wm_a.state_dict().items(), wm_b.state_dict().values()):
+        assert float((a - b).abs().max()) <= 2e-6, k
+    for (k, a), b in zip(beh_a.state_dict().items(), beh_b.state_dict().values()):
+        assert float((a.float() - b.float()).abs().max()) <= 2e-6, k

@@ -109,6 +109,13 @@ __global__ void __launch_bounds__(PO_THREADS, 1) observe_persistent_fwd_kernel(P
     lin_b[u] = i < Hd ? p.ln_in_b[i] : 0.f;
   }
   const float bos = (lane < C) ? p.b_os[(size_t)gE * C + lane] : 0.f;
+  const int init_i = tid < S ? p.init_idx[tid] : 0;
+  float init_h[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int j = tid + u * PO_THREADS;
+    init_h[u] = j < D ? p.init_deter[j] : 0.f;
+  }
 
   unsigned gen = 0;
   for (int t = 0; t < T; ++t) {
@@ -117,20 +124,40 @@ __global__ void __launch_bounds__(PO_THREADS, 1) observe_persistent_fwd_kernel(P
     if (cta < B) {
       const int b = cta;
       const size_t bt = (size_t)b * T + t;
-      const bool first = p.first_eff[bt] != 0.f;
+      // the reset flag, the previous state and the action are fetched TOGETHER (the previous state
+      // through a pointer that is valid either way) and selected afterwards: one L2 round trip
+      // instead of flag -> state
       const int32_t* pidx = t ? p.post_idx + (bt - 1) * S : (p.state_idx ? p.state_idx + (size_t)b * S : nullptr);
       const float* ph = t ? p.deter + (bt - 1) * D : (p.state_deter ? p.state_deter + (size_t)b * D : nullptr);
-      for (int i = tid; i < S; i += PO_THREADS) {
-        const int v = first ? p.init_idx[i] : __ldcg(pidx + i);
-        p.sprev_idx[bt * S + i] = v;
-        sidx[i] = v + i * C;
+      const int32_t* pidx_l = pidx ? pidx : p.init_idx;
+      const float* ph_l = ph ? ph : p.init_deter;
+      const float fflag = __ldcg(p.first_eff + bt);
+      int vi = 0;
+      float vh[4], va = 0.f;
+      if (tid < S) vi = __ldcg(pidx_l + tid);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = tid + u * PO_THREADS;
+        vh[u] = j < D ? __ldcg(ph_l + j) : 0.f;
       }
-      for (int j = tid; j < D; j += PO_THREADS)
-        p.hprev[bt * D + j] = first ? p.init_deter[j] : __ldcg(ph + j);
-      for (int a = tid; a < A; a += PO_THREADS) {
-        const float v = first ? 0.f : p.action[bt * A + a];
-        p.aprev[bt * A + a] = v;
-        sact[a] = v;
+      if (tid < A) va = __ldcg(p.action + bt * A + tid);
+      const bool first = fflag != 0.f || pidx == nullptr;
+      if (tid < S) {
+        const int v = first ? init_i : vi;
+        p.sprev_idx[bt * S + tid] = v;
+        sidx[tid] = v + tid * C;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = tid + u * PO_THREADS;
+        if (j < D) p.hprev[bt * D + j] = first ? init_h[u] : vh[u];
+      }
+      for (int j = tid + 4 * PO_THREADS; j < D; j += PO_THREADS)       // (D > 1024 never reaches here)
+        p.hprev[bt * D + j] = first ? p.init_deter[j] : __ldcg(ph_l + j);
+      if (tid < A) {
+        const float v = first ? 0.f : va;
+        p.aprev[bt * A + tid] = v;
+        sact[tid] = v;
       }
       __syncthreads();
       // (the barrier's acquire has dropped L1: every load below is an L2 round trip, so all S + A of
@@ -398,7 +425,7 @@ int observe_fwd_persistent(const dv3_rssm_dims* d, const dv3_rssm_params* p,
   DV3_CHECK_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
   if (!coop) return 0;
   const int G = sms >= 128 ? 128 : sms;
-  if (S > G || io->B > G) return 0;
+  if (S > G || io->B > G || d->actions > PO_THREADS) return 0;
   PoArgs a{};
   a.B = io->B; a.T = io->T; a.S = S; a.C = C; a.D = D; a.Hd = Hd; a.A = d->actions; a.E = d->embed;
   a.unimix = d->unimix; a.eps = d->ln_eps;

@@ -121,10 +121,15 @@ class TrainStepGraph:
                         imag_action=None, weights=None, beh_metrics={})
         cur = torch.cuda.current_stream()
         sb = self._beh_stream
-        sb.wait_stream(cur)
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        # batch t+1: forward + backward, no update yet.  Enqueued first so that, in data-parallel
+        # runs, the world model's all-reduces are issued ahead of the behaviour's (collectives
+        # execute in issue order); the two branches still start together (the fork event).
+        st = self.wm._train_begin(batch, noise=n1, sync=True)
+        sb.wait_event(fork)
         with torch.cuda.stream(sb):          # batch t: reads the world model, updates actor / critic
             feat, state, action, weights, m2 = self.beh._train(self._start, self.objective, noise=n2)
-        st = self.wm._train_begin(batch, noise=n1)      # batch t+1: forward + backward, no update yet
         cur.wait_stream(sb)
         post, context, m1 = self.wm._train_end(st)      # ... now the world model may change
         self._stash(post)

@@ -175,14 +175,14 @@ class WorldModel(nn.Module):
     def _train(self, data, noise=None):
         return self._train_end(self._train_begin(data, noise))
 
-    def _train_begin(self, data, noise=None):
+    def _train_begin(self, data, noise=None, sync=False):
         """Forward + backward of the world-model step (gradients in the optimizer's buffer, weights
         untouched).  ``_train_end`` applies the update and builds the metrics; work that only reads
         the weights may run in between (graphs.TrainStepGraph, pipelined schedule)."""
         data = self.preprocess(data)
         with tools.RequiresGrad(self):
             loss, post, aux = self.loss(data, noise)
-            opt_state = self._model_opt.backward(loss)
+            opt_state = self._model_opt.backward(loss, sync=sync)
         return dict(post=post, aux=aux, opt_state=opt_state)
 
     def _train_end(self, st):

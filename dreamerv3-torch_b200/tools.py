@@ -528,10 +528,12 @@ class Optimizer:
     def __call__(self, loss, params=None, retain_graph=False):
         return self.step(self.backward(loss, retain_graph=retain_graph))
 
-    def backward(self, loss, retain_graph=False):
+    def backward(self, loss, retain_graph=False, sync=False):
         """First half of a step: zero_grad -> backward (gradients into the flat buffer).  Returns
         the state ``step`` needs.  Split from ``step`` so that a caller can put work that only
-        READS the parameters between the two (graphs.TrainStepGraph, pipelined schedule)."""
+        READS the parameters between the two (graphs.TrainStepGraph, pipelined schedule).
+        ``sync``: issue the data-parallel all-reduce here instead of in ``step`` (collectives run in
+        issue order: the pipelined schedule wants the world model's ahead of the behaviour's)."""
         if loss.dim() != 0:
             raise AssertionError(loss.shape)
         params = self._params
@@ -565,7 +567,12 @@ class Optimizer:
                     p.grad = None
                 elif not w:
                     skipped.append(i)
-        return dict(metrics=metrics, skipped=skipped)
+        synced = False
+        if sync and self._sync is not None:
+            self._sync.flat(self._fg, getattr(self, "_segments", None))
+            K.join_grad_streams()
+            synced = True
+        return dict(metrics=metrics, skipped=skipped, synced=synced)
 
     def step(self, state):
         """Second half: [DP all-reduce] -> clip -> (weight decay) -> Adam; returns the metrics."""
@@ -593,7 +600,7 @@ class Optimizer:
         if skipped:
             pv, mv, vv = self._views(self._fp), self._views(self._fm), self._views(self._fv)
             keep = [(pv[i], pv[i].clone(), mv[i], mv[i].clone(), vv[i], vv[i].clone()) for i in skipped]
-        if self._sync is not None:
+        if self._sync is not None and not state.get("synced"):
             self._sync.flat(self._fg, getattr(self, "_segments", None))
             K.join_grad_streams()
         L_ = K.L

@@ -139,7 +139,7 @@ class TrainStepGraph:
     def flush(self, noise=None):
         """Pipelined schedule: apply the behaviour update of the last batch (eagerly).  Returns its
         (feat, state, action, weights, metrics), or None when nothing is pending."""
-        if not self.pipeline or self._start is None:
+        if not self.pipeline or self._start is None or getattr(self, "_flushed", False):
             return None
         cfg = self.wm._config
         keep = getattr(cfg, "device_metrics", False)
@@ -157,11 +157,14 @@ class TrainStepGraph:
         finally:
             cfg.device_metrics = keep
         K.invalidate_weight_splits()
-        self._start = None
+        self._flushed = True                 # the captured graph would train on this batch again
         return out
 
     # -- one training step ---------------------------------------------------------------
     def __call__(self, data, noise=None):
+        if getattr(self, "_flushed", False):
+            raise K.L.Dv3Error("TrainStepGraph: flush() ended the pipelined schedule; build a new "
+                               "TrainStepGraph to continue training")
         batch = self._stage(data, noise)
         if self._graph is None and self._calls < self.warmup:
             cur = torch.cuda.current_stream()

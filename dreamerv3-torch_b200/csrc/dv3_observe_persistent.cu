@@ -228,6 +228,9 @@ __global__ void __launch_bounds__(PO_THREADS, 1) observe_persistent_fwd_kernel(P
       const bool act = rl < rCn && on > 0;
       const int b = rC0 + rl;
       const size_t bt = (size_t)b * T + t;
+      // the hoisted embed half of z_pre is an input: fetched with the phase's first loads, not after
+      // the dot product (an exposed L2 round trip at the end of the phase)
+      const float pre_e_v = (half == 0 && act && lane < on) ? __ldg(p.pre_e + bt * Hd + o0 + lane) : 0.f;
       if (act) {
         const float* row = p.g_pre + bt * D3;
         float v[3 * DV], hp[DV / 2];
@@ -286,7 +289,7 @@ __global__ void __launch_bounds__(PO_THREADS, 1) observe_persistent_fwd_kernel(P
       __syncthreads();
       if (half == 0 && act && lane < on) {
         const size_t o = bt * Hd + o0 + lane;
-        p.z_pre[o] = acc + xch[rl * 32 + lane] + p.pre_e[o];
+        p.z_pre[o] = acc + xch[rl * 32 + lane] + pre_e_v;
       }
     }
     po_stamp(p, t, 5);

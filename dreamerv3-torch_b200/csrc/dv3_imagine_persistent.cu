@@ -160,30 +160,11 @@ __device__ __forceinline__ float pi_bfly_sum32(float (&a)[32]) {
     for (int i = 0; i < o; ++i) a[i] += a[i + o];
   return a[0];
 }
-__device__ __forceinline__ float pi_max32(const float (&a)[32]) {
-  float m = a[0];
-#pragma unroll
-  for (int i = 1; i < 32; ++i) m = fmaxf(m, a[i]);
-  return m;
-}
 
 __device__ __forceinline__ void pi_store16(float* p, const float* v) {
 #pragma unroll
   for (int i = 0; i < 16; i += 4)
     *reinterpret_cast<float4*>(p + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-}
-__device__ __forceinline__ void pi_store_planes16(float* hi, float* lo, const float* v) {
-#pragma unroll
-  for (int i = 0; i < 16; i += 4) {
-    float4 h, l;
-    h.x = __uint_as_float(__float_as_uint(v[i]) & 0xFFFFE000u);
-    h.y = __uint_as_float(__float_as_uint(v[i + 1]) & 0xFFFFE000u);
-    h.z = __uint_as_float(__float_as_uint(v[i + 2]) & 0xFFFFE000u);
-    h.w = __uint_as_float(__float_as_uint(v[i + 3]) & 0xFFFFE000u);
-    l.x = v[i] - h.x; l.y = v[i + 1] - h.y; l.z = v[i + 2] - h.z; l.w = v[i + 3] - h.w;
-    *reinterpret_cast<float4*>(hi + i) = h;
-    *reinterpret_cast<float4*>(lo + i) = l;
-  }
 }
 
 // The chain of unimix_probs + the supplied-uniform argmax (dv3_common.cuh, dv3_rowwise.cu) for one

@@ -8,12 +8,15 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _agent(pkg, device, seed=0):
+def _agent(pkg, device, seed=0, full=False):
     cfgs = pkg.configs
     torch.manual_seed(seed)
-    cfg = cfgs.make_config("dmc_proprio", device=device, dyn_stoch=8, dyn_discrete=8, dyn_deter=64,
-                           dyn_hidden=64, units=64, imag_horizon=5,
-                           encoder=dict(mlp_units=64, mlp_layers=2), decoder=dict(mlp_units=64, mlp_layers=2))
+    if full:        # configs.yaml defaults: the sizes the benchmark runs
+        cfg = cfgs.make_config("dmc_proprio", device=device)
+    else:
+        cfg = cfgs.make_config("dmc_proprio", device=device, dyn_stoch=8, dyn_discrete=8, dyn_deter=64,
+                               dyn_hidden=64, units=64, imag_horizon=5,
+                               encoder=dict(mlp_units=64, mlp_layers=2), decoder=dict(mlp_units=64, mlp_layers=2))
     wm = pkg.models.WorldModel(cfgs.ObsSpace(cfgs.PROPRIO_SHAPES), None, 0, cfg)
     beh = pkg.models.ImagBehavior(cfg, wm)
     return cfg, wm, beh
@@ -113,15 +116,15 @@ def test_eager_forwards_between_replays_see_updated_weights(pkg, device):
     assert float((fresh - got[0]).abs().max()) > 1e-5
 
 
-def test_pipelined_schedule_matches_sequential(pkg, device):
+@pytest.mark.parametrize("full,B,T,K", [(False, 6, 10, 6), (True, 16, 64, 4)])
+def test_pipelined_schedule_matches_sequential(pkg, device, full, B, T, K):
     """TrainStepGraph(pipeline=True): the behaviour update of batch t runs concurrently with the
     world-model forward + backward of batch t+1 (it only reads the world model; Adam follows the
     join).  Every update sees the inputs it sees in the sequential schedule, so after the same
     batches and noise (+ flush) all parameters equal those of an agent trained by sequential eager
     calls; the noise of call r drives the behaviour update of batch r-1."""
-    B, T, K = 6, 10, 6
-    cfg, wm_a, beh_a = _agent(pkg, device)
-    _, wm_b, beh_b = _agent(pkg, device)
+    cfg, wm_a, beh_a = _agent(pkg, device, full=full)
+    _, wm_b, beh_b = _agent(pkg, device, full=full)
     wm_b.load_state_dict(wm_a.state_dict())
     beh_b.load_state_dict(beh_a.state_dict())
     A, S, C, H = cfg.num_actions, cfg.dyn_stoch, cfg.dyn_discrete, cfg.imag_horizon
@@ -157,7 +160,14 @@ def test_pipelined_schedule_matches_sequential(pkg, device):
     assert last is not None
     for k in ("actor_loss", "value_loss"):
         assert abs(float(last[4][k]) - float(m2_prev[k])) <= 2e-5 * abs(float(m2_prev[k])) + 1e-7, k
-    for (k, a), b in zip(wm_a.state_dict().items(), wm_b.state_dict().values()):
-        assert float((a - b).abs().max()) <= 2e-6, k
-    for (k, a), b in zip(beh_a.state_dict().items(), beh_b.state_dict().values()):
-        assert float((a.float() - b.float()).abs().max()) <= 2e-6, k
+    # small config: everything reproduces to rounding; full size: the split-K parameter-gradient
+    # products add with fp32 atomics (summation order not fixed), and Adam turns a gradient at noise
+    # level into +-lr per step -- the same bound as tests/test_gpu_reference.py, per step taken
+    tol = 2e-6 if not full else K * 2 * 1e-4 + 1e-6
+    frac_tol = 2e-6
+    for sd_a, sd_b in ((wm_a.state_dict(), wm_b.state_dict()), (beh_a.state_dict(), beh_b.state_dict())):
+        for (k, a), b in zip(sd_a.items(), sd_b.values()):
+            d = (a.float() - b.float()).abs()
+            assert float(d.max()) <= tol, k
+            if full and d.numel() > 1000:      # ... and all but a vanishing fraction agree closely
+                assert float((d > frac_tol + 1e-4 * b.float().abs()).float().mean()) < 0.02, k

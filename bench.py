@@ -376,20 +376,31 @@ def run_ours(args):
     value = world * args.steps / (ms / 1e3)
 
     # ---- timed region 2: end to end through the public API with host buffers ------------
-    graph.device_metrics = False             # numpy metrics: one stacked D2H per call
+    # numpy metrics of EVERY step, read through one asynchronous packed D2H per call that the next
+    # call collects (graphs.TrainStepGraph(lazy_metrics=True)); the last step's are drained inside
+    # the timed region
+    graph.device_metrics = False
+    graph.lazy_metrics = not args.eager_metrics
     d2h = 0
     for _ in range(2):
         graph(pinned)
+    graph.drain()
     stage("e2e warm calls done")
     barrier()
     t0 = time.perf_counter()
+    reads = 0
     for _ in range(args.steps):
         out = graph(pinned)
-        if not d2h:
-            d2h = sum(np.asarray(v).nbytes for v in list(out["wm_metrics"].values()) +
-                      list(out["beh_metrics"].values()) if isinstance(v, np.ndarray))
+        if out["wm_metrics"] is not None:
+            reads += 1
+            if not d2h:
+                d2h = sum(np.asarray(v).nbytes for v in list(out["wm_metrics"].values()) +
+                          list(out["beh_metrics"].values()) if isinstance(v, np.ndarray))
+    if graph.lazy_metrics and graph.drain() is not None:
+        reads += 1
     barrier()
     e2e_s = time.perf_counter() - t0
+    assert reads == args.steps, (reads, args.steps)      # one host read of the results per step
     t_e = torch.tensor([e2e_s], device=device)
     if world > 1:
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
@@ -568,6 +579,9 @@ def main():
     ap.add_argument("--suite", default="dmc_proprio", choices=["dmc_proprio", "dmc_vision", "atari100k"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run every step eagerly (debugging)")
+    ap.add_argument("--eager-metrics", action="store_true",
+                    help="e2e: wait for each call's own metrics (one synchronous stacked D2H per call) "
+                         "instead of collecting them one call late")
     ap.add_argument("--schedule", default="pipelined", choices=["sequential", "pipelined"],
                     help="pipelined (default): the behaviour update of batch t overlaps the world-model "
                          "forward + backward of batch t+1 (graphs.TrainStepGraph(pipeline=True)): the "

@@ -29,9 +29,16 @@ from . import tools
 
 class TrainStepGraph:
     def __init__(self, world_model, behavior, objective=None, warmup=3, device_metrics=False,
-                 pipeline=False):
+                 pipeline=False, lazy_metrics=False):
         self.wm, self.beh = world_model, behavior
         self.pipeline = bool(pipeline)
+        # lazy_metrics: host metrics come back ONE CALL LATE (None from the first call, drain() for
+        # the last): the call packs its metrics on the device, starts one asynchronous copy into
+        # pinned memory and returns without waiting for the step, so the host prepares the next call
+        # while the GPU still runs this one
+        self.lazy_metrics = bool(lazy_metrics)
+        self._lazy_pending = None
+        self._pin = [None, None]
         self._start = None                   # static start states of the pending behaviour update
         self._pending_noise = None
         if objective is None:
@@ -195,9 +202,53 @@ class TrainStepGraph:
         if self.device_metrics:
             return out
         out = dict(out)
+        if self.lazy_metrics:
+            out["wm_metrics"], out["beh_metrics"] = self._lazy(out["wm_metrics"], out["beh_metrics"])
+            return out
         out["wm_metrics"] = tools.to_host(out["wm_metrics"])
         out["beh_metrics"] = tools.to_host(out["beh_metrics"])
         return out
+
+    # -- metrics one call late -----------------------------------------------------------------
+    def _lazy(self, m1, m2):
+        groups = (m1 or {}, m2 or {})
+        layout, parts = [], []
+        for gi, grp in enumerate(groups):
+            for k, v in grp.items():
+                if torch.is_tensor(v):
+                    layout.append((gi, k, tuple(v.shape), v.numel()))
+                    parts.append(v.detach().reshape(-1).float())
+                else:
+                    layout.append((gi, k, None, v))
+        n = sum(p.numel() for p in parts)
+        slot = self._calls & 1
+        if self._pin[slot] is None or self._pin[slot].numel() < n:
+            self._pin[slot] = torch.empty(max(n, 1), dtype=torch.float32).pin_memory()
+        ev = torch.cuda.Event()
+        if parts:
+            self._pin[slot][:n].copy_(torch.cat(parts), non_blocking=True)
+        ev.record()
+        prev, self._lazy_pending = self._lazy_pending, (slot, ev, layout)
+        return self._unpack(prev) if prev is not None else (None, None)
+
+    def _unpack(self, pending):
+        import numpy as np
+        slot, ev, layout = pending
+        ev.synchronize()
+        host = self._pin[slot].numpy()
+        out, pos = ({}, {}), 0
+        for gi, k, shape, n in layout:
+            if shape is None:
+                out[gi][k] = n
+            else:
+                out[gi][k] = np.array(host[pos:pos + n]).reshape(shape)
+                pos += n
+        return out
+
+    def drain(self):
+        """lazy_metrics: the (wm_metrics, beh_metrics) of the last call, or None."""
+        prev, self._lazy_pending = self._lazy_pending, None
+        return self._unpack(prev) if prev is not None else None
 
     @property
     def captured(self):

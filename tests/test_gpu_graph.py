@@ -171,3 +171,43 @@ def test_pipelined_schedule_matches_sequential(pkg, device, full, B, T, K):
             assert float(d.max()) <= tol, k
             if full and d.numel() > 1000:      # ... and all but a vanishing fraction agree closely
                 assert float((d > frac_tol + 1e-4 * b.float().abs()).float().mean()) < 0.02, k
+
+
+def test_lazy_metrics_are_the_previous_calls(pkg, device):
+    """TrainStepGraph(lazy_metrics=True): host metrics come back one call late (None first, drain()
+    last) and equal the metrics an eager-reading twin returns for the same call."""
+    B, T = 6, 10
+    cfg, wm_a, beh_a = _agent(pkg, device)
+    _, wm_b, beh_b = _agent(pkg, device)
+    wm_b.load_state_dict(wm_a.state_dict())
+    beh_b.load_state_dict(beh_a.state_dict())
+    A, S, C, H = cfg.num_actions, cfg.dyn_stoch, cfg.dyn_discrete, cfg.imag_horizon
+    N = B * T
+    g_a = pkg.graphs.TrainStepGraph(wm_a, beh_a, warmup=2)
+    g_b = pkg.graphs.TrainStepGraph(wm_b, beh_b, warmup=2, lazy_metrics=True)
+    rs = np.random.RandomState(3)
+    gen = torch.Generator().manual_seed(5)
+    prev = None
+    for step in range(5):
+        data = _batch(rs, B, T, A)
+        noise = dict(u_prior=torch.rand(T, B, S, C, generator=gen).clamp_(1e-30, 1.0),
+                     u_post=torch.rand(T, B, S, C, generator=gen).clamp_(1e-30, 1.0),
+                     act_noise=torch.randn(H, N, A, generator=gen),
+                     u_state=torch.rand(H, N, S, C, generator=gen).clamp_(1e-30, 1.0))
+        ref = g_a(data, noise=noise)
+        out = g_b(data, noise=noise)
+        if step == 0:
+            assert out["wm_metrics"] is None and out["beh_metrics"] is None
+        else:
+            for grp in ("wm_metrics", "beh_metrics"):
+                assert set(out[grp]) == set(prev[grp])
+                for k, v in prev[grp].items():
+                    np.testing.assert_allclose(np.asarray(out[grp][k], dtype=np.float64),
+                                               np.asarray(v, dtype=np.float64), rtol=2e-5, atol=1e-7, err_msg=k)
+        prev = ref
+    last = g_b.drain()
+    assert last is not None and g_b.drain() is None
+    for gi, grp in enumerate(("wm_metrics", "beh_metrics")):
+        for k, v in prev[grp].items():
+            np.testing.assert_allclose(np.asarray(last[gi][k], dtype=np.float64), np.asarray(v, dtype=np.float64),
+                                       rtol=2e-5, atol=1e-7, err_msg=k)

@@ -123,7 +123,7 @@ class ImagineBwdIO(C.Structure):
         ("d_mean_raw", "f"), ("d_std_raw", "f"), ("d_x_pre", "f"), ("d_x_ln", "f"),
         ("d_g_pre", "f"), ("d_g_ln", "f"), ("d_y_pre", "f"), ("d_y_ln", "f"), ("d_logit", "f"),
         ("d_start_stoch", "f"), ("d_start_deter", "f"),
-        ("workspace", "v"), ("workspace_bytes", "sz")])
+        ("workspace", "v"), ("workspace_bytes", "sz"), ("g_state_ld", "i32")])
 
 
 STRUCTS = {"dv3_tc_operand": TcOperand, "dv3_rssm_dims": RssmDims, "dv3_rssm_params": RssmParams,

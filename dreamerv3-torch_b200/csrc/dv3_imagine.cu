@@ -506,22 +506,27 @@ extern "C" int dv3_imagine_bwd(const dv3_rssm_dims* d, const dv3_rssm_params* p,
   // the last action feeds nothing downstream
   DV3_TRY(actor_bwd(H - 1, nullptr, 0, 0));
 
+  // upstream state gradients: packed, or the column ranges of one [H,N,pitch] buffer
+  DV3_REQUIRE(io->g_state_ld == 0 || (io->g_state_ld >= SC && io->g_state_ld % 4 == 0), DV3_ERR_BAD_SHAPE,
+              "imagine_bwd: g_state_ld=%d", io->g_state_ld);
+  const size_t lgs = io->g_state_ld ? (size_t)io->g_state_ld : (size_t)SC;
+  const size_t lgd = io->g_state_ld ? (size_t)io->g_state_ld : (size_t)D;
   const float* ds_rec = nullptr;  // [N, SC+A] view into dsa once it is valid
   const float* dh_rec = nullptr;  // h columns of dxh
   for (int k = H - 2; k >= 0; --k) {
     const size_t on = (size_t)(k + 1) * N;  // row offset of state k+1
-    const float* gs = io->g_stoch ? io->g_stoch + on * SC : nullptr;
+    const float* gs = io->g_stoch ? io->g_stoch + on * lgs : nullptr;
     const float* gl = io->g_logit ? io->g_logit + on * SC : nullptr;
     float* dlog = io->d_logit + on * SC;
-    DV3_TRY(onehot_st_bwd(io->logit + on * SC, SC, gs, SC, ds_rec, SC + A, gl, SC, d->unimix, N, S,
+    DV3_TRY(onehot_st_bwd(io->logit + on * SC, SC, gs, (int)lgs, ds_rec, SC + A, gl, SC, d->unimix, N, S,
                           C, dlog, SC, st, w.dlsp));
     DV3_TRY(blin(w.ims, dlog, SC, SC, w.dlsp, nullptr, 0, w.d_y, Hd));
     const size_t ok = (size_t)k * N;
     DV3_TRY(ln_silu_bwd(io->y_pre + ok * Hd, Hd, p->ln_out_g, p->ln_out_b, d->ln_eps, w.d_y, Hd, N,
                         Hd, io->d_y_pre + ok * Hd, Hd, io->d_y_ln + ok * Hd, Hd, st, w.dysp));
     DV3_TRY(blin(w.out, io->d_y_pre + ok * Hd, Hd, Hd, w.dysp, nullptr, 0, w.dh_y, D));
-    const float* dh_in[4] = {w.dh_y, io->g_deter ? io->g_deter + on * D : nullptr, dh_rec, nullptr};
-    const int ld_in[4] = {D, D, Hd + D, 0};
+    const float* dh_in[4] = {w.dh_y, io->g_deter ? io->g_deter + on * lgd : nullptr, dh_rec, nullptr};
+    const int ld_in[4] = {D, (int)lgd, Hd + D, 0};
     DV3_TRY(gru_gates_bwd(io->g_pre + ok * 3 * D, 3 * D, p->ln_gru_g, p->ln_gru_b, d->ln_eps,
                           io->feat + ok * F + SC, F, dh_in, ld_in, N, D, io->d_g_pre + ok * 3 * D,
                           3 * D, io->d_g_ln + ok * 3 * D, 3 * D, w.dxh_add + Hd, Hd + D, st, w.dgsp));
@@ -537,12 +542,12 @@ extern "C" int dv3_imagine_bwd(const dv3_rssm_dims* d, const dv3_rssm_params* p,
   }
   if (io->d_start_stoch) {
     add2_rows_kernel<<<(int)(((long long)N * SC + 255) / 256), 256, 0, st>>>(
-        io->g_stoch, SC, ds_rec, SC + A, N, SC, io->d_start_stoch, SC);
+        io->g_stoch, (int)lgs, ds_rec, SC + A, N, SC, io->d_start_stoch, SC);
     DV3_CHECK_LAUNCH("add2_rows_kernel");
   }
   if (io->d_start_deter) {
     add2_rows_kernel<<<(int)(((long long)N * D + 255) / 256), 256, 0, st>>>(
-        io->g_deter, D, dh_rec, Hd + D, N, D, io->d_start_deter, D);
+        io->g_deter, (int)lgd, dh_rec, Hd + D, N, D, io->d_start_deter, D);
     DV3_CHECK_LAUNCH("add2_rows_kernel");
   }
   return 0;

@@ -1055,11 +1055,12 @@ class _Imagine(torch.autograd.Function):
         pst, keep_r = pack_rssm(rssm_params, rpl)
         act_struct, keep_a = spec.pack(actor_params)
         f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
-        g_stoch = g_deter = None
+        # the gradient of the feature buffer is handed over as it is: its two column ranges are the
+        # gradients of stoch and deter (row pitch S*C + D), no split copies of 94 MB
+        g_state_ld = 0
         if g_feat is not None:
-            g_feat = _f32(g_feat)
-            g_stoch = g_feat[..., :SC].contiguous()
-            g_deter = g_feat[..., SC:].contiguous()
+            g_feat = _c(_f32(g_feat))
+            g_state_ld = SC + D
         o = dict(d_mean_raw=f(H, N, A), d_x_pre=f(H, N, Hd), d_x_ln=f(H, N, Hd),
                  d_g_pre=f(H, N, 3 * D), d_g_ln=f(H, N, 3 * D), d_y_pre=f(H, N, Hd),
                  d_y_ln=f(H, N, Hd), d_logit=f(H, N, SC))
@@ -1069,9 +1070,13 @@ class _Imagine(torch.autograd.Function):
                  dev)
         io = L.fill(L.ImagineBwdIO(), N=N, H=H, logit=logit, feat=feat, x_pre=x_pre, g_pre=g_pre,
                     y_pre=y_pre, a_mean_raw=a_mean_raw, a_std_raw=a_std_raw, act_noise=act_noise,
-                    g_stoch=g_stoch, g_deter=g_deter, g_logit=_f32(g_logit),
+                    g_stoch=None, g_deter=None, g_logit=_f32(g_logit),
                     g_action=_f32(g_action), d_start_stoch=None, d_start_deter=None,
-                    workspace=ws, workspace_bytes=ws.numel(), **o)
+                    workspace=ws, workspace_bytes=ws.numel(), g_state_ld=g_state_ld, **o)
+        if g_feat is not None:
+            fp = C.POINTER(C.c_float)
+            io.g_stoch = C.cast(C.c_void_p(g_feat.data_ptr()), fp)
+            io.g_deter = C.cast(C.c_void_p(g_feat.data_ptr() + 4 * SC), fp)
         L.check(L.lib().dv3_imagine_bwd(C.byref(d), C.byref(pst), C.byref(act_struct),
                                         C.byref(io), L.stream_ptr()), "imagine_bwd")
         if any(ctx.needs_input_grad[9:9 + 17]):

@@ -302,6 +302,10 @@ typedef struct {
   float* d_start_stoch;            /* [N,S*C] grad wrt start stoch */
   float* d_start_deter;            /* [N,D]   */
   void* workspace; size_t workspace_bytes;
+  int32_t g_state_ld;              /* row pitch (floats) of g_stoch / g_deter; 0 = packed (S*C / D).
+                                    * With S*C+D the two are the column ranges of ONE [H,N,S*C+D]
+                                    * gradient of the feature buffer (g_deter = g_stoch + S*C): no
+                                    * split copies of the upstream gradient */
 } dv3_imagine_bwd_io;
 
 size_t dv3_imagine_bwd_workspace_bytes(const dv3_rssm_dims* d, const dv3_actor* a, int32_t N, int32_t H);

@@ -1058,9 +1058,13 @@ class _Imagine(torch.autograd.Function):
         # the gradient of the feature buffer is handed over as it is: its two column ranges are the
         # gradients of stoch and deter (row pitch S*C + D), no split copies of 94 MB
         g_state_ld = 0
+        g_packed = None
         if g_feat is not None:
             g_feat = _c(_f32(g_feat))
-            g_state_ld = SC + D
+            if os.environ.get("DV3_BWD_PACKED_G") == "1":      # the ABI's packed form (tests)
+                g_packed = (g_feat[..., :SC].contiguous(), g_feat[..., SC:].contiguous())
+            else:
+                g_state_ld = SC + D
         o = dict(d_mean_raw=f(H, N, A), d_x_pre=f(H, N, Hd), d_x_ln=f(H, N, Hd),
                  d_g_pre=f(H, N, 3 * D), d_g_ln=f(H, N, 3 * D), d_y_pre=f(H, N, Hd),
                  d_y_ln=f(H, N, Hd), d_logit=f(H, N, SC))
@@ -1073,7 +1077,9 @@ class _Imagine(torch.autograd.Function):
                     g_stoch=None, g_deter=None, g_logit=_f32(g_logit),
                     g_action=_f32(g_action), d_start_stoch=None, d_start_deter=None,
                     workspace=ws, workspace_bytes=ws.numel(), g_state_ld=g_state_ld, **o)
-        if g_feat is not None:
+        if g_packed is not None:
+            io.g_stoch, io.g_deter = L.fptr(g_packed[0]), L.fptr(g_packed[1])
+        elif g_feat is not None:
             fp = C.POINTER(C.c_float)
             io.g_stoch = C.cast(C.c_void_p(g_feat.data_ptr()), fp)
             io.g_deter = C.cast(C.c_void_p(g_feat.data_ptr() + 4 * SC), fp)

@@ -88,6 +88,16 @@ def test_imagine_persistent_kernel(pkg, device, config, N, H, knob):
     _assert(pc.imagine_case(pkg, device, config=config, N=N, H=H))
 
 
+def test_imagine_bwd_packed_and_strided_state_gradients(pkg, device, monkeypatch):
+    """dv3_imagine_bwd takes the upstream state gradients packed ([H,N,S*C] and [H,N,D]) or as the
+    two column ranges of one feature-gradient buffer (g_state_ld = S*C + D, what the autograd
+    wrapper passes): same oracle, same bar, both forms."""
+    monkeypatch.setenv("DV3_BWD_PACKED_G", "1")
+    _assert(pc.imagine_case(pkg, device, config="dmc_proprio", N=256, H=6))
+    monkeypatch.delenv("DV3_BWD_PACKED_G")
+    _assert(pc.imagine_case(pkg, device, config="dmc_proprio", N=256, H=6))
+
+
 def test_policy_walk_public_methods(pkg, device):
     """Dreamer._policy (dreamer.py:117-190) through RSSM.obs_step(None, None, ...) / obs_step /
     img_step / get_feat / actor(feat): the acting path's public-method surface."""

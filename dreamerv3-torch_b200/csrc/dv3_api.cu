@@ -38,10 +38,13 @@ const char* env_cached(const char* name, EnvSlot& slot) {
   return slot.has ? slot.val : nullptr;
 }
 
-bool pdl_enabled() {
+// 0 = off (default), 1 = every launch_pdl() launch, 2 = only launches with <= 64 KB of dynamic shared
+// memory (the row kernels: resident early they do not take an SM away from a 200 KB GEMM CTA)
+int pdl_mode() {
   const char* e = DV3_ENV("DV3_PDL");
-  return e && e[0] == '1';             // measured: 16.76 ms/step with it, 16.33 without -> off
+  return (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0;
 }
+bool pdl_enabled() { return pdl_mode() == 1; }   // measured: 16.76 ms/step with it, 16.33 without -> off
 
 int sm_count() {
   static int sms[64] = {0};

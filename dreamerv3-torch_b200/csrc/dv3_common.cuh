@@ -62,6 +62,7 @@ __device__ __forceinline__ void pdl_launch_dependents() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 bool pdl_enabled();
+int pdl_mode();
 
 // ---- process-level caches ------------------------------------------------------------------
 // Environment knobs are read once and cached; dv3_reload_env() (tests, A/B runs) drops the cache.
@@ -98,7 +99,8 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
   cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  const int pm = pdl_mode();
+  at[0].val.programmaticStreamSerializationAllowed = (pm == 1 || (pm == 2 && smem <= 64 * 1024)) ? 1 : 0;
   cfg.attrs = at;
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
